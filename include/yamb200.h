@@ -1,0 +1,172 @@
+/*
+ * yamb200.h — C ABI of libyamb200.so, the B200 (sm_100a) backend for the per-pixel hot path of
+ * GerryDoesStuff/YamImageProcessor (preprocessing -> segmentation -> extraction).
+ *
+ * The reference is pure Python; its "FFI" for this path is the set of cv2 / skimage calls made
+ * by its step functions.  Each entry point below replaces one of those call sites (cited as
+ * file:line relative to the reference checkout) and is bound from Python with ctypes
+ * (yamimageprocessor_b200/_lib.py; the reference-side stub is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C types only; no exceptions or aborts cross this boundary.  Every function returns
+ *    YAM_OK (0) or a negative YAM_E* code; yam_last_error() returns the thread-local message.
+ *  - images are dense row-major planes; a call processes a stack of `n` frames laid out
+ *    back-to-back (n, h, w[, 3]).  The reference processes stacks plane by plane
+ *    (processing/pipeline_manager.py:475-492), so every statistic (min/max, histogram, Otsu
+ *    threshold, CLAHE tiles, labels) is per frame.
+ *  - all `src`/`dst`/`labels`... pointers are DEVICE pointers on the context's GPU, 16-byte aligned.
+ *    Work is enqueued on the context's stream; functions with host out-parameters synchronise
+ *    that stream before returning.  A context is not re-entrant; use one per host thread.
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef YAMB200_H
+#define YAMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YAM_ABI_VERSION 1
+
+/* error codes */
+#define YAM_OK 0
+#define YAM_EINVAL (-1)   /* bad argument (unsupported dtype / size / parameter) */
+#define YAM_ECUDA (-2)    /* CUDA runtime error; message carries cudaGetErrorString */
+#define YAM_ENOMEM (-3)   /* device scratch allocation failed */
+#define YAM_ENODEV (-4)   /* no usable sm_100 device */
+
+/* dtype codes */
+#define YAM_U8 0
+#define YAM_U16 1
+#define YAM_F32 2
+#define YAM_I32 3
+
+/* border modes (cv2 names) */
+#define YAM_BORDER_REFLECT101 0
+#define YAM_BORDER_REPLICATE 1
+
+/* morphology */
+#define YAM_MORPH_ERODE 0
+#define YAM_MORPH_DILATE 1
+#define YAM_MORPH_OPEN 2
+#define YAM_MORPH_CLOSE 3
+#define YAM_SHAPE_RECT 0
+#define YAM_SHAPE_ELLIPSE 1
+#define YAM_SHAPE_CROSS 2
+
+typedef struct yam_ctx yam_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int yam_abi_version(void);
+const char* yam_last_error(void);
+/* number of visible CUDA devices, or a negative error */
+int yam_device_count(void);
+int yam_ctx_create(int device, yam_ctx** out);
+int yam_ctx_destroy(yam_ctx* ctx);
+/* stream: a cudaStream_t (NULL = the context's own non-blocking stream) */
+int yam_ctx_set_stream(yam_ctx* ctx, void* stream);
+int yam_ctx_synchronize(yam_ctx* ctx);
+/* counts kernel launches issued through this context since the last reset (bench "gpu_launches") */
+int64_t yam_ctx_launch_count(yam_ctx* ctx, int reset);
+/* raw device memory + copies for hosts that do not bring their own allocator */
+int yam_malloc(yam_ctx* ctx, int64_t bytes, void** out);
+int yam_free(yam_ctx* ctx, void* ptr);
+int yam_memcpy_h2d(yam_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int yam_memcpy_d2h(yam_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* ---- host-only helpers (no GPU needed; used by the CPU test-suite) ------------------------- */
+/* cv2.getGaussianKernel(ksize, sigma) in double; sigma<=0 => 0.3*((k-1)*0.5-1)+0.8 / small tables */
+int yam_gaussian_taps_f64(int ksize, double sigma, double* out);
+/* cv2 fixed-point taps (bits = 8 | 16), edge->centre error diffusion */
+int yam_gaussian_taps_fixed(int ksize, double sigma, int bits, int64_t* out);
+/* cv2.getStructuringElement(shape,(k,k)) as k*k bytes of 0/1 */
+int yam_structuring_element(int shape, int ksize, uint8_t* out);
+/* cv2 Otsu recurrence on a histogram of `bins` 64-bit counts (bit-exact incl. >= 2^31 px) */
+int yam_otsu_from_hist(const uint64_t* hist, int bins, int* out_threshold);
+
+/* ---- K1 colour -> gray: cv2.cvtColor(BGR2GRAY) --------------------------------------------
+ * replaces modules/preprocessing.py:54, core/preprocessing.py:56, core/segmentation.py:48,
+ * core/extraction.py:47.   src (n,h,w,3) interleaved BGR -> dst (n,h,w); dtype U8|U16|F32. */
+int yam_bgr2gray(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype);
+
+/* ---- K2 elementwise --------------------------------------------------------------------------
+ * yam_minmax: per-frame min and max -> out_dev[2*n] doubles on device (and host if out_host). */
+int yam_minmax(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
+               double* out_dev, double* out_host);
+/* cv2.normalize(src,None,alpha,beta,NORM_MINMAX) — modules/preprocessing.py:123. dtype kept. */
+int yam_normalize_minmax(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+                         int dtype, double alpha, double beta);
+/* cv2.convertScaleAbs — modules/preprocessing.py:78, core/segmentation.py:52. dst is U8. */
+int yam_convert_scale_abs(yam_ctx* ctx, const void* src, void* dst, int64_t count, int dtype,
+                          double alpha, double beta);
+/* cv2.LUT(u8, table[256]) — modules/preprocessing.py:102 (Gamma). table is a HOST pointer. */
+int yam_lut_u8(yam_ctx* ctx, const void* src, void* dst, int64_t count, const uint8_t* table_host);
+/* cv2.threshold(src,t,maxval,THRESH_BINARY) — core/segmentation.py:142, core/preprocessing.py */
+int yam_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t count, int dtype,
+                  double thresh, double maxval);
+
+/* ---- K3/K5 separable filters ---------------------------------------------------------------
+ * cv2.GaussianBlur(src,(k,k),sigma) — modules/preprocessing.py:145,170; core/preprocessing.py:86.
+ * U8/U16: cv2's fixed-point path, bit-exact. F32: cv2 4.13 vector-path summation order. */
+int yam_gaussian(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+                 int dtype, int ksize, double sigma, int border);
+/* cv2.blur(src,(k,k)) odd k, BORDER_REFLECT_101 (absent from the reference; north_star op) */
+int yam_box(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+            int ksize);
+/* cv2.medianBlur(src,k) k in {3,5} — modules/preprocessing.py:147. border REPLICATE */
+int yam_median(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+               int dtype, int ksize);
+
+/* ---- K9 adaptive threshold -----------------------------------------------------------------
+ * cv2.adaptiveThreshold(src,255,GAUSSIAN_C,THRESH_BINARY,block,C) — core/segmentation.py:93.
+ * src U8 (reference semantics) or U16 (extension: same formula, mean saturated to u16); dst U8. */
+int yam_adaptive_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h,
+                           int64_t w, int dtype, int block_size, double C);
+
+/* ---- K6 morphology -------------------------------------------------------------------------
+ * cv2.erode/dilate/morphologyEx with getStructuringElement(shape,(k,k)), `iterations` —
+ * core/segmentation.py:264-314, :102-103. border = identity element. dtype U8|U16. */
+int yam_morph(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+              int op, int shape, int ksize, int iterations);
+/* open(k,it) followed by close(k,it), rectangular SE, fused in one pass (segmentation config) */
+int yam_morph_open_close(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+                         int dtype, int ksize, int iterations);
+
+/* ---- K7/K8 histogram family ----------------------------------------------------------------
+ * per-frame histogram: hist_dev[n][bins] of uint64, bins = 256 (U8) | 65536 (U16) */
+int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
+                  uint64_t* hist_dev);
+/* Otsu threshold per frame from src (cv2.threshold(...THRESH_OTSU) — core/segmentation.py:147,
+ * core/extraction.py:59,72): thresholds to thresh_dev[n] (int32, device) and thresh_host[n]
+ * (optional), then dst = src > t ? maxval : 0 in the source dtype if dst != NULL. */
+int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+                       int dtype, double maxval, int32_t* thresh_dev, int32_t* thresh_host);
+/* cv2.equalizeHist — core/preprocessing.py:76. U8 only, like the reference. */
+int yam_equalize_hist(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w);
+/* cv2.createCLAHE(clip,(tiles_x,tiles_y)).apply (absent from the reference; north_star op) */
+int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+              double clip_limit, int tiles_x, int tiles_y);
+
+/* ---- K10 connected components --------------------------------------------------------------
+ * 8-connectivity, background 0, labels 1..N per frame numbered in raster order of each
+ * component's first pixel (skimage.measure.label order — core/extraction.py:60,73; same partition
+ * as cv2.connectedComponents — core/segmentation.py:108).  mask U8 (non-zero = foreground),
+ * labels I32.  counts_dev[n] int32 on device (optional), counts_host[n] optional. */
+int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
+                  int32_t* counts_dev, int32_t* counts_host);
+
+/* ---- K11 region properties -----------------------------------------------------------------
+ * skimage.measure.regionprops restated (core/extraction.py:61,74): for a single labelled frame
+ * with labels 1..n_labels writes, per label (row i = label i+1), 8 int64 accumulators to
+ * props_dev[n_labels][8]: area, sum_row, sum_col, sum_intensity, min_row, min_col, max_row+1,
+ * max_col+1.  intensity may be NULL (sum_intensity = 0); intensity dtype U8|U16. */
+#define YAM_PROPS_STRIDE 8
+int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype,
+                     int64_t h, int64_t w, int64_t n_labels, int64_t* props_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YAMB200_H */

@@ -1,0 +1,418 @@
+"""Device-level operator API over ``libyamb200.so``.
+
+``Backend`` owns one ``yam_ctx`` on one GPU.  Operators take and return
+``torch`` CUDA tensors (used only as device-memory handles; all arithmetic is in
+the hand-written sm_100a kernels) shaped ``(h, w)`` or ``(n, h, w)`` for a stack
+of frames (``(..., 3)`` for BGR input of ``bgr2gray``).  Everything is enqueued
+on torch's current CUDA stream, so operators chain without host round trips.
+
+``to_device`` / ``to_host`` move NumPy arrays through pinned staging buffers.
+There is no CPU implementation behind any of these calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (
+    BORDER_REFLECT101,
+    BORDER_REPLICATE,
+    MORPH_CLOSE,
+    MORPH_DILATE,
+    MORPH_ERODE,
+    MORPH_OPEN,
+    PROPS_STRIDE,
+    SHAPE_CROSS,
+    SHAPE_ELLIPSE,
+    SHAPE_RECT,
+    YAM_F32,
+    YAM_I32,
+    YAM_U8,
+    YAM_U16,
+    BackendUnavailable,
+    YamError,
+)
+
+_SHAPES = {"rectangular": SHAPE_RECT, "elliptical": SHAPE_ELLIPSE, "cross": SHAPE_CROSS}
+
+
+def _torch():
+    import torch  # deferred: importing the package must not require CUDA
+
+    return torch
+
+
+def _dtype_code(t) -> int:
+    torch = _torch()
+    table = {torch.uint8: YAM_U8, torch.uint16: YAM_U16, torch.float32: YAM_F32, torch.int32: YAM_I32}
+    try:
+        return table[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected uint8, uint16, float32 or int32") from None
+
+
+def shape_code(kernel_shape: str) -> int:
+    """core/segmentation.py:265-274: unknown names fall back to rectangular."""
+    return _SHAPES.get(str(kernel_shape).lower(), SHAPE_RECT)
+
+
+class Backend:
+    """One libyamb200 context bound to one CUDA device."""
+
+    def __init__(self, device: int = 0) -> None:
+        torch = _torch()
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise BackendUnavailable(
+                "no CUDA device visible; yamimageprocessor_b200 runs on B200 only and has no CPU fallback"
+            )
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        handle = C.c_void_p()
+        _lib.check("yam_ctx_create", self.lib.yam_ctx_create(self.device_index, C.byref(handle)))
+        self._ctx = handle
+        self._pinned: Dict[Tuple[str, int], object] = {}
+        self._lock = threading.RLock()
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self.lib.yam_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name: str, *args) -> None:
+        torch = _torch()
+        with self._lock:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check("yam_ctx_set_stream", self.lib.yam_ctx_set_stream(self._ctx, C.c_void_p(stream)))
+            _lib.check(name, getattr(self.lib, name)(self._ctx, *args))
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.yam_ctx_launch_count(self._ctx, 1 if reset else 0))
+
+    def synchronize(self) -> None:
+        _torch().cuda.synchronize(self.device)
+
+    def _check(self, t, *, ndim=(2, 3), dtypes: Optional[Sequence] = None, name="image"):
+        torch = _torch()
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise TypeError(f"{name} must be a CUDA tensor on {self.device}")
+        if t.dim() not in ndim:
+            raise ValueError(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
+        if dtypes is not None and t.dtype not in dtypes:
+            raise TypeError(f"{name} dtype {t.dtype} not supported (expected one of {list(dtypes)})")
+        if t.numel() == 0:
+            raise ValueError(f"{name} is empty")
+        return t.contiguous()
+
+    @staticmethod
+    def _nhw(t) -> Tuple[int, int, int]:
+        if t.dim() == 2:
+            return 1, int(t.shape[0]), int(t.shape[1])
+        return int(t.shape[0]), int(t.shape[1]), int(t.shape[2])
+
+    @staticmethod
+    def _p(t) -> C.c_void_p:
+        return C.c_void_p(t.data_ptr())
+
+    # ------------------------------------------------------------------ host <-> device
+    def _staging(self, kind: str, nbytes: int):
+        torch = _torch()
+        key = (kind, self.device_index)
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self._pinned[key] = buf
+        return buf
+
+    _NP2T = None
+
+    @classmethod
+    def _np2t(cls):
+        if cls._NP2T is None:
+            torch = _torch()
+            cls._NP2T = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
+                         np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
+                         np.dtype(np.int64): torch.int64}
+        return cls._NP2T
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """A NumPy array in page-locked memory (inputs placed here upload without a staging copy)."""
+        torch = _torch()
+        t = torch.empty(tuple(shape), dtype=self._np2t()[np.dtype(dtype)], pin_memory=True)
+        return t.numpy()
+
+    def to_device(self, array: np.ndarray):
+        """NumPy -> CUDA tensor, async on the current stream.
+
+        Page-locked inputs (``pinned_empty``) are copied directly; pageable inputs go through a
+        pinned staging buffer.
+        """
+        torch = _torch()
+        a = np.ascontiguousarray(array)
+        if a.dtype not in self._np2t() or a.dtype == np.int64:
+            raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16, float32 or int32")
+        out = torch.empty(a.shape, dtype=self._np2t()[a.dtype], device=self.device)
+        if a.size == 0:
+            return out
+        src = torch.from_numpy(a)
+        if src.is_pinned():
+            out.copy_(src, non_blocking=True)
+            # keep the host array alive until the copy has been consumed
+            out._yam_host_ref = a  # type: ignore[attr-defined]
+            return out
+        nbytes = a.nbytes
+        stage = self._staging("h2d", nbytes)
+        torch.cuda.current_stream(self.device).synchronize()  # previous user of the staging buffer
+        stage.numpy()[:nbytes] = a.reshape(-1).view(np.uint8)
+        out.view(torch.uint8).reshape(-1).copy_(stage[:nbytes], non_blocking=True)
+        return out
+
+    def to_host(self, t) -> np.ndarray:
+        """CUDA tensor -> fresh C-contiguous NumPy array backed by page-locked memory (synchronous)."""
+        torch = _torch()
+        t = t.contiguous()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
+    # ------------------------------------------------------------------ K1
+    def bgr2gray(self, img):
+        """cv2.cvtColor(BGR2GRAY); 2-D (or stack of 2-D) input is returned unchanged like the reference."""
+        torch = _torch()
+        if img.dim() == 2 or (img.dim() == 3 and img.shape[-1] not in (3, 4)):
+            return img
+        img = self._check(img, ndim=(3, 4), dtypes=(torch.uint8, torch.uint16, torch.float32))
+        if img.shape[-1] == 4:  # cv2 BGRA2GRAY ignores alpha; BGR2GRAY itself rejects 4 channels
+            raise ValueError("bgr2gray expects 3 channels (cv2.COLOR_BGR2GRAY)")
+        lead = img.shape[:-1]
+        n = 1 if img.dim() == 3 else int(img.shape[0])
+        h, w = int(lead[-2]), int(lead[-1])
+        out = torch.empty(lead, dtype=img.dtype, device=self.device)
+        self._call("yam_bgr2gray", self._p(img), self._p(out), n, h, w, _dtype_code(img))
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def minmax(self, img) -> np.ndarray:
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16, torch.float32))
+        n, h, w = self._nhw(img)
+        host = (C.c_double * (2 * n))()
+        self._call("yam_minmax", self._p(img), n, h, w, _dtype_code(img), None, C.cast(host, C.c_void_p))
+        return np.array(host, dtype=np.float64).reshape(n, 2)
+
+    def normalize_minmax(self, img, alpha: float = 0.0, beta: float = 255.0):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16, torch.float32))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_normalize_minmax", self._p(img), self._p(out), n, h, w, _dtype_code(img),
+                   float(alpha), float(beta))
+        return out
+
+    def convert_scale_abs(self, img, alpha: float = 1.0, beta: float = 0.0):
+        torch = _torch()
+        img = self._check(img, ndim=(2, 3, 4), dtypes=(torch.uint8, torch.uint16, torch.float32))
+        out = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        self._call("yam_convert_scale_abs", self._p(img), self._p(out), img.numel(), _dtype_code(img),
+                   float(alpha), float(beta))
+        return out
+
+    def lut_u8(self, img, table: np.ndarray):
+        torch = _torch()
+        img = self._check(img, ndim=(2, 3, 4), dtypes=(torch.uint8,))
+        tab = np.ascontiguousarray(table, dtype=np.uint8)
+        if tab.size != 256:
+            raise ValueError("LUT must have 256 entries")
+        out = torch.empty_like(img)
+        self._call("yam_lut_u8", self._p(img), self._p(out), img.numel(), tab.ctypes.data_as(C.c_void_p))
+        return out
+
+    def threshold(self, img, thresh: float, maxval: float = 255.0):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16, torch.float32))
+        out = torch.empty_like(img)
+        self._call("yam_threshold", self._p(img), self._p(out), img.numel(), _dtype_code(img),
+                   float(thresh), float(maxval))
+        return out
+
+    # ------------------------------------------------------------------ K3 / K4 / K5
+    def gaussian(self, img, ksize: int, sigma: float = 0.0, border: int = BORDER_REFLECT101):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16, torch.float32))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_gaussian", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(ksize),
+                   float(sigma), int(border))
+        return out
+
+    def box(self, img, ksize: int):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_box", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(ksize))
+        return out
+
+    def median(self, img, ksize: int):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_median", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(ksize))
+        return out
+
+    # ------------------------------------------------------------------ K9
+    def adaptive_threshold(self, img, block_size: int = 11, C_: float = 2.0):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        self._call("yam_adaptive_threshold", self._p(img), self._p(out), n, h, w, _dtype_code(img),
+                   int(block_size), float(C_))
+        return out
+
+    # ------------------------------------------------------------------ K6
+    def morph(self, img, op: int, kernel_shape: str = "Rectangular", kernel_size: int = 3, iterations: int = 1):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_morph", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(op),
+                   shape_code(kernel_shape), int(kernel_size), int(iterations))
+        return out
+
+    def erode(self, img, kernel_shape="Rectangular", kernel_size=3, iterations=1):
+        return self.morph(img, MORPH_ERODE, kernel_shape, kernel_size, iterations)
+
+    def dilate(self, img, kernel_shape="Rectangular", kernel_size=3, iterations=1):
+        return self.morph(img, MORPH_DILATE, kernel_shape, kernel_size, iterations)
+
+    def morph_open(self, img, kernel_shape="Rectangular", kernel_size=3, iterations=1):
+        return self.morph(img, MORPH_OPEN, kernel_shape, kernel_size, iterations)
+
+    def morph_close(self, img, kernel_shape="Rectangular", kernel_size=3, iterations=1):
+        return self.morph(img, MORPH_CLOSE, kernel_shape, kernel_size, iterations)
+
+    def morph_open_close(self, img, kernel_size: int = 5, iterations: int = 1):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_morph_open_close", self._p(img), self._p(out), n, h, w, _dtype_code(img),
+                   int(kernel_size), int(iterations))
+        return out
+
+    # ------------------------------------------------------------------ K7 / K8
+    def histogram(self, img):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        bins = 256 if img.dtype == torch.uint8 else 65536
+        hist = torch.empty((n, bins), dtype=torch.int64, device=self.device)
+        self._call("yam_histogram", self._p(img), n, h, w, _dtype_code(img), self._p(hist))
+        return hist
+
+    def otsu_threshold(self, img, maxval: float = 255.0, want_image: bool = True):
+        """Returns (thresholds int32[n] on device, thresholded image or None)."""
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        t = torch.empty((n,), dtype=torch.int32, device=self.device)
+        out = torch.empty_like(img) if want_image else None
+        self._call("yam_otsu_threshold", self._p(img), self._p(out) if out is not None else None, n, h, w,
+                   _dtype_code(img), float(maxval), self._p(t), None)
+        return t, out
+
+    def equalize_hist(self, img):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8,))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_equalize_hist", self._p(img), self._p(out), n, h, w)
+        return out
+
+    def clahe(self, img, clip_limit: float = 2.0, tile_grid: Tuple[int, int] = (8, 8)):
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_clahe", self._p(img), self._p(out), n, h, w, _dtype_code(img), float(clip_limit),
+                   int(tile_grid[0]), int(tile_grid[1]))
+        return out
+
+    # ------------------------------------------------------------------ K10 / K11
+    def ccl_label(self, mask):
+        """Returns (labels int32 like mask, counts int32[n] on device)."""
+        torch = _torch()
+        mask = self._check(mask, dtypes=(torch.uint8,), name="mask")
+        n, h, w = self._nhw(mask)
+        labels = torch.empty(mask.shape, dtype=torch.int32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._call("yam_ccl_label", self._p(mask), self._p(labels), n, h, w, self._p(counts), None)
+        return labels, counts
+
+    def region_props(self, labels, intensity=None, n_labels: Optional[int] = None):
+        """Per-label accumulators int64[n_labels, 8] on device (see include/yamb200.h)."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(2,), dtypes=(torch.int32,), name="labels")
+        h, w = int(labels.shape[0]), int(labels.shape[1])
+        if n_labels is None:
+            n_labels = int(labels.max().item())
+        idt = 0
+        iptr = None
+        if intensity is not None:
+            intensity = self._check(intensity, ndim=(2,), dtypes=(torch.uint8, torch.uint16), name="intensity")
+            if tuple(intensity.shape) != (h, w):
+                raise ValueError("intensity image must match the label image shape")
+            idt = _dtype_code(intensity)
+            iptr = self._p(intensity)
+        props = torch.empty((int(n_labels), PROPS_STRIDE), dtype=torch.int64, device=self.device)
+        if n_labels > 0:
+            self._call("yam_region_props", self._p(labels), iptr, idt, h, w, int(n_labels), self._p(props))
+        return props
+
+
+_default: Dict[int, Backend] = {}
+_default_lock = threading.Lock()
+
+
+def get_backend(device: int = 0) -> Backend:
+    """Process-wide Backend per device (created on first use; raises if no GPU / no library)."""
+    with _default_lock:
+        be = _default.get(device)
+        if be is None:
+            be = Backend(device)
+            _default[device] = be
+        return be
+
+
+def props_table(props: np.ndarray) -> Dict[str, np.ndarray]:
+    """Turn the int64[n,8] accumulators into skimage-style columns (core/extraction.py:70-87)."""
+    area = props[:, 0]
+    safe = np.maximum(area, 1).astype(np.float64)
+    return {
+        "area": area.copy(),
+        "sum_y": props[:, 1].copy(),
+        "sum_x": props[:, 2].copy(),
+        "sum_intensity": props[:, 3].copy(),
+        "centroid_row": props[:, 1] / safe,
+        "centroid_col": props[:, 2] / safe,
+        "mean_intensity": props[:, 3] / safe,
+        "bbox": props[:, 4:8].copy(),
+    }
+
+
+__all__ = ["Backend", "get_backend", "props_table", "shape_code", "BackendUnavailable", "YamError"]

@@ -1,0 +1,576 @@
+// K3 / K5 / K9 / K4: separable Gaussian (cv2 fixed-point and float32 orders), box filter,
+// Gaussian adaptive threshold and small-window median — all as ONE fused pass per op:
+// a (TH+2r) x (TW+2r) halo tile is staged in shared memory with 128-bit loads, the horizontal
+// pass writes an intermediate tile to shared memory, the vertical pass reads it back register-
+// tiled and writes the output with coalesced stores.  HBM traffic = 1 read + 1 write per pixel
+// (halo re-reads hit L2).  Arithmetic follows oracle/np_oracle.py bit for bit.
+#include <math.h>
+
+#include "yam_common.cuh"
+#include "yam_host.h"
+#include "yam_median_net.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TW = 64;   // output tile width  (2 columns per lane in the vertical pass)
+constexpr int TH = 64;   // output tile height (8 warps x 8 rows)
+constexpr int RB = 8;    // rows per warp in the vertical pass
+
+struct TapsU {
+    uint32_t v[YAM_MAX_TAPS + 1];
+};
+struct TapsF {
+    float v[YAM_MAX_TAPS + 1];
+};
+
+enum { EPI_SHIFT = 0, EPI_BOX = 1 };
+enum { FEPI_STORE = 0, FEPI_ADAPTIVE = 1 };
+
+template <typename T>
+struct FixedTraits;
+template <>
+struct FixedTraits<uint8_t> {
+    typedef uint32_t Acc;
+    static constexpr int bits = 8;
+};
+template <>
+struct FixedTraits<uint16_t> {
+    typedef unsigned long long Acc;
+    static constexpr int bits = 16;
+};
+
+__host__ __device__ constexpr int round_up_c(int v, int a) { return (v + a - 1) / a * a; }
+
+// ----------------------------------------------------------------------------------------------
+// tile loader: s_in[rows][SW] <- src[(y0-r .. y0+TH+r) x (x0-ra .. x0+TW+ra)] with border mapping.
+// TS = smem element type (T itself, or float when Tin is converted on load).
+template <typename T, typename TS>
+__device__ __forceinline__ void load_tile(const T* __restrict__ src, TS* __restrict__ s_in, int h, int w,
+                                          int x0, int y0, int r, int ra, int SW, int rows, int border) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int vec_per_row = SW / VEC;
+    const int total = rows * vec_per_row;
+    const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int v = threadIdx.x; v < total; v += kThreads) {
+        const int ry = v / vec_per_row;
+        const int vx = v - ry * vec_per_row;
+        const int gy = yam_border(y0 - r + ry, h, border);
+        const int gx = x0 - ra + vx * VEC;
+        TS* d = s_in + ry * SW + vx * VEC;
+        const T* row = src + (int64_t)gy * w;
+        if (row_aligned && gx >= 0 && gx + VEC <= w) {
+            uint4 q = *reinterpret_cast<const uint4*>(row + gx);
+            const T* e = reinterpret_cast<const T*>(&q);
+            if (sizeof(TS) == sizeof(T)) {
+                *reinterpret_cast<uint4*>(d) = q;
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; i++) d[i] = (TS)e[i];
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < VEC; i++) d[i] = (TS)row[yam_border(gx + i, w, border)];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// fixed-point separable filter, compile-time K (register-tiled)
+template <typename T, int KS, int EPI>
+__global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict__ src, T* __restrict__ dst,
+                                                            int h, int w, TapsU taps, int border,
+                                                            uint32_t box_div) {
+    typedef typename FixedTraits<T>::Acc Acc;
+    constexpr int bits = FixedTraits<T>::bits;
+    constexpr int VEC = 16 / sizeof(T);
+    constexpr int R = KS / 2;
+    constexpr int RA = round_up_c(R, VEC);
+    constexpr int SW = TW + 2 * RA;
+    constexpr int ROWS = TH + 2 * R;
+    constexpr int NV = 1 + 2 * RA / VEC;  // aligned vectors covering VEC outputs + halo
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_in = reinterpret_cast<T*>(smem_raw);
+    uint32_t* s_t = reinterpret_cast<uint32_t*>(smem_raw + round_up_c(ROWS * SW * (int)sizeof(T), 16));
+
+    const int64_t frame = blockIdx.z;
+    src += frame * (int64_t)h * w;
+    dst += frame * (int64_t)h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+
+    load_tile<T, T>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, border);
+    __syncthreads();
+
+    // horizontal pass: VEC outputs per item, exact integer, symmetric pairs share one multiply
+    constexpr int GROUPS = TW / VEC;
+    for (int item = threadIdx.x; item < ROWS * GROUPS; item += kThreads) {
+        const int ry = item / GROUPS, cg = item - ry * GROUPS;
+        const T* p = s_in + ry * SW + cg * VEC;
+        uint32_t e[NV * VEC];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            uint4 q = *reinterpret_cast<const uint4*>(p + v * VEC);
+            const T* qe = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) e[v * VEC + i] = qe[i];
+        }
+        uint32_t out[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) {
+            const int c = RA + j;  // centre element
+            uint32_t acc = taps.v[R] * e[c];
+#pragma unroll
+            for (int i = 1; i <= R; i++) acc += taps.v[R + i] * (e[c - i] + e[c + i]);
+            out[j] = acc;
+        }
+        uint32_t* t = s_t + ry * TW + cg * VEC;
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4)
+            *reinterpret_cast<uint4*>(t + j) = make_uint4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+    }
+    __syncthreads();
+
+    // vertical pass: lane -> column pair, warp -> RB output rows; sliding window in registers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = 2 * lane;
+    const int r0 = warp * RB;
+    Acc acc0[RB], acc1[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) acc0[j] = acc1[j] = 0;
+#pragma unroll
+    for (int i = 0; i < RB + 2 * R; i++) {
+        const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TW + cx);
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+            const int k = i - j;  // tap index for output row j
+            if (k >= 0 && k < KS) {
+                acc0[j] += (Acc)taps.v[k] * tv.x;
+                acc1[j] += (Acc)taps.v[k] * tv.y;
+            }
+        }
+    }
+    const int gx = x0 + cx;
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+        const int gy = y0 + r0 + j;
+        if (gy >= h || gx >= w) continue;
+        uint32_t o0, o1;
+        if (EPI == EPI_SHIFT) {
+            o0 = (uint32_t)((acc0[j] + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
+            o1 = (uint32_t)((acc1[j] + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
+        } else {
+            // rint(sum / k^2), k^2 odd: (2 sum + k^2) / (2 k^2)
+            o0 = (uint32_t)((2 * (uint32_t)acc0[j] + box_div) / (2 * box_div));
+            o1 = (uint32_t)((2 * (uint32_t)acc1[j] + box_div) / (2 * box_div));
+        }
+        T* d = dst + (int64_t)gy * w + gx;
+        if (gx + 1 < w && ((reinterpret_cast<uintptr_t>(d) & (2 * sizeof(T) - 1)) == 0)) {
+            if (sizeof(T) == 2)
+                *reinterpret_cast<uint32_t*>(d) = o0 | (o1 << 16);
+            else
+                *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
+        } else {
+            d[0] = (T)o0;
+            if (gx + 1 < w) d[1] = (T)o1;
+        }
+    }
+}
+
+// fixed-point separable filter, runtime K (any odd K <= YAM_MAX_TAPS that fits shared memory)
+template <typename T, int EPI>
+__global__ void __launch_bounds__(kThreads) sep_fixed_generic(const T* __restrict__ src, T* __restrict__ dst,
+                                                              int h, int w, TapsU taps, int ks, int border,
+                                                              uint32_t box_div) {
+    typedef typename FixedTraits<T>::Acc Acc;
+    constexpr int bits = FixedTraits<T>::bits;
+    constexpr int VEC = 16 / sizeof(T);
+    const int R = ks / 2;
+    const int RA = round_up_c(R, VEC);
+    const int SW = TW + 2 * RA;
+    const int ROWS = TH + 2 * R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_in = reinterpret_cast<T*>(smem_raw);
+    uint32_t* s_t = reinterpret_cast<uint32_t*>(smem_raw + round_up_c(ROWS * SW * (int)sizeof(T), 16));
+    const int64_t frame = blockIdx.z;
+    src += frame * (int64_t)h * w;
+    dst += frame * (int64_t)h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile<T, T>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, border);
+    __syncthreads();
+    for (int item = threadIdx.x; item < ROWS * TW; item += kThreads) {
+        const int ry = item / TW, cx = item - ry * TW;
+        const T* p = s_in + ry * SW + cx + RA - R;
+        uint32_t acc = 0;
+        for (int i = 0; i < ks; i++) acc += taps.v[i] * (uint32_t)p[i];
+        s_t[item] = acc;
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < TH * TW; item += kThreads) {
+        const int ry = item / TW, cx = item - ry * TW;
+        const int gx = x0 + cx, gy = y0 + ry;
+        if (gx >= w || gy >= h) continue;
+        Acc acc = 0;
+        for (int i = 0; i < ks; i++) acc += (Acc)taps.v[i] * s_t[(ry + i) * TW + cx];
+        uint32_t o;
+        if (EPI == EPI_SHIFT)
+            o = (uint32_t)((acc + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
+        else
+            o = (uint32_t)((2 * (uint32_t)acc + box_div) / (2 * box_div));
+        dst[(int64_t)gy * w + gx] = (T)o;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// float32 separable Gaussian in cv2 4.13's summation order (see oracle gaussian_f32):
+//   rows  K>=7: s = k0*x0; s = fma(x_i, k_i, s)            (sequential)
+//         K==5: s = (x-1 + x+1)*k1; s = fma(x0,kc,s); s = fma(x-2 + x+2, k2, s)
+//         K==3: s = fma(x-1 + x+1, k1, x0*kc)
+//   cols       t = kc*y0; t = fma(y+j + y-j, k_{c+j}, t)    (centre, then symmetric pairs)
+template <int KSC>
+__device__ __forceinline__ float row_dot(const float* __restrict__ x, const TapsF& taps, int ks) {
+    // x points at the left-most tap
+    const int K = KSC > 0 ? KSC : ks;
+    if (K == 3) return __fmaf_rn(__fadd_rn(x[0], x[2]), taps.v[2], __fmul_rn(x[1], taps.v[1]));
+    if (K == 5) {
+        float s = __fmul_rn(__fadd_rn(x[1], x[3]), taps.v[3]);
+        s = __fmaf_rn(x[2], taps.v[2], s);
+        return __fmaf_rn(__fadd_rn(x[0], x[4]), taps.v[4], s);
+    }
+    float s = __fmul_rn(taps.v[0], x[0]);
+    if (KSC > 0) {
+#pragma unroll
+        for (int i = 1; i < (KSC > 0 ? KSC : 1); i++) s = __fmaf_rn(x[i], taps.v[i], s);
+    } else {
+        for (int i = 1; i < K; i++) s = __fmaf_rn(x[i], taps.v[i], s);
+    }
+    return s;
+}
+
+template <typename Tin, typename Tout, int KSC, int FEPI>
+__global__ void __launch_bounds__(kThreads) sep_f32_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst,
+                                                           int h, int w, TapsF taps, int ks, int border,
+                                                           int sat_hi, int idelta) {
+    constexpr int VEC = 16 / sizeof(Tin);
+    const int K = KSC > 0 ? KSC : ks;
+    const int R = K / 2;
+    const int RA = round_up_c(R, VEC);
+    const int SW = TW + 2 * RA;
+    const int ROWS = TH + 2 * R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_in = reinterpret_cast<float*>(smem_raw);
+    float* s_t = s_in + ROWS * SW;
+    const int64_t frame = blockIdx.z;
+    src += frame * (int64_t)h * w;
+    dst += frame * (int64_t)h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile<Tin, float>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, border);
+    __syncthreads();
+
+    // horizontal pass, 4 outputs per item
+    constexpr int PX = 4;
+    constexpr int GROUPS = TW / PX;
+    for (int item = threadIdx.x; item < ROWS * GROUPS; item += kThreads) {
+        const int ry = item / GROUPS, cg = item - ry * GROUPS;
+        const float* p = s_in + ry * SW + cg * PX + RA - R;
+        float o[PX];
+        if (KSC > 0) {
+            float e[PX + (KSC > 0 ? KSC : 1) - 1];
+#pragma unroll
+            for (int i = 0; i < PX + (KSC > 0 ? KSC : 1) - 1; i++) e[i] = p[i];
+#pragma unroll
+            for (int j = 0; j < PX; j++) o[j] = row_dot<KSC>(e + j, taps, ks);
+        } else {
+#pragma unroll
+            for (int j = 0; j < PX; j++) o[j] = row_dot<0>(p + j, taps, ks);
+        }
+        *reinterpret_cast<float4*>(s_t + ry * TW + cg * PX) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+
+    // vertical pass: lane -> column pair, warp -> RB rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = 2 * lane;
+    const int r0 = warp * RB;
+    const int gx = x0 + cx;
+    float out0[RB], out1[RB];
+    if (KSC > 0) {
+        constexpr int KK = KSC > 0 ? KSC : 1;
+        constexpr int RR = KK / 2;
+        float c0[RB + KK - 1], c1[RB + KK - 1];
+#pragma unroll
+        for (int i = 0; i < RB + KK - 1; i++) {
+            const float2 v = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TW + cx);
+            c0[i] = v.x;
+            c1[i] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+            float a = __fmul_rn(taps.v[RR], c0[j + RR]);
+            float b = __fmul_rn(taps.v[RR], c1[j + RR]);
+#pragma unroll
+            for (int q = 1; q <= RR; q++) {
+                a = __fmaf_rn(__fadd_rn(c0[j + RR + q], c0[j + RR - q]), taps.v[RR + q], a);
+                b = __fmaf_rn(__fadd_rn(c1[j + RR + q], c1[j + RR - q]), taps.v[RR + q], b);
+            }
+            out0[j] = a;
+            out1[j] = b;
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < RB; j++) {
+            const float* col = s_t + (r0 + j + R) * TW + cx;
+            float a = __fmul_rn(taps.v[R], col[0]);
+            float b = __fmul_rn(taps.v[R], col[1]);
+            for (int q = 1; q <= R; q++) {
+                a = __fmaf_rn(__fadd_rn(col[q * TW], col[-q * TW]), taps.v[R + q], a);
+                b = __fmaf_rn(__fadd_rn(col[q * TW + 1], col[-q * TW + 1]), taps.v[R + q], b);
+            }
+            out0[j] = a;
+            out1[j] = b;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+        const int gy = y0 + r0 + j;
+        if (gy >= h || gx >= w) continue;
+        Tout* d = dst + (int64_t)gy * w + gx;
+        if (FEPI == FEPI_ADAPTIVE) {
+            // mean = saturate(rint(blur)); dst = (src - mean > -idelta) ? 255 : 0
+            const float* sp = s_in + (r0 + j + R) * SW + RA + cx;
+            const int m0 = yam_rint_sat(out0[j], sat_hi), m1 = yam_rint_sat(out1[j], sat_hi);
+            const int s0 = (int)sp[0], s1 = (int)sp[1];
+            const uint32_t o0 = (s0 - m0 > -idelta) ? 255u : 0u, o1 = (s1 - m1 > -idelta) ? 255u : 0u;
+            if (gx + 1 < w && ((reinterpret_cast<uintptr_t>(d) & 1) == 0))
+                *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
+            else {
+                d[0] = (Tout)o0;
+                if (gx + 1 < w) d[1] = (Tout)o1;
+            }
+        } else {
+            d[0] = (Tout)out0[j];
+            if (gx + 1 < w) d[1] = (Tout)out1[j];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// median 3x3 / 5x5 (cv2.medianBlur, BORDER_REPLICATE): exact rank filter via min/max exchanges
+template <typename T, int KS>
+__global__ void __launch_bounds__(kThreads) median_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                          int h, int w) {
+    constexpr int VEC = 16 / sizeof(T);
+    constexpr int R = KS / 2;
+    constexpr int RA = round_up_c(R, VEC);
+    constexpr int SW = TW + 2 * RA;
+    constexpr int ROWS = TH + 2 * R;
+    __shared__ __align__(16) T s_in[ROWS * SW];
+    const int64_t frame = blockIdx.z;
+    src += frame * (int64_t)h * w;
+    dst += frame * (int64_t)h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile<T, T>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, YAM_BORDER_REPLICATE);
+    __syncthreads();
+    for (int item = threadIdx.x; item < TH * TW; item += kThreads) {
+        const int ry = item / TW, cx = item - ry * TW;
+        const int gx = x0 + cx, gy = y0 + ry;
+        if (gx >= w || gy >= h) continue;
+        uint32_t p[KS * KS];
+#pragma unroll
+        for (int dy = 0; dy < KS; dy++)
+#pragma unroll
+            for (int dx = 0; dx < KS; dx++) p[dy * KS + dx] = s_in[(ry + dy) * SW + cx + RA - R + dx];
+        dst[(int64_t)gy * w + gx] = (T)(KS == 3 ? median9(p) : median25(p));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch helpers
+
+inline dim3 tile_grid(int64_t n, int64_t h, int64_t w) {
+    return dim3((unsigned)((w + TW - 1) / TW), (unsigned)((h + TH - 1) / TH), (unsigned)n);
+}
+
+template <typename T>
+size_t fixed_smem(int ks) {
+    const int VEC = 16 / sizeof(T);
+    const int R = ks / 2, RA = round_up_c(R, VEC), SW = TW + 2 * RA, ROWS = TH + 2 * R;
+    return (size_t)round_up_c(ROWS * SW * (int)sizeof(T), 16) + (size_t)ROWS * TW * 4;
+}
+
+template <typename Tin>
+size_t f32_smem(int ks) {
+    const int VEC = 16 / sizeof(Tin);
+    const int R = ks / 2, RA = round_up_c(R, VEC), SW = TW + 2 * RA, ROWS = TH + 2 * R;
+    return (size_t)ROWS * SW * 4 + (size_t)ROWS * TW * 4;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (bytes > 227 * 1024) {
+            yam_set_error("filter window too large for shared memory (%zu bytes)", bytes);
+            return YAM_EINVAL;
+        }
+        YAM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return YAM_OK;
+}
+
+template <typename T, int EPI>
+int launch_fixed(yam_ctx* ctx, const T* src, T* dst, int64_t n, int64_t h, int64_t w, const TapsU& taps,
+                 int ks, int border, uint32_t box_div) {
+    dim3 grid = tile_grid(n, h, w);
+    const size_t smem = fixed_smem<T>(ks);
+#define YAM_FIXED_CASE(K)                                                                         \
+    case K: {                                                                                     \
+        if (int rc = set_smem(sep_fixed_tiled<T, K, EPI>, smem)) return rc;                       \
+        sep_fixed_tiled<T, K, EPI><<<grid, kThreads, smem, ctx->stream>>>(src, dst, (int)h, (int)w, \
+                                                                          taps, border, box_div); \
+        break;                                                                                    \
+    }
+    switch (ks) {
+        YAM_FIXED_CASE(3)
+        YAM_FIXED_CASE(5)
+        YAM_FIXED_CASE(7)
+        YAM_FIXED_CASE(9)
+        YAM_FIXED_CASE(11)
+        YAM_FIXED_CASE(13)
+        YAM_FIXED_CASE(15)
+        YAM_FIXED_CASE(17)
+        default: {
+            if (int rc = set_smem(sep_fixed_generic<T, EPI>, smem)) return rc;
+            sep_fixed_generic<T, EPI><<<grid, kThreads, smem, ctx->stream>>>(src, dst, (int)h, (int)w, taps,
+                                                                            ks, border, box_div);
+        }
+    }
+#undef YAM_FIXED_CASE
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+template <typename Tin, typename Tout, int FEPI>
+int launch_f32(yam_ctx* ctx, const Tin* src, Tout* dst, int64_t n, int64_t h, int64_t w, const TapsF& taps,
+               int ks, int border, int sat_hi, int idelta) {
+    dim3 grid = tile_grid(n, h, w);
+    const size_t smem = f32_smem<Tin>(ks);
+#define YAM_F32_CASE(K)                                                                              \
+    case K: {                                                                                        \
+        if (int rc = set_smem(sep_f32_kernel<Tin, Tout, K, FEPI>, smem)) return rc;                  \
+        sep_f32_kernel<Tin, Tout, K, FEPI><<<grid, kThreads, smem, ctx->stream>>>(                  \
+            src, dst, (int)h, (int)w, taps, ks, border, sat_hi, idelta);                             \
+        break;                                                                                       \
+    }
+    switch (ks) {
+        YAM_F32_CASE(3)
+        YAM_F32_CASE(5)
+        YAM_F32_CASE(7)
+        YAM_F32_CASE(11)
+        YAM_F32_CASE(15)
+        default: {
+            if (int rc = set_smem(sep_f32_kernel<Tin, Tout, 0, FEPI>, smem)) return rc;
+            sep_f32_kernel<Tin, Tout, 0, FEPI><<<grid, kThreads, smem, ctx->stream>>>(
+                src, dst, (int)h, (int)w, taps, ks, border, sat_hi, idelta);
+        }
+    }
+#undef YAM_F32_CASE
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+int check_shape(const void* src, const void* dst, int64_t n, int64_t h, int64_t w, const char* what) {
+    YAM_REQUIRE(src && dst, "%s: NULL image pointer", what);
+    YAM_REQUIRE(n > 0 && h > 0 && w > 0, "%s: empty image (%lld,%lld,%lld)", what, (long long)n, (long long)h, (long long)w);
+    YAM_REQUIRE(n <= 65535, "%s: at most 65535 frames per call", what);
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "%s: image side too large", what);
+    return YAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yam_gaussian(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+                 int ksize, double sigma, int border) {
+    if (int rc = yam_enter(ctx)) return rc;
+    if (int rc = check_shape(src, dst, n, h, w, "gaussian")) return rc;
+    YAM_REQUIRE(src != dst, "gaussian: in-place operation is not supported");
+    YAM_REQUIRE(border == YAM_BORDER_REFLECT101 || border == YAM_BORDER_REPLICATE, "gaussian: unknown border %d", border);
+    if (ksize <= 0) {
+        // cv2 createGaussianKernels: ksize from sigma
+        YAM_REQUIRE(sigma > 0, "gaussian: ksize and sigma cannot both be <= 0");
+        ksize = (int)lrint(sigma * (dtype == YAM_U8 ? 3 : 4) * 2 + 1) | 1;
+    }
+    YAM_REQUIRE((ksize & 1) && ksize <= YAM_MAX_TAPS, "gaussian: ksize must be odd and <= %d, got %d", YAM_MAX_TAPS, ksize);
+    double kf[YAM_MAX_TAPS];
+    yam_host_gaussian_taps(ksize, sigma, kf);
+    if (dtype == YAM_U8 || dtype == YAM_U16) {
+        int64_t kq[YAM_MAX_TAPS];
+        yam_host_fixed_taps(kf, ksize, dtype == YAM_U8 ? 8 : 16, kq);
+        TapsU taps;
+        for (int i = 0; i < ksize; i++) {
+            YAM_REQUIRE(kq[i] >= 0, "gaussian: negative fixed-point tap (sigma too small for ksize)");
+            taps.v[i] = (uint32_t)kq[i];
+        }
+        if (dtype == YAM_U8)
+            return launch_fixed<uint8_t, EPI_SHIFT>(ctx, (const uint8_t*)src, (uint8_t*)dst, n, h, w, taps, ksize, border, 0);
+        return launch_fixed<uint16_t, EPI_SHIFT>(ctx, (const uint16_t*)src, (uint16_t*)dst, n, h, w, taps, ksize, border, 0);
+    }
+    YAM_REQUIRE(dtype == YAM_F32, "gaussian: unsupported dtype %d", dtype);
+    TapsF taps;
+    for (int i = 0; i < ksize; i++) taps.v[i] = (float)kf[i];
+    return launch_f32<float, float, FEPI_STORE>(ctx, (const float*)src, (float*)dst, n, h, w, taps, ksize, border, 0, 0);
+}
+
+int yam_box(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype, int ksize) {
+    if (int rc = yam_enter(ctx)) return rc;
+    if (int rc = check_shape(src, dst, n, h, w, "box")) return rc;
+    YAM_REQUIRE(src != dst, "box: in-place operation is not supported");
+    YAM_REQUIRE((ksize & 1) && ksize >= 1 && ksize <= 31, "box: ksize must be odd in [1,31], got %d", ksize);
+    TapsU taps;
+    for (int i = 0; i < ksize; i++) taps.v[i] = 1;
+    const uint32_t kk = (uint32_t)(ksize * ksize);
+    if (dtype == YAM_U8)
+        return launch_fixed<uint8_t, EPI_BOX>(ctx, (const uint8_t*)src, (uint8_t*)dst, n, h, w, taps, ksize, YAM_BORDER_REFLECT101, kk);
+    YAM_REQUIRE(dtype == YAM_U16, "box: unsupported dtype %d", dtype);
+    return launch_fixed<uint16_t, EPI_BOX>(ctx, (const uint16_t*)src, (uint16_t*)dst, n, h, w, taps, ksize, YAM_BORDER_REFLECT101, kk);
+}
+
+int yam_adaptive_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
+                           int dtype, int block_size, double C) {
+    if (int rc = yam_enter(ctx)) return rc;
+    if (int rc = check_shape(src, dst, n, h, w, "adaptive_threshold")) return rc;
+    YAM_REQUIRE(src != dst, "adaptive_threshold: in-place operation is not supported");
+    YAM_REQUIRE((block_size & 1) && block_size >= 3 && block_size <= YAM_MAX_TAPS,
+                "adaptive_threshold: block_size must be odd in [3,%d], got %d", YAM_MAX_TAPS, block_size);
+    double kf[YAM_MAX_TAPS];
+    yam_host_gaussian_taps(block_size, 0.0, kf);
+    TapsF taps;
+    for (int i = 0; i < block_size; i++) taps.v[i] = (float)kf[i];
+    const int idelta = (int)ceil(C);
+    if (dtype == YAM_U8)
+        return launch_f32<uint8_t, uint8_t, FEPI_ADAPTIVE>(ctx, (const uint8_t*)src, (uint8_t*)dst, n, h, w, taps,
+                                                           block_size, YAM_BORDER_REPLICATE, 255, idelta);
+    YAM_REQUIRE(dtype == YAM_U16, "adaptive_threshold: unsupported dtype %d", dtype);
+    return launch_f32<uint16_t, uint8_t, FEPI_ADAPTIVE>(ctx, (const uint16_t*)src, (uint8_t*)dst, n, h, w, taps,
+                                                        block_size, YAM_BORDER_REPLICATE, 65535, idelta);
+}
+
+int yam_median(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype, int ksize) {
+    if (int rc = yam_enter(ctx)) return rc;
+    if (int rc = check_shape(src, dst, n, h, w, "median")) return rc;
+    YAM_REQUIRE(src != dst, "median: in-place operation is not supported");
+    YAM_REQUIRE(ksize == 3 || ksize == 5, "median: ksize must be 3 or 5 (got %d)", ksize);
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "median: unsupported dtype %d", dtype);
+    dim3 grid = tile_grid(n, h, w);
+    if (dtype == YAM_U8) {
+        if (ksize == 3) median_kernel<uint8_t, 3><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, (int)w);
+        else median_kernel<uint8_t, 5><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, (int)w);
+    } else {
+        if (ksize == 3) median_kernel<uint16_t, 3><<<grid, kThreads, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, (int)h, (int)w);
+        else median_kernel<uint16_t, 5><<<grid, kThreads, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, (int)h, (int)w);
+    }
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,674 @@
+// K7 / K8 histogram family: histogram, Otsu threshold, equalizeHist, CLAHE.
+//
+// 16-bit histograms: 65536 bins x 4 B = 256 KiB does not fit the 227 KiB of shared memory an SM
+// offers, so each CTA keeps a privatised histogram of PACKED 16-bit counters (65536 x 2 B =
+// 128 KiB, two bins per 32-bit word, shared-memory atomics).  A counter that reaches 0x8000 is
+// "spilled": 0x8000 is subtracted from it and added to a global overflow histogram, so a half
+// never carries into its neighbour and counts stay exact for any region size.
+//   * Otsu / plain histogram: P CTAs per frame (row slabs), non-zero bins flushed with RED to a
+//     global u64 histogram.
+//   * CLAHE: ONE CTA per CLAHE tile does histogram -> clip -> redistribute -> prefix sum -> LUT
+//     entirely on chip and writes only the 128 KiB LUT (no histogram ever reaches HBM).
+// 8-bit histograms use per-warp privatised 256-bin shared histograms.
+#include <math.h>
+
+#include "yam_common.cuh"
+#include "yam_host.h"
+
+int yam_threshold_dev(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t frame_px, int dtype,
+                      const int32_t* t_dev, double maxval);
+
+namespace {
+
+constexpr int kHistThreads = 1024;
+constexpr int kBins16 = 65536;
+constexpr int kWords16 = kBins16 / 2;
+constexpr size_t kSmem16 = (size_t)kWords16 * 4;
+
+// ---------------------------------------------------------------------------------------------
+// packed 16-bit shared-memory counters with spill
+
+template <typename CntT>
+__device__ __forceinline__ void bump16(uint32_t* __restrict__ sh, CntT* __restrict__ overflow,
+                                       int* __restrict__ spill_flag, uint32_t v, uint32_t count) {
+    const uint32_t shift = (v & 1u) * 16u;
+    const uint32_t old = (atomicAdd(&sh[v >> 1], count << shift) >> shift) & 0xffffu;
+    if (old < 0x8000u && old + count >= 0x8000u) {
+        atomicSub(&sh[v >> 1], 0x8000u << shift);
+        atomicAdd(&overflow[v], (CntT)0x8000u);
+        if (spill_flag) *spill_flag = 1;
+    }
+}
+
+// Accumulate rows [r0, r1) x cols [c0, c1) of a (possibly reflect-padded) region into `sh`.
+template <typename CntT>
+__device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __restrict__ overflow,
+                                             int* __restrict__ spill_flag, const uint16_t* __restrict__ src, int h, int w, int c0, int c1,
+                                             int r0, int r1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool aligned = ((w & 7) == 0) && ((c0 & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int cw = c1 - c0;
+    const int cin = min(c1, w) - c0;               // columns inside the image
+    const int nvec = aligned ? (cin > 0 ? cin / 8 : 0) : 0;
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+        const int gy = yam_border(r, h, YAM_BORDER_REFLECT101);
+        const uint16_t* row = src + (int64_t)gy * w;
+        for (int v = lane; v < nvec; v += 32) {
+            const uint4 q = yam_ld_stream(reinterpret_cast<const uint4*>(row + c0) + v);
+            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t a = wd[i] & 0xffffu, b = wd[i] >> 16;
+                if (a == b) {
+                    bump16(sh, overflow, spill_flag, a, 2u);
+                } else {
+                    bump16(sh, overflow, spill_flag, a, 1u);
+                    bump16(sh, overflow, spill_flag, b, 1u);
+                }
+            }
+        }
+        for (int c = nvec * 8 + lane; c < cw; c += 32) {
+            const int gx = yam_border(c0 + c, w, YAM_BORDER_REFLECT101);
+            bump16(sh, overflow, spill_flag, row[gx], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plain histogram (Otsu): grid (parts, 1, frames)
+__global__ void __launch_bounds__(kHistThreads, 1) hist16_kernel(const uint16_t* __restrict__ src, int h, int w,
+                                                                 unsigned long long* __restrict__ hist) {
+    extern __shared__ __align__(16) uint32_t sh[];
+    src += (int64_t)blockIdx.z * h * w;
+    unsigned long long* out = hist + (int64_t)blockIdx.z * kBins16;
+    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) sh[i] = 0;
+    __syncthreads();
+    const int parts = gridDim.x;
+    const int rows_per = (h + parts - 1) / parts;
+    const int r0 = blockIdx.x * rows_per, r1 = min(h, r0 + rows_per);
+    accumulate16<unsigned long long>(sh, out, nullptr, src, h, w, 0, w, r0, r1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) {
+        const uint32_t wv = sh[i];
+        if (wv & 0xffffu) atomicAdd(&out[2 * i], (unsigned long long)(wv & 0xffffu));
+        if (wv >> 16) atomicAdd(&out[2 * i + 1], (unsigned long long)(wv >> 16));
+    }
+}
+
+// 8-bit histogram: grid (blocks, 1, frames); per-warp private histograms
+__global__ void __launch_bounds__(256) hist8_kernel(const uint8_t* __restrict__ src, int64_t frame_px,
+                                                    unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t sh[8][256];
+    src += (int64_t)blockIdx.z * frame_px;
+    unsigned long long* out = hist + (int64_t)blockIdx.z * 256;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t* mine = sh[threadIdx.x >> 5];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    int64_t done = 0;
+    if (aligned) {
+        const int64_t groups = frame_px / 16;
+        for (int64_t g = tid; g < groups; g += stride) {
+            const uint4 q = yam_ld_stream(reinterpret_cast<const uint4*>(src) + g);
+            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                atomicAdd(&mine[wd[i] & 0xff], 1u);
+                atomicAdd(&mine[(wd[i] >> 8) & 0xff], 1u);
+                atomicAdd(&mine[(wd[i] >> 16) & 0xff], 1u);
+                atomicAdd(&mine[wd[i] >> 24], 1u);
+            }
+        }
+        done = groups * 16;
+    }
+    for (int64_t i = done + tid; i < frame_px; i += stride) atomicAdd(&mine[src[i]], 1u);
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) total += sh[wv][threadIdx.x];
+    if (total) atomicAdd(&out[threadIdx.x], (unsigned long long)total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Otsu scan on device, one thread per frame (used for stacks; a single frame is scanned on the
+// host because 65536 dependent fp64 divisions are ~10x faster on a CPU core than on one GPU thread).
+__global__ void otsu_scan_kernel(const unsigned long long* __restrict__ hist, int bins, int64_t n,
+                                 int32_t* __restrict__ out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const unsigned long long* h = hist + f * bins;
+    double total = 0.0, mu = 0.0;
+    for (int i = 0; i < bins; i++) {
+        const double c = (double)h[i];
+        total = __dadd_rn(total, c);
+        mu = __dadd_rn(mu, __dmul_rn((double)i, c));
+    }
+    if (!(total > 0.0)) {
+        out[f] = 0;
+        return;
+    }
+    const double scale = __ddiv_rn(1.0, total);
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0.0, q1 = 0.0, best = 0.0;
+    int best_i = 0;
+    const double eps = 1.1920928955078125e-07;
+    for (int i = 0; i < bins; i++) {
+        const double p = __dmul_rn((double)h[i], scale);
+        mu1 = __dmul_rn(mu1, q1);
+        q1 = __dadd_rn(q1, p);
+        const double q2 = __dsub_rn(1.0, q1);
+        if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
+        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p)), q1);
+        const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > best) {
+            best = sigma;
+            best_i = i;
+        }
+    }
+    out[f] = best_i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// equalizeHist (u8): LUT from the global histogram, one block per frame, then gather
+__global__ void __launch_bounds__(256) equalize_lut_kernel(const unsigned long long* __restrict__ hist,
+                                                           int64_t total, uint8_t* __restrict__ lut) {
+    __shared__ unsigned long long s_h[256];
+    __shared__ unsigned long long s_cum[256];
+    const unsigned long long* h = hist + (int64_t)blockIdx.x * 256;
+    uint8_t* out = lut + (int64_t)blockIdx.x * 256;
+    s_h[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c = 0;
+        for (int i = 0; i < 256; i++) {
+            c += s_h[i];
+            s_cum[i] = c;
+        }
+    }
+    __syncthreads();
+    // first non-empty bin
+    __shared__ int s_i0;
+    if (threadIdx.x == 0) {
+        int i0 = 0;
+        while (i0 < 255 && s_h[i0] == 0) i0++;
+        s_i0 = i0;
+    }
+    __syncthreads();
+    const int i0 = s_i0;
+    const int b = threadIdx.x;
+    if (s_h[i0] == (unsigned long long)total) {
+        out[b] = (uint8_t)i0;  // constant image: every pixel maps to itself (only bin i0 occurs)
+        return;
+    }
+    const float scale = __fdiv_rn(255.0f, (float)(total - (int64_t)s_h[i0]));
+    if (b <= i0) {
+        out[b] = 0;
+    } else {
+        const float s = (float)(long long)(s_cum[b] - s_h[i0]);
+        out[b] = (uint8_t)yam_rint_sat(__fmul_rn(s, scale), 255);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_lut8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                          int64_t frame_px, const uint8_t* __restrict__ luts) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = luts[(int64_t)blockIdx.z * 256 + threadIdx.x];
+    __syncthreads();
+    src += (int64_t)blockIdx.z * frame_px;
+    dst += (int64_t)blockIdx.z * frame_px;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    int64_t done = 0;
+    if (aligned) {
+        const int64_t groups = frame_px / 16;
+        for (int64_t g = tid; g < groups; g += stride) {
+            uint4 q = yam_ld_stream(reinterpret_cast<const uint4*>(src) + g);
+            uint8_t* e = reinterpret_cast<uint8_t*>(&q);
+#pragma unroll
+            for (int i = 0; i < 16; i++) e[i] = s_lut[e[i]];
+            yam_st_stream(reinterpret_cast<uint4*>(dst) + g, q);
+        }
+        done = groups * 16;
+    }
+    for (int64_t i = done + tid; i < frame_px; i += stride) dst[i] = s_lut[src[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLAHE
+struct ClaheGeom {
+    int h, w;            // image
+    int tiles_x, tiles_y;
+    int tw, th;          // tile size (of the padded image)
+    int clip;            // 0 = no clipping
+    float lut_scale;     // (histSize-1)/area
+    float inv_tw, inv_th;
+};
+
+// u16: one CTA per tile at a time (persistent CTAs loop over the tiles of a frame chunk):
+// histogram -> clip -> redistribute -> scan -> LUT.  grid (min(tiles_total, SMs)); each CTA owns
+// one 256 KiB overflow slot that is all-zero between tiles.
+__global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint16_t* __restrict__ src_all,
+                                                                      ClaheGeom g, int frames,
+                                                                      uint32_t* __restrict__ overflow,
+                                                                      uint16_t* __restrict__ luts) {
+    extern __shared__ __align__(16) uint32_t sh[];
+    __shared__ unsigned long long s_red[32];
+    __shared__ unsigned long long s_base[32];
+    __shared__ int s_spilled;
+    const int tiles_per_frame = g.tiles_x * g.tiles_y;
+    const int total_tiles = tiles_per_frame * frames;
+    uint32_t* ovf = overflow + (int64_t)blockIdx.x * kBins16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long area = (long long)g.tw * g.th;
+    const int wbase = warp * 1024;  // each warp owns words [1024*warp, +1024); lane reads base+32*i+lane
+    const unsigned long long clipv = g.clip > 0 ? (unsigned long long)g.clip : ~0ull;
+
+    for (int slot = blockIdx.x; slot < total_tiles; slot += gridDim.x) {
+        const int frame = slot / tiles_per_frame, tile = slot - frame * tiles_per_frame;
+        const int tyi = tile / g.tiles_x, txi = tile - tyi * g.tiles_x;
+        const uint16_t* src = src_all + (int64_t)frame * g.h * g.w;
+        uint16_t* lut = luts + (int64_t)slot * kBins16;
+
+        for (int i = threadIdx.x; i < kWords16; i += kHistThreads) sh[i] = 0;
+        if (threadIdx.x == 0) s_spilled = 0;
+        __syncthreads();
+        accumulate16<uint32_t>(sh, ovf, &s_spilled, src, g.h, g.w, txi * g.tw, (txi + 1) * g.tw, tyi * g.th,
+                               (tyi + 1) * g.th);
+        __threadfence();
+        __syncthreads();
+        const bool use_ovf = s_spilled != 0;
+
+        // pass 0: sum of clipped counts -> excess
+        unsigned long long part = 0;
+        for (int i = 0; i < 32; i++) {
+            const int wi = wbase + 32 * i + lane;
+            const uint32_t wv = sh[wi];
+            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
+            if (use_ovf) {
+                c0 += __ldcg(&ovf[2 * wi]);
+                c1 += __ldcg(&ovf[2 * wi + 1]);
+            }
+            part += (c0 < clipv ? c0 : clipv) + (c1 < clipv ? c1 : clipv);
+        }
+        part = yam_warp_sum(part);
+        if (lane == 0) s_red[warp] = part;
+        __syncthreads();
+        unsigned long long clipped_total = 0;
+        for (int i = 0; i < 32; i++) clipped_total += s_red[i];
+        __syncthreads();
+        const unsigned long long excess = (unsigned long long)area - clipped_total;
+        const unsigned long long batch = g.clip > 0 ? excess / kBins16 : 0;
+        const uint32_t residual = g.clip > 0 ? (uint32_t)(excess - batch * kBins16) : 0;
+        const uint32_t step = residual ? max((uint32_t)kBins16 / residual, 1u) : 1u;
+
+        auto adjusted = [&](uint32_t bin, unsigned long long c) -> unsigned long long {
+            unsigned long long a = (c < clipv ? c : clipv) + batch;
+            if (residual && (bin % step) == 0 && (bin / step) < residual) a += 1;
+            return a;
+        };
+
+        // pass 1: warp totals of adjusted counts
+        part = 0;
+        for (int i = 0; i < 32; i++) {
+            const int wi = wbase + 32 * i + lane;
+            const uint32_t wv = sh[wi];
+            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
+            if (use_ovf) {
+                c0 += __ldcg(&ovf[2 * wi]);
+                c1 += __ldcg(&ovf[2 * wi + 1]);
+            }
+            part += adjusted(2 * wi, c0) + adjusted(2 * wi + 1, c1);
+        }
+        part = yam_warp_sum(part);
+        if (lane == 0) s_red[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long run0 = 0;
+            for (int i = 0; i < 32; i++) {
+                s_base[i] = run0;
+                run0 += s_red[i];
+            }
+        }
+        __syncthreads();
+
+        // pass 2: ordered prefix sum -> LUT
+        unsigned long long run = s_base[warp];
+        for (int i = 0; i < 32; i++) {
+            const int wi = wbase + 32 * i + lane;
+            const uint32_t wv = sh[wi];
+            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
+            if (use_ovf) {
+                c0 += __ldcg(&ovf[2 * wi]);
+                c1 += __ldcg(&ovf[2 * wi + 1]);
+            }
+            const unsigned long long a0 = adjusted(2 * wi, c0), a1 = adjusted(2 * wi + 1, c1);
+            unsigned long long incl = a0 + a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned long long before = run + incl - (a0 + a1);
+            const unsigned long long cum0 = before + a0, cum1 = cum0 + a1;
+            // cv2: saturate_cast<ushort>(sum * lutScale) with sum an int converted to float
+            const uint32_t l0 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum0, g.lut_scale), 65535);
+            const uint32_t l1 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum1, g.lut_scale), 65535);
+            reinterpret_cast<uint32_t*>(lut)[wi] = l0 | (l1 << 16);
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncthreads();
+        // leave the overflow slot zero for the next tile / call
+        if (use_ovf) {
+            for (int i = threadIdx.x; i < kBins16; i += kHistThreads) ovf[i] = 0;
+            __threadfence();
+            __syncthreads();
+        }
+    }
+}
+
+// u8: one CTA (256 threads) per tile
+__global__ void __launch_bounds__(256) clahe_lut8_kernel(const uint8_t* __restrict__ src, ClaheGeom g,
+                                                         uint8_t* __restrict__ luts) {
+    __shared__ uint32_t sh[8][256];
+    __shared__ unsigned long long s_cnt[256];
+    __shared__ unsigned long long s_cum[256];
+    __shared__ unsigned long long s_excess;
+    const int tile = blockIdx.x;
+    const int tyi = tile / g.tiles_x, txi = tile - tyi * g.tiles_x;
+    src += (int64_t)blockIdx.z * g.h * g.w;
+    uint8_t* lut = luts + ((int64_t)blockIdx.z * g.tiles_x * g.tiles_y + tile) * 256;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* mine = sh[warp];
+    const int c0 = txi * g.tw, r0 = tyi * g.th;
+    for (int r = r0 + warp; r < r0 + g.th; r += 8) {
+        const int gy = yam_border(r, g.h, YAM_BORDER_REFLECT101);
+        const uint8_t* row = src + (int64_t)gy * g.w;
+        for (int c = lane; c < g.tw; c += 32)
+            atomicAdd(&mine[row[yam_border(c0 + c, g.w, YAM_BORDER_REFLECT101)]], 1u);
+    }
+    __syncthreads();
+    const int b = threadIdx.x;
+    unsigned long long cnt = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) cnt += sh[wv][b];
+    const unsigned long long clipv = g.clip > 0 ? (unsigned long long)g.clip : ~0ull;
+    s_cnt[b] = cnt < clipv ? cnt : clipv;
+    __syncthreads();
+    if (b == 0) {
+        unsigned long long s = 0;
+        for (int i = 0; i < 256; i++) s += s_cnt[i];
+        s_excess = (unsigned long long)g.tw * g.th - s;
+    }
+    __syncthreads();
+    if (g.clip > 0) {
+        const unsigned long long excess = s_excess;
+        const unsigned long long batch = excess / 256;
+        const uint32_t residual = (uint32_t)(excess - batch * 256);
+        const uint32_t step = residual ? max(256u / residual, 1u) : 1u;
+        unsigned long long a = s_cnt[b] + batch;
+        if (residual && (b % step) == 0 && (b / step) < residual) a += 1;
+        s_cnt[b] = a;
+    }
+    __syncthreads();
+    if (b == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 256; i++) {
+            run += s_cnt[i];
+            s_cum[i] = run;
+        }
+    }
+    __syncthreads();
+    lut[b] = (uint8_t)yam_rint_sat(__fmul_rn((float)(long long)s_cum[b], g.lut_scale), 255);
+}
+
+// bilinear blend of the four neighbouring tile LUTs, cv2 order, no FMA contraction
+template <typename T>
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                          ClaheGeom g, const T* __restrict__ luts) {
+    constexpr int VEC = 16 / sizeof(T);
+    constexpr int BINS = sizeof(T) == 1 ? 256 : 65536;
+    constexpr int HI = BINS - 1;
+    const int64_t frame_px = (int64_t)g.h * g.w;
+    src += (int64_t)blockIdx.z * frame_px;
+    dst += (int64_t)blockIdx.z * frame_px;
+    luts += (int64_t)blockIdx.z * g.tiles_x * g.tiles_y * BINS;
+    const int y = blockIdx.x;
+    const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+    int ty1 = (int)floorf(tyf);
+    const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
+    const int ty2 = min(ty1 + 1, g.tiles_y - 1);
+    ty1 = max(ty1, 0);
+    const T* lrow1 = luts + (int64_t)ty1 * g.tiles_x * BINS;
+    const T* lrow2 = luts + (int64_t)ty2 * g.tiles_x * BINS;
+    const T* srow = src + (int64_t)y * g.w;
+    T* drow = dst + (int64_t)y * g.w;
+    const bool aligned = ((g.w % VEC) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+    const int groups = (g.w + VEC - 1) / VEC;
+    for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+        const int x0 = gi * VEC;
+        T in[VEC], out[VEC];
+        if (aligned) {
+            const uint4 q = yam_ld_stream(reinterpret_cast<const uint4*>(srow + x0));
+            *reinterpret_cast<uint4*>(in) = q;
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; i++) in[i] = (x0 + i < g.w) ? srow[x0 + i] : (T)0;
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; i++) {
+            const int x = x0 + i;
+            const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+            int tx1 = (int)floorf(txf);
+            const float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.0f, xa);
+            const int tx2 = min(tx1 + 1, g.tiles_x - 1);
+            tx1 = max(tx1, 0);
+            const int v = in[i];
+            const float l11 = (float)__ldg(lrow1 + (int64_t)tx1 * BINS + v);
+            const float l12 = (float)__ldg(lrow1 + (int64_t)tx2 * BINS + v);
+            const float l21 = (float)__ldg(lrow2 + (int64_t)tx1 * BINS + v);
+            const float l22 = (float)__ldg(lrow2 + (int64_t)tx2 * BINS + v);
+            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+            out[i] = (T)yam_rint_sat(res, HI);
+        }
+        if (aligned) {
+            yam_st_stream(reinterpret_cast<uint4*>(drow + x0), *reinterpret_cast<const uint4*>(out));
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; i++)
+                if (x0 + i < g.w) drow[x0 + i] = out[i];
+        }
+    }
+}
+
+int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
+              unsigned long long* hist) {
+    const int bins = dtype == YAM_U8 ? 256 : kBins16;
+    YAM_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * bins * n, ctx->stream));
+    if (dtype == YAM_U8) {
+        const int64_t frame_px = h * w;
+        int64_t bx = (frame_px / 16 + 255) / 256;
+        int64_t cap = (int64_t)ctx->num_sms * 8 / n;
+        if (cap < 1) cap = 1;
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        hist8_kernel<<<dim3((unsigned)bx, 1, (unsigned)n), 256, 0, ctx->stream>>>((const uint8_t*)src, frame_px, hist);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            YAM_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+            attr_set = true;
+        }
+        int64_t parts = ctx->num_sms / n;
+        if (parts < 1) parts = 1;
+        if (parts > h) parts = h;
+        hist16_kernel<<<dim3((unsigned)parts, 1, (unsigned)n), kHistThreads, kSmem16, ctx->stream>>>(
+            (const uint16_t*)src, (int)h, (int)w, hist);
+    }
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype, uint64_t* hist_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && hist_dev && n > 0 && h > 0 && w > 0 && n <= 65535, "histogram: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "histogram: unsupported dtype %d", dtype);
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "histogram: image side too large");
+    return hist_into(ctx, src, n, h, w, dtype, (unsigned long long*)hist_dev);
+}
+
+int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+                       double maxval, int32_t* thresh_dev, int32_t* thresh_host) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && n > 0 && h > 0 && w > 0 && n <= 65535, "otsu: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "otsu: unsupported dtype %d", dtype);
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "otsu: image side too large");
+    const int bins = dtype == YAM_U8 ? 256 : kBins16;
+    const size_t hist_bytes = sizeof(unsigned long long) * bins * n;
+    void* scratch = nullptr;
+    if (int rc = yam_scratch(ctx, hist_bytes + sizeof(int32_t) * n + 256, &scratch)) return rc;
+    unsigned long long* hist = (unsigned long long*)scratch;
+    int32_t* t_dev = thresh_dev ? thresh_dev : (int32_t*)((char*)scratch + yam_align_up(hist_bytes, 256));
+    if (int rc = hist_into(ctx, src, n, h, w, dtype, hist)) return rc;
+    // scan: host for few frames of 16-bit bins (sequential fp64 recurrence), device otherwise
+    const bool host_scan = (dtype == YAM_U16 && n < 8);
+    if (host_scan) {
+        void* pinned = nullptr;
+        if (int rc = yam_pinned(ctx, hist_bytes + sizeof(int32_t) * n, &pinned)) return rc;
+        YAM_CUDA(cudaMemcpyAsync(pinned, hist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        YAM_CUDA(cudaStreamSynchronize(ctx->stream));
+        int32_t* t_host = (int32_t*)((char*)pinned + hist_bytes);
+        for (int64_t f = 0; f < n; f++) t_host[f] = yam_host_otsu((const uint64_t*)pinned + f * bins, bins);
+        YAM_CUDA(cudaMemcpyAsync(t_dev, t_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (thresh_host) memcpy(thresh_host, t_host, sizeof(int32_t) * n);
+    } else {
+        otsu_scan_kernel<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(hist, bins, n, t_dev);
+        YAM_LAUNCHED(ctx);
+    }
+    if (dst) {
+        if (int rc = yam_threshold_dev(ctx, src, dst, n, h * w, dtype, t_dev, maxval)) return rc;
+    }
+    if (thresh_host && !host_scan) {
+        YAM_CUDA(cudaMemcpyAsync(thresh_host, t_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        YAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return YAM_OK;
+}
+
+int yam_equalize_hist(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && n <= 65535, "equalize_hist: bad arguments");
+    const size_t hist_bytes = sizeof(unsigned long long) * 256 * n;
+    void* scratch = nullptr;
+    if (int rc = yam_scratch(ctx, hist_bytes + 256 * n, &scratch)) return rc;
+    unsigned long long* hist = (unsigned long long*)scratch;
+    uint8_t* luts = (uint8_t*)scratch + hist_bytes;
+    if (int rc = hist_into(ctx, src, n, h, w, YAM_U8, hist)) return rc;
+    equalize_lut_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(hist, h * w, luts);
+    YAM_LAUNCHED(ctx);
+    const int64_t frame_px = h * w;
+    int64_t bx = (frame_px / 16 + 255) / 256;
+    int64_t cap = (int64_t)ctx->num_sms * 8 / n;
+    if (cap < 1) cap = 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    gather_lut8_kernel<<<dim3((unsigned)bx, 1, (unsigned)n), 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst,
+                                                                                  frame_px, luts);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+              double clip_limit, int tiles_x, int tiles_y) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && src != dst && n > 0 && h > 0 && w > 0 && n <= 65535, "clahe: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "clahe: unsupported dtype %d", dtype);
+    YAM_REQUIRE(tiles_x >= 1 && tiles_y >= 1 && tiles_x <= 256 && tiles_y <= 256, "clahe: bad tile grid %dx%d", tiles_x, tiles_y);
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "clahe: image side too large");
+    const int bins = dtype == YAM_U8 ? 256 : kBins16;
+    // cv2: pad right/bottom (REFLECT_101) when either side is not divisible — both sides get padded
+    int64_t pw = w, ph = h;
+    if (w % tiles_x || h % tiles_y) {
+        pw = w + (tiles_x - w % tiles_x);
+        ph = h + (tiles_y - h % tiles_y);
+    }
+    ClaheGeom g;
+    g.h = (int)h;
+    g.w = (int)w;
+    g.tiles_x = tiles_x;
+    g.tiles_y = tiles_y;
+    g.tw = (int)(pw / tiles_x);
+    g.th = (int)(ph / tiles_y);
+    const long long area = (long long)g.tw * g.th;
+    YAM_REQUIRE(area < (1ll << 31), "clahe: tile area too large");
+    g.lut_scale = (float)(bins - 1) / (float)area;
+    g.clip = 0;
+    if (clip_limit > 0) {
+        int c = (int)(clip_limit * (double)area / bins);
+        g.clip = c < 1 ? 1 : c;
+    }
+    g.inv_tw = 1.0f / (float)g.tw;
+    g.inv_th = 1.0f / (float)g.th;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y;
+    const size_t lut_bytes = (size_t)n * tiles * bins * yam_dtype_size(dtype);
+    if (dtype == YAM_U16) {
+        // frames are processed in chunks so the LUT set of a chunk (tiles x 128 KiB per frame) stays
+        // L2-resident between the LUT kernel and the apply kernel, and scratch stays bounded.
+        const size_t lut_frame = (size_t)tiles * kBins16 * sizeof(uint16_t);
+        int64_t chunk = (int64_t)((64u << 20) / lut_frame);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;
+        const int slots = ctx->num_sms;
+        const size_t ovf_bytes = (size_t)slots * kBins16 * sizeof(uint32_t);
+        const size_t luts_bytes = yam_align_up(lut_frame * chunk, 256);
+        void* scratch = nullptr;
+        if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes, &scratch)) return rc;
+        uint16_t* luts = (uint16_t*)scratch;
+        uint32_t* ovf = (uint32_t*)((char*)scratch + luts_bytes);
+        // the kernel restores zeros after use, but scratch is shared with other ops: clear it
+        YAM_CUDA(cudaMemsetAsync(ovf, 0, ovf_bytes, ctx->stream));
+        static bool attr_set = false;
+        if (!attr_set) {
+            YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+            attr_set = true;
+        }
+        const int64_t frame_px = h * w;
+        for (int64_t f0 = 0; f0 < n; f0 += chunk) {
+            const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
+            const uint16_t* s_ptr = (const uint16_t*)src + f0 * frame_px;
+            uint16_t* d_ptr = (uint16_t*)dst + f0 * frame_px;
+            const int64_t total_tiles = tiles * nf;
+            const unsigned gridx = (unsigned)(total_tiles < slots ? total_tiles : slots);
+            clahe_lut16_kernel<<<gridx, kHistThreads, kSmem16, ctx->stream>>>(s_ptr, g, (int)nf, ovf, luts);
+            YAM_LAUNCHED(ctx);
+            dim3 grid((unsigned)h, 1, (unsigned)nf);
+            clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, luts);
+            YAM_LAUNCHED(ctx);
+        }
+    } else {
+        void* scratch = nullptr;
+        if (int rc = yam_scratch(ctx, lut_bytes, &scratch)) return rc;
+        uint8_t* luts = (uint8_t*)scratch;
+        clahe_lut8_kernel<<<dim3((unsigned)tiles, 1, (unsigned)n), 256, 0, ctx->stream>>>((const uint8_t*)src, g, luts);
+        YAM_LAUNCHED(ctx);
+        dim3 grid((unsigned)h, 1, (unsigned)n);
+        clahe_apply_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, g, luts);
+        YAM_LAUNCHED(ctx);
+    }
+    return YAM_OK;
+}
+
+}  // extern "C"

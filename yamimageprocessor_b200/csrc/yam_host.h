@@ -1,0 +1,11 @@
+// Host-side parameter preparation shared by the .cu translation units.
+#pragma once
+#include <stdint.h>
+
+#define YAM_MAX_TAPS 127  // adaptive threshold block size goes to 101 (ui/control_metadata.py:301-309)
+#define YAM_MAX_SE 31     // morphology kernel_size 1..31 (ui/control_metadata.py:557-676)
+
+void yam_host_gaussian_taps(int k, double sigma, double* out);
+void yam_host_fixed_taps(const double* kf, int k, int bits, int64_t* out);
+void yam_host_structuring_element(int shape, int k, uint8_t* out);
+int yam_host_otsu(const uint64_t* h, int bins);
