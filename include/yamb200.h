@@ -65,7 +65,8 @@ const char* yam_last_error(void);
 int yam_device_count(void);
 int yam_ctx_create(int device, yam_ctx** out);
 int yam_ctx_destroy(yam_ctx* ctx);
-/* stream: a cudaStream_t (NULL = the context's own non-blocking stream) */
+/* stream: a cudaStream_t; NULL is CUDA's legacy default stream. A new context starts on its own
+ * non-blocking stream. */
 int yam_ctx_set_stream(yam_ctx* ctx, void* stream);
 int yam_ctx_synchronize(yam_ctx* ctx);
 /* counts kernel launches issued through this context since the last reset (bench "gpu_launches") */

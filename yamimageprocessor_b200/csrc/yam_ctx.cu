@@ -82,7 +82,8 @@ int yam_ctx_destroy(yam_ctx* ctx) {
 
 int yam_ctx_set_stream(yam_ctx* ctx, void* stream) {
     YAM_REQUIRE(ctx != nullptr, "ctx is NULL");
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    // a NULL handle is CUDA's legacy default stream (what torch reports for its default stream)
+    ctx->stream = (cudaStream_t)stream;
     return YAM_OK;
 }
 

@@ -292,7 +292,7 @@ template <typename T>
 int morph_typed(yam_ctx* ctx, const T* src, T* dst, int64_t n, int64_t h, int64_t w, int op, int shape,
                 int k, int iterations) {
     const int a = k / 2;
-    bool rect = (shape == YAM_SHAPE_RECT) || k <= 2;
+    bool rect = (shape == YAM_SHAPE_RECT);
     uint8_t se_bytes[YAM_MAX_SE * YAM_MAX_SE];
     SeRows se;
     if (!rect) {
