@@ -1,0 +1,177 @@
+"""Step name -> device operator table.
+
+Keys are the step names the reference uses (they enter the ``pipeline_cache`` signatures):
+preprocessing module identifiers (``modules/preprocessing.py:46,66,89,113,134``), segmentation
+method names (``processing/segmentation_pipeline.py:84-184``) and the extraction name
+``Region Properties`` (``processing/extraction_pipeline.py:77-127``), plus the north_star ops the
+reference lacks (``CLAHE``, ``BoxFilter``, ``HistogramEqualization``, ``ConnectedComponents``).
+
+Every function takes ``(backend, tensor, params)`` with a CUDA tensor shaped ``(h, w)``,
+``(n, h, w)`` (stack, processed per frame like ``_apply_slice_wise``) or ``(h, w, 3)`` BGR and
+returns a CUDA tensor.  Parameter names and defaults follow the reference call sites.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, Mapping
+
+import numpy as np
+
+from ..backend import Backend
+from .._lib import MORPH_CLOSE, MORPH_DILATE, MORPH_ERODE, MORPH_OPEN
+
+
+class UnsupportedOnDevice(NotImplementedError):
+    """Raised for inputs/parameters the hot path does not cover (there is no CPU fallback)."""
+
+
+def _is_colour(t) -> bool:
+    return t.dim() == 3 and t.shape[-1] in (3, 4)
+
+
+def _gray(be: Backend, t):
+    """Preprocessor.to_grayscale (core/segmentation.py:47-48): BGR2GRAY when 3-D colour."""
+    return be.bgr2gray(t) if _is_colour(t) else t
+
+
+def _plane_only(t, name: str):
+    if _is_colour(t):
+        raise UnsupportedOnDevice(
+            f"{name}: colour input is outside the GPU hot path; run Grayscale first (single-channel planes only)"
+        )
+    return t
+
+
+def grayscale(be: Backend, t, p: Mapping[str, Any]):
+    return _gray(be, t)
+
+
+def brightness_contrast(be: Backend, t, p):
+    alpha = float(p.get("alpha", 1.0))
+    if alpha <= 0:
+        raise ValueError("Alpha must be > 0")  # modules/preprocessing.py:76
+    return be.convert_scale_abs(t, alpha, float(p.get("beta", 0)))
+
+
+def gamma(be: Backend, t, p):
+    g = float(p.get("gamma", 1.0))
+    if g <= 0:
+        raise ValueError("Gamma must be > 0")  # modules/preprocessing.py:98
+    inv = 1.0 / g
+    table = np.array([(i / 255.0) ** inv * 255 for i in range(256)]).astype("uint8")
+    return be.lut_u8(t, table)  # uint8 only, like cv2.LUT
+
+
+def intensity_normalization(be: Backend, t, p):
+    return be.normalize_minmax(_plane_only(t, "IntensityNormalization"), float(p.get("alpha", 0)), float(p.get("beta", 255)))
+
+
+def noise_reduction(be: Backend, t, p):
+    method = str(p.get("method", "Gaussian"))
+    ksize = int(p.get("ksize", 5))
+    t = _plane_only(t, "NoiseReduction")
+    if method == "Gaussian":
+        return be.gaussian(t, ksize, 0.0)
+    if method == "Median":
+        return be.median(t, ksize)
+    if method == "Bilateral":
+        raise UnsupportedOnDevice("NoiseReduction(method='Bilateral') is outside the GPU hot path")
+    return t  # unknown method: identity, like modules/preprocessing.py:150
+
+
+def clahe(be: Backend, t, p):
+    grid = (int(p.get("tile_grid_x", 8)), int(p.get("tile_grid_y", 8)))
+    return be.clahe(_plane_only(t, "CLAHE"), float(p.get("clip_limit", 2.0)), grid)
+
+
+def box_filter(be: Backend, t, p):
+    return be.box(_plane_only(t, "BoxFilter"), int(p.get("ksize", 3)))
+
+
+def histogram_equalization(be: Backend, t, p):
+    return be.equalize_hist(_plane_only(t, "HistogramEqualization"))
+
+
+def global_threshold(be: Backend, t, p):
+    return be.threshold(_gray(be, t), float(p.get("threshold", 127)), 255)
+
+
+def otsu(be: Backend, t, p):
+    return be.otsu_threshold(_gray(be, t), 255)[1]
+
+
+def adaptive(be: Backend, t, p):
+    return be.adaptive_threshold(_gray(be, t), int(p.get("block_size", 11)), float(p.get("C", 2)))
+
+
+def _morph(op: int) -> Callable:
+    def run(be: Backend, t, p):
+        return be.morph(
+            _plane_only(t, "morphology"),
+            op,
+            str(p.get("kernel_shape", "Rectangular")),
+            int(p.get("kernel_size", 3)),
+            int(p.get("iterations", 1)),
+        )
+
+    return run
+
+
+def _as_mask_u8(be: Backend, t):
+    import torch
+
+    if t.dtype == torch.uint8:
+        return t
+    if t.dtype == torch.uint16:
+        return be.convert_scale_abs(t, 1.0, 0.0)  # saturates: non-zero stays non-zero
+    raise UnsupportedOnDevice(f"ConnectedComponents: mask dtype {t.dtype} not supported")
+
+
+def connected_components(be: Backend, t, p):
+    return be.ccl_label(_as_mask_u8(be, _plane_only(t, "ConnectedComponents")))[0]
+
+
+def region_properties_labels(be: Backend, t, p):
+    """Otsu -> 8-connected labels (core/extraction.py:58-60); the table comes from region_table()."""
+    mask = be.otsu_threshold(_gray(be, t), 255)[1]
+    return be.ccl_label(_as_mask_u8(be, mask))[0]
+
+
+DEVICE_STEPS: Dict[str, Callable] = {
+    "Grayscale": grayscale,
+    "BrightnessContrast": brightness_contrast,
+    "Gamma": gamma,
+    "IntensityNormalization": intensity_normalization,
+    "NoiseReduction": noise_reduction,
+    "CLAHE": clahe,
+    "BoxFilter": box_filter,
+    "HistogramEqualization": histogram_equalization,
+    "Global": global_threshold,
+    "Otsu": otsu,
+    "Adaptive": adaptive,
+    "Opening": _morph(MORPH_OPEN),
+    "Closing": _morph(MORPH_CLOSE),
+    "Dilation": _morph(MORPH_DILATE),
+    "Erosion": _morph(MORPH_ERODE),
+    "ConnectedComponents": connected_components,
+    "Region Properties": region_properties_labels,
+}
+
+
+def region_table(be: Backend, labels, intensity=None, n_labels=None) -> Dict[str, np.ndarray]:
+    """Per-region table for a single labelled frame, columns in skimage semantics
+    (core/extraction.py:70-87: region_index = label, centroid = (row, col)); bbox is half-open."""
+    from ..backend import props_table
+
+    if n_labels is None:
+        n_labels = int(labels.max().item()) if labels.numel() else 0
+    props = be.to_host(be.region_props(labels, intensity, n_labels))
+    table = props_table(props)
+    table["region_index"] = np.arange(1, n_labels + 1, dtype=np.int64)
+    table["centroid"] = np.stack([table["centroid_row"], table["centroid_col"]], axis=1) if n_labels else np.zeros((0, 2))
+    if intensity is None:
+        table.pop("mean_intensity", None)
+        table.pop("sum_intensity", None)
+    return table
+
+
+__all__ = ["DEVICE_STEPS", "UnsupportedOnDevice", "region_table"]

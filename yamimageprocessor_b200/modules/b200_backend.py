@@ -1,0 +1,165 @@
+"""Plugin package for the reference application: GPU-backed processing modules.
+
+Add ``"yamimageprocessor_b200.modules"`` to ``AppConfiguration.plugin_packages``
+(``core/app_core.py:55``); ``AppCore._discover_plugins`` (``:680-749``) imports this module and
+calls ``register_module(app_core)``, which registers one ``ModuleBase`` subclass per operator.
+
+* Identifiers and parameter names are the reference's own (``Grayscale``, ``NoiseReduction``,
+  ``IntensityNormalization``, ... ; ``modules/preprocessing.py:46-134``) so ``pipeline_cache``
+  signatures are unchanged; ops the reference lacks get new identifiers.
+* ``pipeline_execution_metadata()`` says ``requires_gpu=True`` so ``PipelineManager.apply`` routes
+  the step to a configured ``GpuExecutor`` (``processing/pipeline_manager.py:448-454``) ...
+* ... and ``process()`` ITSELF runs on the GPU, because ``PipelineCache.compute``
+  (``processing/pipeline_cache.py:379,496``) and ``run_enabled_stages`` (``ui/unified.py:558``)
+  call ``step.apply`` directly and never see the executor.  There is no CPU path in either.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Mapping
+
+import numpy as np
+
+from ..host.params import MODULE_PARAMS, ParamSpec
+from ..host.plugin import binding
+
+ModuleBase, ModuleMetadata, ModuleStage, StepExecutionMetadata, _PipelineStep = binding()
+
+_EXECUTOR = None
+
+
+def _executor():
+    global _EXECUTOR
+    if _EXECUTOR is None:
+        from ..host.executor import B200Executor
+
+        _EXECUTOR = B200Executor()
+    return _EXECUTOR
+
+
+class _GpuModule(ModuleBase):
+    """Common behaviour: parameter table, GPU execution hints, GPU ``process``."""
+
+    IDENTIFIER = ""
+    TITLE = ""
+    STAGE = ModuleStage.PREPROCESSING
+    DESCRIPTION = ""
+    MENU = ("Pre-Processing",)
+
+    def _build_metadata(self):
+        return ModuleMetadata(
+            identifier=self.IDENTIFIER,
+            title=self.TITLE,
+            stage=self.STAGE,
+            description=self.DESCRIPTION,
+            menu_path=self.MENU,
+        )
+
+    def parameter_metadata(self) -> Mapping[str, ParamSpec]:
+        return MODULE_PARAMS.get(self.IDENTIFIER, {})
+
+    def _load_parameter_metadata(self):  # the reference's ModuleBase calls this name
+        return self.parameter_metadata()
+
+    def pipeline_execution_metadata(self):
+        return StepExecutionMetadata(supports_inplace=False, requires_gpu=True)
+
+    def process(self, image: np.ndarray, **kwargs: Any) -> np.ndarray:
+        params = self.sanitize_parameters(kwargs)
+        ex = _executor()
+        be = ex.backend
+        out = ex.run_on_device(self.IDENTIFIER, be.to_device(np.asarray(image)), params)
+        return be.to_host(out)
+
+
+def _module(identifier: str, title: str, stage, description: str, menu=("Pre-Processing",)):
+    return type(
+        identifier.replace(" ", "") + "Module",
+        (_GpuModule,),
+        {"IDENTIFIER": identifier, "TITLE": title, "STAGE": stage, "DESCRIPTION": description, "MENU": menu,
+         "__doc__": description},
+    )
+
+
+GrayscaleModule = _module("Grayscale", "Toggle Greyscale", ModuleStage.PREPROCESSING,
+                          "BGR -> gray (cv2.cvtColor BGR2GRAY, modules/preprocessing.py:52-55).")
+BrightnessContrastModule = _module("BrightnessContrast", "Brightness / Contrast", ModuleStage.PREPROCESSING,
+                                   "cv2.convertScaleAbs (modules/preprocessing.py:72-78).")
+GammaCorrectionModule = _module("Gamma", "Gamma Correction", ModuleStage.PREPROCESSING,
+                                "256-entry LUT (modules/preprocessing.py:95-102).")
+IntensityNormalizationModule = _module("IntensityNormalization", "Intensity Normalization", ModuleStage.PREPROCESSING,
+                                       "cv2.normalize NORM_MINMAX (modules/preprocessing.py:119-123).")
+NoiseReductionModule = _module("NoiseReduction", "Noise Reduction", ModuleStage.PREPROCESSING,
+                               "Gaussian / median denoising (modules/preprocessing.py:140-150).")
+ClaheModule = _module("CLAHE", "CLAHE", ModuleStage.PREPROCESSING,
+                      "cv2.createCLAHE(clip_limit,(tile_grid_x,tile_grid_y)).apply (north_star op).")
+BoxFilterModule = _module("BoxFilter", "Box Filter", ModuleStage.PREPROCESSING,
+                          "cv2.blur(k,k), odd k (north_star op).")
+HistogramEqualizationModule = _module("HistogramEqualization", "Histogram Equalization", ModuleStage.PREPROCESSING,
+                                      "cv2.equalizeHist, uint8 (core/preprocessing.py:74-79).")
+_SEG = ("Segmentation",)
+GlobalThresholdModule = _module("Global", "Global Threshold", ModuleStage.SEGMENTATION,
+                                "cv2.threshold BINARY (core/segmentation.py:140-143).", _SEG)
+OtsuThresholdModule = _module("Otsu", "Otsu Threshold", ModuleStage.SEGMENTATION,
+                              "cv2.threshold BINARY+OTSU (core/segmentation.py:145-148).", _SEG)
+AdaptiveThresholdModule = _module("Adaptive", "Adaptive Threshold", ModuleStage.SEGMENTATION,
+                                  "cv2.adaptiveThreshold GAUSSIAN_C (core/segmentation.py:91-94).", _SEG)
+OpeningModule = _module("Opening", "Opening", ModuleStage.SEGMENTATION,
+                        "cv2.morphologyEx OPEN (core/segmentation.py:264-275).", _SEG)
+ClosingModule = _module("Closing", "Closing", ModuleStage.SEGMENTATION,
+                        "cv2.morphologyEx CLOSE (core/segmentation.py:277-288).", _SEG)
+DilationModule = _module("Dilation", "Dilation", ModuleStage.SEGMENTATION,
+                         "cv2.dilate (core/segmentation.py:290-301).", _SEG)
+ErosionModule = _module("Erosion", "Erosion", ModuleStage.SEGMENTATION,
+                        "cv2.erode (core/segmentation.py:303-314).", _SEG)
+ConnectedComponentsModule = _module("ConnectedComponents", "Connected Components", ModuleStage.SEGMENTATION,
+                                    "8-connected labels in raster-first order (core/segmentation.py:108, core/extraction.py:60).", _SEG)
+RegionPropertiesModule = _module("Region Properties", "Region Properties", ModuleStage.ANALYSIS,
+                                 "Otsu -> label -> per-region table (core/extraction.py:57-87).", ("Extraction",))
+
+MODULE_CLASSES = (
+    GrayscaleModule,
+    BrightnessContrastModule,
+    GammaCorrectionModule,
+    IntensityNormalizationModule,
+    NoiseReductionModule,
+    ClaheModule,
+    BoxFilterModule,
+    HistogramEqualizationModule,
+    GlobalThresholdModule,
+    OtsuThresholdModule,
+    AdaptiveThresholdModule,
+    OpeningModule,
+    ClosingModule,
+    DilationModule,
+    ErosionModule,
+    ConnectedComponentsModule,
+    RegionPropertiesModule,
+)
+
+
+def register_module(app_core) -> None:
+    """Plugin entry point (same contract as modules/preprocessing.py:270-274)."""
+    for cls in MODULE_CLASSES:
+        app_core.register_module(cls)
+
+
+def region_properties_data(image: np.ndarray) -> Dict[str, np.ndarray]:
+    """GPU counterpart of core/extraction.py:70-87 for the columns on the hot path:
+    region_index, area, centroid (row, col), bbox (half-open) and mean_intensity (extension)."""
+    from ..host.steps import region_table
+
+    ex = _executor()
+    be = ex.backend
+    t = be.to_device(np.asarray(image))
+    gray = be.bgr2gray(t)
+    labels = ex.run_on_device("Region Properties", gray, {})
+    return region_table(be, labels, gray if gray.dtype in _intensity_dtypes() else None)
+
+
+def _intensity_dtypes():
+    import torch
+
+    return (torch.uint8, torch.uint16)
+
+
+__all__ = [cls.__name__ for cls in MODULE_CLASSES] + ["MODULE_CLASSES", "register_module", "region_properties_data"]
