@@ -1,0 +1,82 @@
+"""Oracle vs fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD / "reference_outputs.npz")
+
+
+@pytest.fixture(scope="module")
+def meta():
+    return json.loads((GOLD / "reference_meta.json").read_text())
+
+
+def eq(a, b, what=""):
+    assert a.dtype == b.dtype and a.shape == b.shape, what
+    assert int((a != b).sum()) == 0, what
+
+
+@pytest.mark.parametrize("tag", ["u8", "u16"])
+def test_preprocessing_modules(gold, tag):
+    bgr, gray, noise = gold[f"in_bgr_{tag}"], gold[f"in_gray_{tag}"], gold[f"in_noise_{tag}"]
+    dt = gray.dtype.type
+    eq(O.bgr2gray(bgr), gold[f"grayscale_{tag}"], "Grayscale")
+    for k in (3, 5, 11, 15):
+        eq(O.gaussian(noise, k, 0.0), gold[f"gauss{k}_{tag}"], f"NoiseReduction Gaussian {k}")
+    for k in (3, 5):
+        eq(O.median(noise, k), gold[f"median{k}_{tag}"], f"NoiseReduction Median {k}")
+    eq(O.normalize_minmax(np.maximum(gray, dt(9)), 0, 255), gold[f"normalize_{tag}"], "IntensityNormalization")
+    eq(O.normalize_minmax(np.maximum(gray, dt(9)), 10, 200), gold[f"normalize_10_200_{tag}"], "IntensityNormalization 10..200")
+    eq(O.convert_scale_abs(noise, 1.5, -20), gold[f"brightness_{tag}"], "BrightnessContrast")
+    eq(O.clahe(gray, 2.0, (8, 8)), gold[f"clahe_{tag}"], "CLAHE")
+    eq(O.clahe(gray, 4.0, (3, 5)), gold[f"clahe_4_3x5_{tag}"], "CLAHE 3x5")
+    eq(O.box(noise, 5), gold[f"box5_{tag}"], "box")
+
+
+@pytest.mark.parametrize("tag", ["u8", "u16"])
+def test_segmentation_functions(gold, tag):
+    bgr, gray, noise = gold[f"in_bgr_{tag}"], gold[f"in_gray_{tag}"], gold[f"in_noise_{tag}"]
+    eq(O.otsu_threshold(gray, 255)[1], gold[f"otsu_{tag}"], "otsu")
+    eq(O.otsu_threshold(O.bgr2gray(bgr), 255)[1], gold[f"otsu_bgr_{tag}"], "otsu on colour")
+    eq(O.threshold_binary(gray, 100, 255), gold[f"global100_{tag}"], "global")
+    for shape in ("Rectangular", "Elliptical", "Cross"):
+        for k, it in ((3, 1), (5, 2)):
+            key = f"{shape.lower()}_{k}_{it}_{tag}"
+            eq(O.morph_open(noise, shape, k, it), gold[f"open_{key}"], f"open {key}")
+            eq(O.morph_close(noise, shape, k, it), gold[f"close_{key}"], f"close {key}")
+            eq(O.dilate(noise, shape, k, it), gold[f"dilate_{key}"], f"dilate {key}")
+            eq(O.erode(noise, shape, k, it), gold[f"erode_{key}"], f"erode {key}")
+
+
+def test_u8_only(gold):
+    eq(O.lut_u8(gold["in_noise_u8"], O.gamma_table(2.2)), gold["gamma22_u8"], "Gamma")
+    eq(O.adaptive_threshold(gold["in_gray_u8"], 11, 2), gold["adaptive_11_2_u8"], "Adaptive 11,2")
+    eq(O.adaptive_threshold(gold["in_gray_u8"], 31, -3), gold["adaptive_31_m3_u8"], "Adaptive 31,-3")
+    eq(O.adaptive_threshold(O.bgr2gray(gold["in_bgr_u8"]), 11, 2), gold["adaptive_bgr_u8"], "Adaptive colour")
+    eq(O.equalize_hist(gold["in_gray_u8"]), gold["equalize_u8"], "equalizeHist")
+
+
+def test_connected_components(gold, meta):
+    n, lab = O.ccl_label(gold["ccl_mask_u8"])
+    assert n == meta["ccl_count"]
+    eq(lab, O.canonicalise_labels(gold["ccl_labels_cv2"]), "labels (canonical)")
+    props = O.region_props(lab, gold["in_gray_u8"], n)
+    stats, cent, cvlab = gold["ccl_stats_cv2"], gold["ccl_centroids_cv2"], gold["ccl_labels_cv2"]
+    canon = O.canonicalise_labels(cvlab)
+    for l in range(1, stats.shape[0]):
+        ys, xs = np.nonzero(cvlab == l)
+        i = canon[ys[0], xs[0]] - 1
+        assert props["area"][i] == stats[l, 4]
+        assert tuple(props["bbox"][i]) == (stats[l, 1], stats[l, 0], stats[l, 1] + stats[l, 3], stats[l, 0] + stats[l, 2])
+        assert abs(props["centroid_col"][i] - cent[l, 0]) < 1e-9 and abs(props["centroid_row"][i] - cent[l, 1]) < 1e-9

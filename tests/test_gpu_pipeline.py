@@ -1,0 +1,190 @@
+"""GPU parity through the reference-facing boundary: golden fixtures made by the unmodified
+reference, the plugin's process() path, the GpuExecutor path, and size-independent properties at
+BASELINE sizes."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+from yamimageprocessor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD / "reference_outputs.npz")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from yamimageprocessor_b200.modules import b200_backend as plugin
+
+    return {cls().metadata.identifier: cls() for cls in plugin.MODULE_CLASSES}
+
+
+def eq(a, b, what=""):
+    assert a.dtype == b.dtype and a.shape == b.shape, f"{what}: {a.dtype}{a.shape} vs {b.dtype}{b.shape}"
+    assert int((a != b).sum()) == 0, what
+
+
+@pytest.mark.parametrize("tag", ["u8", "u16"])
+def test_plugin_process_matches_reference_outputs(backend, gold, mods, tag):
+    """ModuleBase.process of the GPU plugin vs the reference modules' outputs (same names, same params)."""
+    bgr, gray, noise = gold[f"in_bgr_{tag}"], gold[f"in_gray_{tag}"], gold[f"in_noise_{tag}"]
+    dt = gray.dtype.type
+    eq(mods["Grayscale"].process(bgr), gold[f"grayscale_{tag}"], "Grayscale")
+    assert mods["Grayscale"].process(gray).shape == gray.shape
+    for k in (3, 5, 11, 15):
+        eq(mods["NoiseReduction"].process(noise, method="Gaussian", ksize=k), gold[f"gauss{k}_{tag}"], f"Gaussian {k}")
+    for k in (3, 5):
+        eq(mods["NoiseReduction"].process(noise, method="Median", ksize=k), gold[f"median{k}_{tag}"], f"Median {k}")
+    eq(mods["IntensityNormalization"].process(np.maximum(gray, dt(9)), alpha=0, beta=255), gold[f"normalize_{tag}"], "normalize")
+    eq(mods["IntensityNormalization"].process(np.maximum(gray, dt(9)), alpha=10, beta=200), gold[f"normalize_10_200_{tag}"], "normalize 10..200")
+    eq(mods["BrightnessContrast"].process(noise, alpha=1.5, beta=-20), gold[f"brightness_{tag}"], "BrightnessContrast")
+    eq(mods["CLAHE"].process(gray, clip_limit=2.0, tile_grid_x=8, tile_grid_y=8), gold[f"clahe_{tag}"], "CLAHE")
+    eq(mods["CLAHE"].process(gray, clip_limit=4.0, tile_grid_x=3, tile_grid_y=5), gold[f"clahe_4_3x5_{tag}"], "CLAHE 3x5")
+    eq(mods["BoxFilter"].process(noise, ksize=5), gold[f"box5_{tag}"], "BoxFilter")
+    eq(mods["Otsu"].process(gray), gold[f"otsu_{tag}"], "Otsu")
+    eq(mods["Otsu"].process(bgr), gold[f"otsu_bgr_{tag}"], "Otsu colour")
+    eq(mods["Global"].process(gray, threshold=100), gold[f"global100_{tag}"], "Global")
+    for shape in ("Rectangular", "Elliptical", "Cross"):
+        for k, it in ((3, 1), (5, 2)):
+            key = f"{shape.lower()}_{k}_{it}_{tag}"
+            kw = dict(kernel_shape=shape, kernel_size=k, iterations=it)
+            eq(mods["Opening"].process(noise, **kw), gold[f"open_{key}"], f"open {key}")
+            eq(mods["Closing"].process(noise, **kw), gold[f"close_{key}"], f"close {key}")
+            eq(mods["Dilation"].process(noise, **kw), gold[f"dilate_{key}"], f"dilate {key}")
+            eq(mods["Erosion"].process(noise, **kw), gold[f"erode_{key}"], f"erode {key}")
+
+
+def test_plugin_u8_only_ops_and_errors(backend, gold, mods):
+    eq(mods["Gamma"].process(gold["in_noise_u8"], gamma=2.2), gold["gamma22_u8"], "Gamma")
+    eq(mods["Adaptive"].process(gold["in_gray_u8"], block_size=11, C=2), gold["adaptive_11_2_u8"], "Adaptive")
+    eq(mods["Adaptive"].process(gold["in_gray_u8"], block_size=31, C=-3), gold["adaptive_31_m3_u8"], "Adaptive 31")
+    eq(mods["Adaptive"].process(gold["in_bgr_u8"], block_size=11, C=2), gold["adaptive_bgr_u8"], "Adaptive colour")
+    eq(mods["HistogramEqualization"].process(gold["in_gray_u8"]), gold["equalize_u8"], "equalizeHist")
+    with pytest.raises(ValueError, match="Gamma must be > 0"):
+        mods["Gamma"].process(gold["in_noise_u8"], gamma=0.0)  # coerced to 0.1 by the registry -> no error
+    with pytest.raises(NotImplementedError):
+        mods["NoiseReduction"].process(gold["in_noise_u8"], method="Bilateral", ksize=5)
+
+
+def test_connected_components_and_region_table_vs_cv2_golden(backend, gold, mods):
+    from yamimageprocessor_b200.modules.b200_backend import region_properties_data
+
+    meta = json.loads((GOLD / "reference_meta.json").read_text())
+    labels = mods["ConnectedComponents"].process(gold["ccl_mask_u8"])
+    eq(labels, O.canonicalise_labels(gold["ccl_labels_cv2"]), "labels")
+    assert labels.max() == meta["ccl_count"]
+    table = region_properties_data(gold["in_gray_u8"])  # Otsu -> label -> props, like core/extraction.py:70-87
+    stats, cent, cvlab = gold["ccl_stats_cv2"], gold["ccl_centroids_cv2"], gold["ccl_labels_cv2"]
+    canon = O.canonicalise_labels(cvlab)
+    assert table["region_index"].tolist() == list(range(1, meta["ccl_count"] + 1))
+    for l in range(1, stats.shape[0]):
+        ys, xs = np.nonzero(cvlab == l)
+        i = canon[ys[0], xs[0]] - 1
+        assert table["area"][i] == stats[l, 4]
+        assert tuple(table["bbox"][i]) == (stats[l, 1], stats[l, 0], stats[l, 1] + stats[l, 3], stats[l, 0] + stats[l, 2])
+        assert table["centroid"][i, 1] == pytest.approx(cent[l, 0], abs=1e-12)
+        assert table["centroid"][i, 0] == pytest.approx(cent[l, 1], abs=1e-12)
+        assert table["mean_intensity"][i] == pytest.approx(gold["in_gray_u8"][cvlab == l].mean(), rel=1e-12)
+
+
+def test_executor_through_pipeline_manager(backend, mods):
+    from yamimageprocessor_b200.host.executor import B200Executor
+    from yamimageprocessor_b200.host.pipeline import PipelineManager
+
+    frame = synth.nuclei(416, 512, seed=3)
+
+    def step(name, **p):
+        s = mods[name].create_pipeline_step()
+        s.enabled = True
+        s.params.update(p)
+        return s
+
+    ex = B200Executor(backend)
+    pm = PipelineManager([step("NoiseReduction", ksize=11), step("CLAHE"), step("Adaptive"),
+                          step("Opening", kernel_size=5), step("Closing", kernel_size=5),
+                          step("ConnectedComponents")], gpu_executor=ex)
+    before = frame.copy()
+    out = pm.apply(frame)
+    assert np.array_equal(frame, before), "input must not be mutated"
+    assert out.flags["C_CONTIGUOUS"] and out.dtype == np.int32
+    g = O.clahe(O.gaussian_fixed(frame, 11, 0.0), 2.0, (8, 8))
+    m = O.morph_close(O.morph_open(O.adaptive_threshold(g, 11, 2), "Rectangular", 5, 1), "Rectangular", 5, 1)
+    eq(out, O.ccl_label(m)[1], "chained pipeline")
+    assert ex.calls == ["NoiseReduction", "CLAHE", "Adaptive", "Opening", "Closing", "ConnectedComponents"]
+    # the reference's own manager calls execute() step by step: same result
+    ex2 = B200Executor(backend)
+    cur = frame
+    for s in pm.steps:
+        cur = ex2.execute(s, cur)
+    eq(cur, out, "step-by-step executor")
+    # a stack is processed plane by plane (per-frame statistics)
+    stack = np.stack([frame, synth.nuclei(416, 512, seed=4)])
+    pm2 = PipelineManager([step("NoiseReduction", ksize=5), step("Otsu")], gpu_executor=ex)
+    got = pm2.apply(stack)
+    want = np.stack([O.otsu_threshold(O.gaussian_fixed(p, 5, 0.0), 255)[1] for p in stack])
+    eq(got, want, "stack")
+
+
+# ---- BASELINE sizes: size-independent properties ---------------------------------------------------
+@pytest.mark.slow
+def test_full_size_segmentation_properties(backend):
+    h = w = 8192
+    frame = synth.nuclei(h, w, seed=2)
+    x = backend.to_device(frame)
+    m = backend.morph_open_close(backend.adaptive_threshold(x, 11, 2), 5, 1)
+    labels, counts = backend.ccl_label(m)
+    n = int(backend.to_host(counts)[0])
+    assert n == synth.expected_nuclei(h, w)  # one component per synthetic nucleus (99 225)
+    # open and close are idempotent
+    assert bool((backend.morph_open(backend.morph_open(m, "Rectangular", 5, 1), "Rectangular", 5, 1)
+                 == backend.morph_open(m, "Rectangular", 5, 1)).all())
+    # labels: background preserved, labels dense 1..n, sorted by first pixel
+    lab = backend.to_host(labels)
+    mh = backend.to_host(m)
+    assert np.array_equal(lab > 0, mh > 0)
+    first = np.full(n + 1, h * w, np.int64)
+    flat = lab.ravel()
+    idx = np.nonzero(flat)[0]
+    np.minimum.at(first, flat[idx], idx)
+    assert np.all(np.diff(first[1:]) > 0)
+    # region table: areas sum to the foreground, bbox contains centroid, intensity sums add up
+    props = backend.to_host(backend.region_props(labels, x, n))
+    assert int(props[:, 0].sum()) == int((mh > 0).sum())
+    assert int(props[:, 3].sum()) == int(frame[mh > 0].astype(np.int64).sum())
+    cy, cx = props[:, 1] / props[:, 0], props[:, 2] / props[:, 0]
+    assert np.all((cy >= props[:, 4]) & (cy < props[:, 6]) & (cx >= props[:, 5]) & (cx < props[:, 7]))
+    # a 1024^2 crop away from the borders labels identically up to numbering (oracle-checked)
+    crop = mh[1024:2048, 2048:3072]
+    n_c, lab_c = O.ccl_label(crop)
+    got_c = backend.to_host(backend.ccl_label(backend.to_device(np.ascontiguousarray(crop)))[0])
+    eq(got_c, lab_c, "crop labels")
+
+
+@pytest.mark.slow
+def test_full_size_preprocess_properties(backend):
+    h = w = 4096
+    frame = synth.nuclei(h, w, seed=1)
+    x = backend.to_device(frame)
+    g = backend.gaussian(x, 11, 0.0)
+    c = backend.clahe(g, 2.0, (8, 8))
+    hist = backend.to_host(backend.histogram(c))[0]
+    assert int(hist.sum()) == h * w                       # checksum of the histogram
+    t, mask = backend.otsu_threshold(c, 255)
+    assert int(backend.to_host(t)[0]) == O.otsu_from_hist(hist)
+    mk = backend.to_host(mask)
+    assert set(np.unique(mk).tolist()) <= {0, 255}
+    assert int((mk > 0).sum()) == int(hist[int(backend.to_host(t)[0]) + 1:].sum())
+    # oracle parity on a band of rows (Gaussian is local: rows away from the band edge agree)
+    band = frame[1000:1300]
+    eq(backend.to_host(g)[1005:1295], O.gaussian_fixed(band, 11, 0.0)[5:295], "gaussian band")
+    # CLAHE at full size against the oracle (tile 512^2, clip 8)
+    eq(backend.to_host(c), O.clahe(backend.to_host(g), 2.0, (8, 8)), "clahe 4096")

@@ -1,0 +1,105 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, ``torch.distributed``).
+
+* Time-lapse batches / file batches: frames are independent units (the reference itself treats
+  planes independently, ``processing/pipeline_manager.py:475-492``, and fans files out per process,
+  ``ui/segmentation.py:2519-2536``) -> contiguous frame blocks per rank, NO data-path collective;
+  only the per-frame region tables are gathered at the end.
+* Mosaic row strips (65536^2): contiguous row strips per rank with a halo of ``halo`` rows read
+  from the shared source (the memmap) so neighbourhood operators see the same pixels as the dense
+  run; global statistics (Otsu histogram, min/max) are all-reduced.
+
+The helpers are backend-agnostic (gloo on CPU in the tests, nccl on the GPU box).
+"""
+from __future__ import annotations
+
+from typing import Any, List, Sequence, Tuple
+
+import numpy as np
+
+
+def frame_block(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [start, stop) of frames for ``rank`` (sizes differ by at most one)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def row_strip(height: int, rank: int, world: int, halo: int = 0, align: int = 1) -> Tuple[int, int, int, int]:
+    """(core_start, core_stop, read_start, read_stop) rows of rank's strip; core rows are a multiple
+    of ``align`` (e.g. the CLAHE tile height) except possibly the last strip."""
+    units = (height + align - 1) // align
+    u0, u1 = frame_block(units, rank, world)
+    c0, c1 = min(u0 * align, height), min(u1 * align, height)
+    return c0, c1, max(0, c0 - halo), min(height, c1 + halo)
+
+
+def allreduce_histogram(hist: Any, group=None):
+    """Sum per-rank histograms (int64 tensor) across ranks — the one collective Otsu needs."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def gather_tables(local: Sequence[Any], group=None) -> List[Any]:
+    """Gather per-frame result objects from every rank in rank order (rank 0 gets the full list)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(local)
+    world = dist.get_world_size(group)
+    bucket: List[Any] = [None] * world
+    dist.all_gather_object(bucket, list(local), group=group)
+    out: List[Any] = []
+    for part in bucket:
+        out.extend(part)
+    return out
+
+
+def merge_label_strips(strips: Sequence[np.ndarray], counts: Sequence[int]) -> Tuple[np.ndarray, int]:
+    """Host-side cross-strip label merge (CPU reference for the multi-GPU CCL path).
+
+    ``strips`` are per-strip canonical label images (1..counts[i]) of vertically adjacent row
+    strips.  Labels are offset to be globally unique, components touching across a strip boundary
+    (8-connectivity) are united, and the result is renumbered in raster-first order.
+    """
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    total = int(offs[-1])
+    parent = np.arange(total + 1, dtype=np.int64)
+
+    def find(x: int) -> int:
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    glob = [np.where(s > 0, s.astype(np.int64) + offs[i], 0) for i, s in enumerate(strips)]
+    for i in range(len(glob) - 1):
+        up, down = glob[i][-1], glob[i + 1][0]
+        w = up.shape[0]
+        for dx in (-1, 0, 1):
+            a = up[max(0, -dx): w - max(0, dx)]
+            b = down[max(0, dx): w - max(0, -dx)]
+            both = (a > 0) & (b > 0)
+            for la, lb in set(zip(a[both].tolist(), b[both].tolist())):
+                ra, rb = find(la), find(lb)
+                if ra != rb:
+                    parent[max(ra, rb)] = min(ra, rb)
+    full = np.concatenate(glob, axis=0)
+    roots = np.array([find(i) for i in range(total + 1)], dtype=np.int64)
+    rooted = roots[full]
+    flat = rooted.ravel()
+    nz = np.nonzero(flat)[0]
+    if nz.size == 0:
+        return np.zeros(full.shape, np.int32), 0
+    uniq, first = np.unique(flat[nz], return_index=True)
+    order = np.argsort(nz[first], kind="stable")
+    remap = np.zeros(total + 1, np.int32)
+    remap[uniq[order]] = np.arange(1, len(uniq) + 1, dtype=np.int32)
+    return remap[rooted].astype(np.int32), int(len(uniq))
+
+
+__all__ = ["allreduce_histogram", "frame_block", "gather_tables", "merge_label_strips", "row_strip"]
