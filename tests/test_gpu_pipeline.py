@@ -69,8 +69,13 @@ def test_plugin_u8_only_ops_and_errors(backend, gold, mods):
     eq(mods["Adaptive"].process(gold["in_gray_u8"], block_size=31, C=-3), gold["adaptive_31_m3_u8"], "Adaptive 31")
     eq(mods["Adaptive"].process(gold["in_bgr_u8"], block_size=11, C=2), gold["adaptive_bgr_u8"], "Adaptive colour")
     eq(mods["HistogramEqualization"].process(gold["in_gray_u8"]), gold["equalize_u8"], "equalizeHist")
+    # the registry clamps gamma to >= 0.1 (ui/control_metadata.py), so process() never sees 0 ...
+    assert mods["Gamma"].process(gold["in_noise_u8"], gamma=0.0).shape == gold["in_noise_u8"].shape
+    # ... but the raw step function keeps the reference's check (modules/preprocessing.py:98)
+    from yamimageprocessor_b200.host.steps import DEVICE_STEPS
+
     with pytest.raises(ValueError, match="Gamma must be > 0"):
-        mods["Gamma"].process(gold["in_noise_u8"], gamma=0.0)  # coerced to 0.1 by the registry -> no error
+        DEVICE_STEPS["Gamma"](backend, backend.to_device(gold["in_noise_u8"]), {"gamma": 0.0})
     with pytest.raises(NotImplementedError):
         mods["NoiseReduction"].process(gold["in_noise_u8"], method="Bilateral", ksize=5)
 

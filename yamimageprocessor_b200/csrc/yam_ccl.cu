@@ -311,68 +311,122 @@ __global__ void props_init_kernel(long long* __restrict__ props, int64_t n_label
     props[i] = (f == kMinR || f == kMinC) ? 0x7fffffffffffffffLL : 0LL;
 }
 
-__device__ __forceinline__ void flush_run(long long* __restrict__ props, int lab, int64_t n_labels, int y, int xs,
-                                          int len, unsigned long long si) {
-    if (lab <= 0 || lab > n_labels) return;
-    long long* p = props + (int64_t)(lab - 1) * YAM_PROPS_STRIDE;
-    atomicAdd((unsigned long long*)&p[kArea], (unsigned long long)len);
-    atomicAdd((unsigned long long*)&p[kSumR], (unsigned long long)y * (unsigned long long)len);
-    // sum of columns xs .. xs+len-1
-    atomicAdd((unsigned long long*)&p[kSumC],
-              (unsigned long long)xs * (unsigned long long)len + (unsigned long long)len * (len - 1) / 2);
-    if (si) atomicAdd((unsigned long long*)&p[kSumI], si);
-    // bbox: values only move monotonically, so a stale read that already satisfies the bound is final
-    if (__ldcg(&p[kMinR]) > (long long)y) atomicMin(&p[kMinR], (long long)y);
-    if (__ldcg(&p[kMaxR]) < (long long)y + 1) atomicMax(&p[kMaxR], (long long)y + 1);
-    if (__ldcg(&p[kMinC]) > (long long)xs) atomicMin(&p[kMinC], (long long)xs);
-    if (__ldcg(&p[kMaxC]) < (long long)(xs + len)) atomicMax(&p[kMaxC], (long long)(xs + len));
+// Per-thread open run: the label last seen by this thread with its partial sums.  A thread owns an
+// 8-pixel-wide column strip over a band of rows, so consecutive rows of the same region merge in
+// registers and each region costs one flush per strip instead of one per row.
+struct OpenRun {
+    int lab;
+    uint32_t area, sumr, sumc, sumi;  // band <= 32 rows x 8 px: 32-bit partials cannot overflow
+    int minr, maxr, minc, maxc;
+};
+
+__device__ __forceinline__ void flush_open(long long* __restrict__ props, int64_t n_labels, const OpenRun& r) {
+    if (r.lab <= 0 || r.lab > n_labels) return;
+    long long* p = props + (int64_t)(r.lab - 1) * YAM_PROPS_STRIDE;
+    atomicAdd((unsigned long long*)&p[kArea], (unsigned long long)r.area);
+    atomicAdd((unsigned long long*)&p[kSumR], (unsigned long long)r.sumr);
+    atomicAdd((unsigned long long*)&p[kSumC], (unsigned long long)r.sumc);
+    if (r.sumi) atomicAdd((unsigned long long*)&p[kSumI], (unsigned long long)r.sumi);
+    atomicMin(&p[kMinR], (long long)r.minr);
+    atomicMax(&p[kMaxR], (long long)r.maxr);
+    atomicMin(&p[kMinC], (long long)r.minc);
+    atomicMax(&p[kMaxC], (long long)r.maxc);
 }
+
+constexpr int kBand = 32;   // rows per block band
+constexpr int kRowsPerIter = 4;
 
 template <typename TI>
 __global__ void __launch_bounds__(kThreads) props_kernel(const int32_t* __restrict__ labels,
                                                          const TI* __restrict__ intensity, int h, int w,
                                                          int64_t n_labels, long long* __restrict__ props) {
-    // one thread per 8-pixel chunk of a row; grid.x covers chunks of a row, grid.y rows (strided)
     const int chunks = (w + 7) / 8;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chunks) return;
+    const int x0 = c * 8;
     const bool aligned = (w % 8) == 0 && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
-    for (int y = blockIdx.y; y < h; y += gridDim.y) {
-        const int32_t* lrow = labels + (int64_t)y * w;
-        const TI* irow = intensity ? intensity + (int64_t)y * w : nullptr;
-        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
-            const int x0 = c * 8;
-            int32_t l[8];
-            uint32_t iv[8];
-            if (aligned) {
-                const int4 a = *reinterpret_cast<const int4*>(lrow + x0);
-                const int4 b = *reinterpret_cast<const int4*>(lrow + x0 + 4);
-                l[0] = a.x; l[1] = a.y; l[2] = a.z; l[3] = a.w;
-                l[4] = b.x; l[5] = b.y; l[6] = b.z; l[7] = b.w;
-            } else {
+    const bool ialigned = intensity && (w % 8) == 0 && ((reinterpret_cast<uintptr_t>(intensity) & (8 * sizeof(TI) - 1)) == 0);
+    OpenRun run;
+    run.lab = 0;
+    run.area = run.sumr = run.sumc = run.sumi = 0;
+    run.minr = run.maxr = run.minc = run.maxc = 0;
+    for (int64_t band = blockIdx.y; band * kBand < h; band += gridDim.y) {
+        const int y_begin = (int)(band * kBand);
+        const int y_end = min(h, y_begin + kBand);
+        for (int yb = y_begin; yb < y_end; yb += kRowsPerIter) {
+            int32_t l[kRowsPerIter][8];
+            // issue all label loads of this iteration first (memory-level parallelism)
 #pragma unroll
-                for (int i = 0; i < 8; i++) l[i] = (x0 + i < w) ? lrow[x0 + i] : 0;
-            }
-            uint32_t any = 0;
+            for (int r = 0; r < kRowsPerIter; r++) {
+                const int y = yb + r;
+                if (y < y_end) {
+                    const int32_t* lrow = labels + (int64_t)y * w;
+                    if (aligned) {
+                        const int4 a = __ldcs(reinterpret_cast<const int4*>(lrow + x0));
+                        const int4 b = __ldcs(reinterpret_cast<const int4*>(lrow + x0 + 4));
+                        l[r][0] = a.x; l[r][1] = a.y; l[r][2] = a.z; l[r][3] = a.w;
+                        l[r][4] = b.x; l[r][5] = b.y; l[r][6] = b.z; l[r][7] = b.w;
+                    } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) any |= (uint32_t)l[i];
-            if (!any) continue;
+                        for (int i = 0; i < 8; i++) l[r][i] = (x0 + i < w) ? lrow[x0 + i] : 0;
+                    }
+                } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) iv[i] = (irow && x0 + i < w && l[i]) ? (uint32_t)irow[x0 + i] : 0u;
-            int cur = 0, xs = 0, len = 0;
-            unsigned long long si = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (l[i] != cur) {
-                    if (cur) flush_run(props, cur, n_labels, y, xs, len, si);
-                    cur = l[i];
-                    xs = x0 + i;
-                    len = 0;
-                    si = 0;
+                    for (int i = 0; i < 8; i++) l[r][i] = 0;
                 }
-                len++;
-                si += iv[i];
             }
-            if (cur) flush_run(props, cur, n_labels, y, xs, len, si);
+#pragma unroll
+            for (int r = 0; r < kRowsPerIter; r++) {
+                const int y = yb + r;
+                uint32_t any = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) any |= (uint32_t)l[r][i];
+                if (!any) continue;
+                uint32_t iv[8];
+                if (ialigned) {
+                    const TI* irow = intensity + (int64_t)y * w + x0;
+                    if (sizeof(TI) == 2) {
+                        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(irow));
+                        iv[0] = q.x & 0xffffu; iv[1] = q.x >> 16; iv[2] = q.y & 0xffffu; iv[3] = q.y >> 16;
+                        iv[4] = q.z & 0xffffu; iv[5] = q.z >> 16; iv[6] = q.w & 0xffffu; iv[7] = q.w >> 16;
+                    } else {
+                        const uint2 q = __ldcs(reinterpret_cast<const uint2*>(irow));
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            iv[i] = (q.x >> (8 * i)) & 0xffu;
+                            iv[4 + i] = (q.y >> (8 * i)) & 0xffu;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        iv[i] = (intensity && x0 + i < w) ? (uint32_t)intensity[(int64_t)y * w + x0 + i] : 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int lab = l[r][i];
+                    if (lab == 0) continue;
+                    const int x = x0 + i;
+                    if (lab != run.lab) {
+                        flush_open(props, n_labels, run);
+                        run.lab = lab;
+                        run.area = run.sumr = run.sumc = run.sumi = 0;
+                        run.minr = y;
+                        run.minc = x;
+                        run.maxc = x + 1;
+                    }
+                    run.area += 1;
+                    run.sumr += (uint32_t)y;
+                    run.sumc += (uint32_t)x;
+                    run.sumi += iv[i];
+                    run.minc = min(run.minc, x);
+                    run.maxc = max(run.maxc, x + 1);
+                    run.maxr = y + 1;
+                }
+            }
         }
+        flush_open(props, n_labels, run);
+        run.lab = 0;
     }
 }
 
@@ -448,7 +502,8 @@ int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity,
     YAM_LAUNCHED(ctx);
     const int chunks = (int)((w + 7) / 8);
     unsigned gx = (unsigned)((chunks + kThreads - 1) / kThreads);
-    unsigned gy = (unsigned)(h < 65535 ? h : 65535);
+    const int64_t bands = (h + kBand - 1) / kBand;
+    unsigned gy = (unsigned)(bands < 65535 ? bands : 65535);
     dim3 grid(gx, gy, 1);
     if (!intensity || intensity_dtype == YAM_U16)
         props_kernel<uint16_t><<<grid, kThreads, 0, ctx->stream>>>(labels, (const uint16_t*)intensity, (int)h, (int)w, n_labels, props);

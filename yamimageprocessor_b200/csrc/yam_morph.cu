@@ -14,6 +14,11 @@
 #include "yam_common.cuh"
 #include "yam_host.h"
 
+// fast path for short symmetric chains (yam_morph_fast.cu): 1 = launched, 0 = not covered, < 0 = error
+template <typename T>
+int yam_morph_fast_try(yam_ctx* ctx, const T* src, T* dst, int64_t n, int64_t h, int64_t w, int nstages,
+                       const int* dilate, const int* radius);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -264,7 +269,21 @@ int run_rect_stages(yam_ctx* ctx, const T* src, T* dst, int64_t n, int64_t h, in
         cur.HR += pieces[i].R;
     }
     chains[nc++] = cur;
-    if (nc == 1) return launch_chain<T>(ctx, src, dst, n, h, w, chains[0]);
+    if (nc == 1) {
+        const Chain& c = chains[0];
+        bool symmetric = c.n <= 3;
+        int dil[3] = {0, 0, 0}, rad[3] = {0, 0, 0};
+        for (int i = 0; i < c.n && symmetric; i++) {
+            symmetric = c.s[i].L == c.s[i].R;
+            dil[i] = c.s[i].dilate;
+            rad[i] = c.s[i].L;
+        }
+        if (symmetric) {
+            const int rc = yam_morph_fast_try<T>(ctx, src, dst, n, h, w, c.n, dil, rad);
+            if (rc != 0) return rc < 0 ? rc : YAM_OK;
+        }
+        return launch_chain<T>(ctx, src, dst, n, h, w, c);
+    }
     // multi-launch: need a scratch image; the final launch must land in dst
     void* scratch = nullptr;
     if (int rc = yam_scratch(ctx, (size_t)n * h * w * sizeof(T), &scratch)) return rc;
