@@ -1,23 +1,24 @@
 // K10 connected-component labelling and K11 region properties.
 //
 // CCL (8-connectivity, raster-first canonical numbering) as a union-find over RUN SEGMENTS:
-//   1. pack     the u8 mask is packed to 1 bit/pixel; every maximal run of set bits inside one
-//               32-pixel word is a node whose id is the (padded) linear index of its first pixel;
-//               parent[id] = id.  Nodes are ~10-30x fewer than pixels, and only they are ever
-//               touched by the union-find, so its traffic stays in L2.
-//   2. union    one thread per word links each of its segments to the segment that continues it
-//               in the previous word and to every 8-connected segment in the row above
-//               (lock-free union by minimum index with atomicMin).
-//   3. flatten  parent[id] = root(id); segments that are their own root set a bit in a root mask.
-//               Linking by minimum index makes the root the component's first pixel in raster
-//               order, so rank(root) among roots IS the canonical label.
-//   4. scan     popcount prefix over the root mask (per frame) -> rank of every root.
-//   5. final    one thread per word writes the 32 int32 labels (1 + rank of the segment's root).
-// HBM traffic: 1 B/px mask read + 4 B/px label write + O(segments).
+//   pack      the u8 mask is packed to 1 bit/pixel; every maximal run of set bits inside one 32-pixel
+//             word is a node.  Nodes are numbered COMPACTLY in raster order (exclusive prefix sum of
+//             the per-word segment counts), so the parent array has one int per segment (~1-2 % of
+//             the pixels) and every union-find access stays in L2.
+//   union     one thread per word links each of its segments to the segment that continues it in
+//             the previous word and to every 8-connected segment in the row above (lock-free union
+//             by minimum index with atomicMin, path halving in find).
+//   flatten   parent[node] = root(node); roots are counted per word.
+//   rootlabel exclusive prefix of the root counts = rank of every root.  Linking by minimum index
+//             makes the root the segment holding the component's first pixel in raster order, so
+//             rank(root) + 1 IS the canonical label; it is stored negated in the root's slot.
+//   final     one thread per word resolves its segments (at most two dependent loads) and the block
+//             writes the int32 labels through a swizzled shared-memory tile with 128-bit coalesced
+//             stores.
+// HBM traffic: 1 B/px mask read + 4 B/px label write + O(words) bookkeeping (12 B per 32 px).
 //
-// Region properties: one pass over labels (+ intensity); every thread folds the runs of equal
-// label inside its 8-pixel chunk and issues one set of 64-bit atomics per run, bbox atomics are
-// skipped when a (monotonic) pre-read shows they cannot change the value.
+// Region properties: threads own an 8-pixel-wide column strip over a band of rows and keep the
+// current label's partial sums in registers; one set of 64-bit atomics per label change.
 #include "yam_common.cuh"
 
 namespace {
@@ -26,20 +27,34 @@ constexpr int kThreads = 256;
 
 struct CclGeom {
     int h, w;
-    int wpr;        // words per row
-    int wp;         // padded row pitch in pixels = 32 * wpr
+    int wpr;                  // words per row
     int64_t words_per_frame;
-    int64_t total_words;  // frames * words_per_frame
+    int64_t total_words;      // frames * words_per_frame
+    int frames;
 };
 
-__device__ __forceinline__ int ld_parent(const int* p) { return __ldcg(p); }
-
-__device__ __forceinline__ int find_root(const int* __restrict__ P, int x) {
-    while (true) {
-        const int p = ld_parent(P + x);
-        if (p == x) return x;
+__device__ __forceinline__ int find_root(int* __restrict__ P, int x) {
+    // path halving: every visited node is re-pointed to its grandparent (plain stores are safe:
+    // parents only ever move to smaller ancestors of the same set)
+    int p = __ldcg(P + x);
+    while (p != x) {
+        const int gp = __ldcg(P + p);
+        if (gp != p) P[x] = gp;
         x = p;
+        p = gp;
     }
+    return x;
+}
+
+// read-only find for the flatten pass: there every slot is written by its owner only, so that
+// "parent == root" holds for all nodes afterwards (halving stores from other threads would race)
+__device__ __forceinline__ int find_root_ro(const int* __restrict__ P, int x) {
+    int p = __ldcg(P + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(P + x);
+    }
+    return x;
 }
 
 __device__ __forceinline__ void unite(int* __restrict__ P, int a, int b) {
@@ -58,66 +73,161 @@ __device__ __forceinline__ void unite(int* __restrict__ P, int a, int b) {
     }
 }
 
+__device__ __forceinline__ uint32_t seg_starts(uint32_t b) { return b & ~(b << 1); }
+
 // start (bit index) of the run of ones in `wv` that contains bit `b` (bit b must be set)
 __device__ __forceinline__ int run_start(uint32_t wv, int b) {
     const uint32_t zeros_below = ~wv & ((1u << b) - 1u);
     return zeros_below ? 32 - __clz(zeros_below) : 0;
 }
 
-// ---- 1. pack + init ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __restrict__ mask, CclGeom g,
-                                                            uint32_t* __restrict__ bits, int* __restrict__ P) {
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gw >= g.total_words) return;
-    const int64_t frame = gw / g.words_per_frame;
-    const int64_t wf = gw - frame * g.words_per_frame;
-    const int y = (int)(wf / g.wpr), j = (int)(wf - (int64_t)y * g.wpr);
-    const uint8_t* row = mask + (frame * g.h + y) * (int64_t)g.w;
-    const int x0 = j * 32;
-    uint32_t b = 0;
-    if (x0 + 32 <= g.w && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
-        const uint4 q0 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0));
-        const uint4 q1 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0) + 1);
-        const uint32_t wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t v = wd[i];
-            b |= ((v & 0xffu) ? 1u : 0u) << (4 * i);
-            b |= ((v & 0xff00u) ? 1u : 0u) << (4 * i + 1);
-            b |= ((v & 0xff0000u) ? 1u : 0u) << (4 * i + 2);
-            b |= ((v & 0xff000000u) ? 1u : 0u) << (4 * i + 3);
-        }
-    } else {
-        for (int i = 0; i < 32 && x0 + i < g.w; i++) b |= (row[x0 + i] ? 1u : 0u) << i;
+// index (within its word) of the segment of `wv` that contains bit `b`
+__device__ __forceinline__ int seg_index(uint32_t wv, int b) {
+    const int s = run_start(wv, b);
+    return __popc(seg_starts(wv) & ((1u << s) - 1u));
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_tmp) {
+    v = yam_warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < kThreads / 32 ? s_tmp[threadIdx.x] : 0u;
+        t = yam_warp_sum(t);
     }
-    bits[gw] = b;
-    // segment starts: bit set and the bit below clear (bit 0 starts a segment of this word)
-    uint32_t starts = b & ~(b << 1);
-    int* Pf = P + frame * (int64_t)g.h * g.wp;
-    const int base = (y * g.wpr + j) * 32;
-    while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        Pf[base + s] = base + s;
+    return t;  // valid in warp 0
+}
+
+// exclusive prefix of v within the block (kThreads threads); returns the prefix for this thread
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; i++)
+        if (i < warp) off += s_tmp[i];
+    return off + incl - v;
+}
+
+// ---- 1. pack: bits + per-block segment counts --------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __restrict__ mask, CclGeom g,
+                                                            uint32_t* __restrict__ bits,
+                                                            uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t s_tmp[kThreads / 32];
+    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = 0;
+    if (gw < g.total_words) {
+        const int64_t row_id = gw / g.wpr;  // frame * h + y
+        const int j = (int)(gw - row_id * g.wpr);
+        const uint8_t* row = mask + row_id * (int64_t)g.w;
+        const int x0 = j * 32;
+        if (x0 + 32 <= g.w && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
+            const uint4 q0 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0));
+            const uint4 q1 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0) + 1);
+            const uint32_t wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t v = wd[i];
+                b |= ((v & 0xffu) ? 1u : 0u) << (4 * i);
+                b |= ((v & 0xff00u) ? 1u : 0u) << (4 * i + 1);
+                b |= ((v & 0xff0000u) ? 1u : 0u) << (4 * i + 2);
+                b |= ((v & 0xff000000u) ? 1u : 0u) << (4 * i + 3);
+            }
+        } else {
+            for (int i = 0; i < 32 && x0 + i < g.w; i++) b |= (row[x0 + i] ? 1u : 0u) << i;
+        }
+        bits[gw] = b;
+    }
+    const uint32_t total = block_sum_u32(__popc(seg_starts(b)), s_tmp);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// ---- exclusive scan of a u32 array in place (single block); total -> *total_out ------------------
+__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ data, int64_t n,
+                                                        uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 4096) {
+        // 4 consecutive elements per thread
+        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t wv = s_warp[lane];
+            uint32_t wi = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            s_warp[lane] = wi - wv;
+        }
+        __syncthreads();
+        uint32_t run = s_carry + s_warp[warp] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) data[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = run;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = s_carry;
+}
+
+// ---- 3. node base per word + parent init -----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ccl_nodebase_kernel(const uint32_t* __restrict__ bits, CclGeom g,
+                                                                const uint32_t* __restrict__ block_offsets,
+                                                                uint32_t* __restrict__ nbase, int* __restrict__ P) {
+    __shared__ uint32_t s_tmp[kThreads / 32];
+    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = gw < g.total_words ? bits[gw] : 0u;
+    const uint32_t cnt = __popc(seg_starts(b));
+    const uint32_t base = block_offsets[blockIdx.x] + block_excl_scan_u32(cnt, s_tmp);
+    if (gw < g.total_words) {
+        nbase[gw] = base;
+        for (uint32_t k = 0; k < cnt; k++) P[base + k] = (int)(base + k);
     }
 }
 
-// ---- 2. union ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_union_kernel(const uint32_t* __restrict__ bits, CclGeom g,
+// ---- 4. union ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ccl_union_kernel(const uint32_t* __restrict__ bits,
+                                                             const uint32_t* __restrict__ nbase, CclGeom g,
                                                              int* __restrict__ P) {
     const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gw >= g.total_words) return;
     const uint32_t b = bits[gw];
     if (!b) return;
-    const int64_t frame = gw / g.words_per_frame;
-    const int64_t wf = gw - frame * g.words_per_frame;
-    const int y = (int)(wf / g.wpr), j = (int)(wf - (int64_t)y * g.wpr);
-    int* Pf = P + frame * (int64_t)g.h * g.wp;
-    const int base = (y * g.wpr + j) * 32;
+    const int64_t row_id = gw / g.wpr;
+    const int j = (int)(gw - row_id * g.wpr);
+    const int y = (int)(row_id % g.h);
+    const int my_base = (int)nbase[gw];
     // horizontal: the segment at bit 0 continues the segment that ends at bit 31 of the previous word
     if ((b & 1u) && j > 0) {
         const uint32_t pv = bits[gw - 1];
-        if (pv >> 31) unite(Pf, base, base - 32 + run_start(pv, 31));
+        if (pv >> 31) unite(P, my_base, (int)nbase[gw - 1] + seg_index(pv, 31));
     }
     if (y == 0) return;
     // vertical: 34-column window of the row above; bit k of `above` <-> column 32*j + k - 1
@@ -127,176 +237,158 @@ __global__ void __launch_bounds__(kThreads) ccl_union_kernel(const uint32_t* __r
     const unsigned long long above =
         (unsigned long long)(up >> 31) | ((unsigned long long)u << 1) | ((unsigned long long)(un & 1u) << 33);
     if (!above) return;
-    const int base_up = base - g.wp;  // node id of bit 0 of word (y-1, j)
-    uint32_t starts = b & ~(b << 1);
+    const int base_u = u ? (int)nbase[gw - g.wpr] : 0;
+    uint32_t starts = seg_starts(b);
+    int k = 0;
     while (starts) {
         const int s = __ffs(starts) - 1;
         starts &= starts - 1;
-        // segment [s, e]
         const uint32_t from_s = b >> s;
         const int len = (~from_s) ? __ffs(~from_s) - 1 : 32 - s;
         const int e = s + len - 1;
         // window bits s .. e+2
-        const unsigned long long wmask = ((e + 3 >= 64) ? ~0ull : ((1ull << (e + 3)) - 1ull)) & ~((1ull << s) - 1ull);
+        const unsigned long long wmask = ((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull);
         unsigned long long m = above & wmask;
         while (m) {
             const int k0 = __ffsll((long long)m) - 1;
-            // clear the lowest run of ones
-            m &= m + (1ull << k0);
+            m &= m + (1ull << k0);  // clear the lowest run of ones
             int node;
             if (k0 == 0) {
-                node = base_up - 32 + run_start(up, 31);
+                node = (int)nbase[gw - g.wpr - 1] + seg_index(up, 31);
             } else if (k0 == 33) {
-                node = base_up + 32;  // bit 0 of the next word starts its segment
+                node = (int)nbase[gw - g.wpr + 1];  // bit 0 of the next word starts its first segment
             } else {
-                node = base_up + run_start(u, k0 - 1);
+                node = base_u + seg_index(u, k0 - 1);
             }
-            unite(Pf, base + s, node);
+            unite(P, my_base + k, node);
         }
+        k++;
     }
 }
 
-// ---- 3. flatten + root mask + per-block root counts ----------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_flatten_kernel(const uint32_t* __restrict__ bits, CclGeom g,
-                                                               int* __restrict__ P, uint32_t* __restrict__ rootmask,
-                                                               uint32_t* __restrict__ blocksums, int blocks_per_frame) {
-    // grid: (blocks_per_frame, frames)
-    const int64_t wf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t frame = blockIdx.y;
-    uint32_t roots = 0;
-    if (wf < g.words_per_frame) {
-        const int64_t gw = frame * g.words_per_frame + wf;
-        const uint32_t b = bits[gw];
-        if (b) {
-            int* Pf = P + frame * (int64_t)g.h * g.wp;
-            const int base = (int)wf * 32;
-            uint32_t starts = b & ~(b << 1);
-            while (starts) {
-                const int s = __ffs(starts) - 1;
-                starts &= starts - 1;
-                const int r = find_root(Pf, base + s);
-                if (r == base + s) roots |= 1u << s;
-                else Pf[base + s] = r;
-            }
-        }
-        rootmask[gw] = roots;
-    }
-    // block sum of popcounts
-    uint32_t c = __popc(roots);
-    c = yam_warp_sum(c);
-    __shared__ uint32_t s_c[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int i = 0; i < kThreads / 32; i++) t += s_c[i];
-        blocksums[frame * blocks_per_frame + blockIdx.x] = t;
-    }
-}
-
-// ---- 4a. exclusive scan of block sums, one block per frame --------------------------------------
-__global__ void __launch_bounds__(1024) ccl_scan_blocks_kernel(uint32_t* __restrict__ blocksums, int blocks_per_frame,
-                                                               int32_t* __restrict__ counts) {
-    uint32_t* bs = blocksums + (int64_t)blockIdx.x * blocks_per_frame;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < blocks_per_frame; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < blocks_per_frame ? bs[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t wv = s_warp[lane];
-            uint32_t wi = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += up;
-            }
-            s_warp[lane] = wi - wv;  // exclusive
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        const uint32_t excl = carry + s_warp[warp] + incl - v;
-        if (i < blocks_per_frame) bs[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = (int32_t)s_carry;
-}
-
-// ---- 4b. per-word exclusive prefix -----------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_word_prefix_kernel(const uint32_t* __restrict__ rootmask, CclGeom g,
-                                                                   const uint32_t* __restrict__ blocksums,
-                                                                   int blocks_per_frame,
-                                                                   uint32_t* __restrict__ wordprefix) {
-    const int64_t wf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t frame = blockIdx.y;
-    const int64_t gw = frame * g.words_per_frame + wf;
-    const uint32_t c = wf < g.words_per_frame ? __popc(rootmask[gw]) : 0u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-    }
-    __shared__ uint32_t s_w[kThreads / 32];
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    uint32_t off = blocksums[frame * blocks_per_frame + blockIdx.x];
-    for (int i = 0; i < warp; i++) off += s_w[i];
-    if (wf < g.words_per_frame) wordprefix[gw] = off + incl - c;
-}
-
-// ---- 5. final labels ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __restrict__ bits, CclGeom g,
-                                                             const int* P, const uint32_t* __restrict__ rootmask,
-                                                             const uint32_t* __restrict__ wordprefix,
-                                                             int32_t* labels) {
+// ---- 5. flatten + per-block root counts -------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ccl_flatten_kernel(const uint32_t* __restrict__ bits,
+                                                               const uint32_t* __restrict__ nbase, CclGeom g,
+                                                               int* __restrict__ P,
+                                                               uint32_t* __restrict__ block_roots) {
+    __shared__ uint32_t s_tmp[kThreads / 32];
     const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gw >= g.total_words) return;
-    const int64_t frame = gw / g.words_per_frame;
-    const int64_t wf = gw - frame * g.words_per_frame;
-    const int y = (int)(wf / g.wpr), j = (int)(wf - (int64_t)y * g.wpr);
-    const uint32_t b = bits[gw];
-    const int* Pf = P + frame * (int64_t)g.h * g.wp;
-    const uint32_t* rm = rootmask + frame * g.words_per_frame;
-    const uint32_t* wpf = wordprefix + frame * g.words_per_frame;
-    const int base = (int)wf * 32;
-    int32_t out[32];
-    int cur = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        const bool set = (b >> i) & 1u;
-        const bool start = set && (i == 0 || !((b >> (i - 1)) & 1u));
-        if (start) {
-            const int r = ld_parent(Pf + base + i);  // flattened: parent is the root (or itself)
-            const uint32_t rw = (uint32_t)r >> 5, rb = (uint32_t)r & 31u;
-            cur = 1 + (int)(wpf[rw] + __popc(rm[rw] & ((1u << rb) - 1u)));
+    uint32_t roots = 0;
+    if (gw < g.total_words) {
+        const uint32_t cnt = __popc(seg_starts(bits[gw]));
+        if (cnt) {
+            const int base = (int)nbase[gw];
+            for (uint32_t k = 0; k < cnt; k++) {
+                const int node = base + (int)k;
+                const int r = find_root_ro(P, node);
+                if (r == node) roots++;
+                else P[node] = r;
+            }
         }
-        out[i] = set ? cur : 0;
     }
-    int32_t* drow = labels + (frame * g.h + y) * (int64_t)g.w + (int64_t)j * 32;
-    const int valid = min(32, g.w - j * 32);
-    if (valid == 32 && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
+    const uint32_t total = block_sum_u32(roots, s_tmp);
+    if (threadIdx.x == 0) block_roots[blockIdx.x] = total;
+}
+
+// ---- 7. root labels: P[root] = -(rank + 1); rbase[word] = roots before this word --------------------
+__global__ void __launch_bounds__(kThreads) ccl_rootlabel_kernel(const uint32_t* __restrict__ bits,
+                                                                 const uint32_t* __restrict__ nbase, CclGeom g,
+                                                                 const uint32_t* __restrict__ block_root_offsets,
+                                                                 int* __restrict__ P, uint32_t* __restrict__ rbase) {
+    __shared__ uint32_t s_tmp[kThreads / 32];
+    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t rootbits = 0, cnt = 0;
+    int base = 0;
+    if (gw < g.total_words) {
+        cnt = __popc(seg_starts(bits[gw]));
+        if (cnt) {
+            base = (int)nbase[gw];
+            for (uint32_t k = 0; k < cnt; k++)
+                if (__ldcg(P + base + (int)k) == base + (int)k) rootbits |= 1u << k;
+        }
+    }
+    const uint32_t before = block_root_offsets[blockIdx.x] + block_excl_scan_u32(__popc(rootbits), s_tmp);
+    if (gw < g.total_words) {
+        rbase[gw] = before;
+        uint32_t rank = before;
+        while (rootbits) {
+            const int k = __ffs(rootbits) - 1;
+            rootbits &= rootbits - 1;
+            P[base + k] = -(int)(rank + 1);
+            rank++;
+        }
+    }
+}
+
+// ---- 8. final labels ----------------------------------------------------------------------------
+// block = 256 words = 8192 pixels; labels are staged in shared memory (swizzled at int4
+// granularity: both the per-thread row writes and the coalesced read-out are conflict free)
+__global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __restrict__ bits,
+                                                             const uint32_t* __restrict__ nbase,
+                                                             const uint32_t* __restrict__ rbase, CclGeom g,
+                                                             const int* __restrict__ P, int32_t* __restrict__ labels,
+                                                             const uint32_t* __restrict__ total_roots,
+                                                             int32_t* __restrict__ counts) {
+    __shared__ int4 s_out[kThreads * 8];
+    const int64_t gw0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t gw = gw0 + threadIdx.x;
+    const int t = threadIdx.x;
+    uint32_t b = 0;
+    int frame_off = 0;
+    if (gw < g.total_words) {
+        b = bits[gw];
+        const int64_t frame = gw / g.words_per_frame;
+        if (b && frame > 0) frame_off = (int)rbase[frame * g.words_per_frame];
+        // per-frame component counts (one thread per frame boundary word)
+        if (counts && gw == frame * g.words_per_frame) {
+            const uint32_t here = rbase[gw];
+            const uint32_t next = (frame + 1 < g.frames) ? rbase[(frame + 1) * g.words_per_frame] : *total_roots;
+            counts[frame] = (int32_t)(next - here);
+        }
+    }
+    int32_t out[32];
+    if (b) {
+        const int base = (int)nbase[gw];
+        int cur = 0, k = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            *reinterpret_cast<int4*>(drow + 4 * i) = make_int4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+        for (int i = 0; i < 32; i++) {
+            const bool set = (b >> i) & 1u;
+            const bool start = set && (i == 0 || !((b >> (i - 1)) & 1u));
+            if (start) {
+                int v = __ldg(P + base + k);
+                if (v >= 0) v = __ldg(P + v);  // non-root: follow to the root, which holds -(label)
+                cur = -v - frame_off;
+                k++;
+            }
+            out[i] = set ? cur : 0;
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-            if (i < valid) drow[i] = out[i];
+        for (int i = 0; i < 32; i++) out[i] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        s_out[t * 8 + ((q + t) & 7)] = make_int4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    __syncthreads();
+    if ((g.w & 31) == 0 && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0)) {
+        // rows are whole words: the block's 256 words are 8192 consecutive labels
+        int4* dst = reinterpret_cast<int4*>(labels + gw0 * 32);
+        const int64_t valid_words = g.total_words - gw0 < kThreads ? g.total_words - gw0 : kThreads;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = it * kThreads + t;  // int4 index inside the block tile
+            const int wd = idx >> 3, q = idx & 7;
+            if (wd < valid_words) dst[idx] = s_out[wd * 8 + ((q + wd) & 7)];
+        }
+    } else if (gw < g.total_words) {
+        const int64_t row_id = gw / g.wpr;
+        const int j = (int)(gw - row_id * g.wpr);
+        int32_t* drow = labels + row_id * (int64_t)g.w + (int64_t)j * 32;
+        const int valid = min(32, g.w - j * 32);
+        for (int i = 0; i < valid; i++) {
+            const int4 v = s_out[t * 8 + (((i >> 2) + t) & 7)];
+            drow[i] = (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+        }
     }
 }
 
@@ -443,42 +535,47 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
     g.h = (int)h;
     g.w = (int)w;
     g.wpr = (int)((w + 31) / 32);
-    g.wp = g.wpr * 32;
     g.words_per_frame = (int64_t)h * g.wpr;
     g.total_words = g.words_per_frame * n;
+    g.frames = (int)n;
     YAM_REQUIRE(g.words_per_frame * 32 < (1ll << 31), "ccl: frame too large for int32 labels (%lld x %lld)",
                 (long long)h, (long long)w);
-    const int blocks_per_frame = (int)((g.words_per_frame + kThreads - 1) / kThreads);
-    const bool alias = (w % 32) == 0;  // labels buffer doubles as the parent array
-    // scratch layout
+    YAM_REQUIRE(g.total_words * 16 < (1ll << 31), "ccl: stack too large for one call (%lld words); split the stack",
+                (long long)g.total_words);
+    const int64_t nblocks = (g.total_words + kThreads - 1) / kThreads;
+    // scratch layout: bits | nbase | rbase | blockA | blockB | totals[2] | counts | P (<= 16 nodes per word)
     const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
-    const size_t bs_bytes = yam_align_up((size_t)n * blocks_per_frame * 4, 256);
+    const size_t blk_bytes = yam_align_up((size_t)nblocks * 4, 256);
     const size_t cnt_bytes = yam_align_up((size_t)n * 4, 256);
-    const size_t p_bytes = alias ? 0 : yam_align_up((size_t)n * h * g.wp * 4, 256);
+    const size_t p_bytes = yam_align_up((size_t)g.total_words * 16 * 4, 256);
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, 3 * words_bytes + bs_bytes + cnt_bytes + p_bytes, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, 3 * words_bytes + 2 * blk_bytes + 256 + cnt_bytes + p_bytes, &scratch)) return rc;
     char* sp = (char*)scratch;
     uint32_t* bits = (uint32_t*)sp;
-    uint32_t* rootmask = (uint32_t*)(sp + words_bytes);
-    uint32_t* wordprefix = (uint32_t*)(sp + 2 * words_bytes);
-    uint32_t* blocksums = (uint32_t*)(sp + 3 * words_bytes);
-    int32_t* counts = counts_dev ? counts_dev : (int32_t*)(sp + 3 * words_bytes + bs_bytes);
-    int* P = alias ? (int*)labels : (int*)(sp + 3 * words_bytes + bs_bytes + cnt_bytes);
+    uint32_t* nbase = (uint32_t*)(sp + words_bytes);
+    uint32_t* rbase = (uint32_t*)(sp + 2 * words_bytes);
+    uint32_t* blockA = (uint32_t*)(sp + 3 * words_bytes);
+    uint32_t* blockB = (uint32_t*)(sp + 3 * words_bytes + blk_bytes);
+    uint32_t* totals = (uint32_t*)(sp + 3 * words_bytes + 2 * blk_bytes);
+    int32_t* counts = counts_dev ? counts_dev : (int32_t*)(sp + 3 * words_bytes + 2 * blk_bytes + 256);
+    int* P = (int*)(sp + 3 * words_bytes + 2 * blk_bytes + 256 + cnt_bytes);
 
-    const unsigned gblocks = (unsigned)((g.total_words + kThreads - 1) / kThreads);
-    ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits, P);
+    const unsigned gblocks = (unsigned)nblocks;
+    ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits, blockA);
     YAM_LAUNCHED(ctx);
-    ccl_union_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, P);
+    scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(blockA, nblocks, totals);
     YAM_LAUNCHED(ctx);
-    ccl_flatten_kernel<<<dim3((unsigned)blocks_per_frame, (unsigned)n), kThreads, 0, ctx->stream>>>(
-        bits, g, P, rootmask, blocksums, blocks_per_frame);
+    ccl_nodebase_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, nbase, P);
     YAM_LAUNCHED(ctx);
-    ccl_scan_blocks_kernel<<<(unsigned)n, 1024, 0, ctx->stream>>>(blocksums, blocks_per_frame, counts);
+    ccl_union_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, P);
     YAM_LAUNCHED(ctx);
-    ccl_word_prefix_kernel<<<dim3((unsigned)blocks_per_frame, (unsigned)n), kThreads, 0, ctx->stream>>>(
-        rootmask, g, blocksums, blocks_per_frame, wordprefix);
+    ccl_flatten_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, P, blockB);
     YAM_LAUNCHED(ctx);
-    ccl_final_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, P, rootmask, wordprefix, labels);
+    scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(blockB, nblocks, totals + 1);
+    YAM_LAUNCHED(ctx);
+    ccl_rootlabel_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, blockB, P, rbase);
+    YAM_LAUNCHED(ctx);
+    ccl_final_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, rbase, g, P, labels, totals + 1, counts);
     YAM_LAUNCHED(ctx);
     if (counts_host) {
         YAM_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));

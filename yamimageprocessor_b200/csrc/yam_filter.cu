@@ -42,6 +42,10 @@ struct FixedTraits<uint16_t> {
 
 __host__ __device__ constexpr int round_up_c(int v, int a) { return (v + a - 1) / a * a; }
 
+template <typename Tout>
+__device__ __forceinline__ void store_tile(const Tout* __restrict__ s_out, Tout* __restrict__ dst, int h, int w,
+                                           int x0, int y0);
+
 // ----------------------------------------------------------------------------------------------
 // tile loader: s_in[rows][SW] <- src[(y0-r .. y0+TH+r) x (x0-ra .. x0+TW+ra)] with border mapping.
 // TS = smem element type (T itself, or float when Tin is converted on load).
@@ -149,11 +153,9 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
             }
         }
     }
-    const int gx = x0 + cx;
+    T* s_out = reinterpret_cast<T*>(s_t + ROWS * TW);
 #pragma unroll
     for (int j = 0; j < RB; j++) {
-        const int gy = y0 + r0 + j;
-        if (gy >= h || gx >= w) continue;
         uint32_t o0, o1;
         if (EPI == EPI_SHIFT) {
             o0 = (uint32_t)((acc0[j] + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
@@ -163,17 +165,14 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
             o0 = (uint32_t)((2 * (uint32_t)acc0[j] + box_div) / (2 * box_div));
             o1 = (uint32_t)((2 * (uint32_t)acc1[j] + box_div) / (2 * box_div));
         }
-        T* d = dst + (int64_t)gy * w + gx;
-        if (gx + 1 < w && ((reinterpret_cast<uintptr_t>(d) & (2 * sizeof(T) - 1)) == 0)) {
-            if (sizeof(T) == 2)
-                *reinterpret_cast<uint32_t*>(d) = o0 | (o1 << 16);
-            else
-                *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
-        } else {
-            d[0] = (T)o0;
-            if (gx + 1 < w) d[1] = (T)o1;
-        }
+        T* d = s_out + (r0 + j) * TW + cx;
+        if (sizeof(T) == 2)
+            *reinterpret_cast<uint32_t*>(d) = o0 | (o1 << 16);
+        else
+            *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
     }
+    __syncthreads();
+    store_tile<T>(s_out, dst, h, w, x0, y0);
 }
 
 // fixed-point separable filter, runtime K (any odd K <= YAM_MAX_TAPS that fits shared memory)
@@ -354,6 +353,176 @@ __global__ void __launch_bounds__(kThreads) sep_f32_kernel(const Tin* __restrict
 }
 
 // ----------------------------------------------------------------------------------------------
+// float32 separable Gaussian, compile-time K, throughput version (same arithmetic order as above).
+//   load   integer pixels become floats with PRMT + FADD (0x4B000000 | v) - 2^23 instead of I2F
+//   H pass 8 outputs per item from aligned 128-bit shared loads
+//   V pass sliding window in registers; adaptive epilogue rounds with the 1.5*2^23 magic add
+//   store  the output tile is staged in shared memory and written with 16-byte coalesced stores
+__device__ __forceinline__ float u16lo_to_f32(uint32_t wd) {
+    return __fadd_rn(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7410)), -8388608.0f);
+}
+__device__ __forceinline__ float u16hi_to_f32(uint32_t wd) {
+    return __fadd_rn(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7432)), -8388608.0f);
+}
+template <int K>
+__device__ __forceinline__ float u8_to_f32(uint32_t wd) {
+    return __fadd_rn(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7440 | K)), -8388608.0f);
+}
+
+template <typename T>
+__device__ __forceinline__ void vec_to_f32(const uint4& q, float* d);
+template <>
+__device__ __forceinline__ void vec_to_f32<uint16_t>(const uint4& q, float* d) {
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        d[2 * i] = u16lo_to_f32(wd[i]);
+        d[2 * i + 1] = u16hi_to_f32(wd[i]);
+    }
+}
+template <>
+__device__ __forceinline__ void vec_to_f32<uint8_t>(const uint4& q, float* d) {
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        d[4 * i] = u8_to_f32<0>(wd[i]);
+        d[4 * i + 1] = u8_to_f32<1>(wd[i]);
+        d[4 * i + 2] = u8_to_f32<2>(wd[i]);
+        d[4 * i + 3] = u8_to_f32<3>(wd[i]);
+    }
+}
+template <>
+__device__ __forceinline__ void vec_to_f32<float>(const uint4& q, float* d) {
+    d[0] = __uint_as_float(q.x); d[1] = __uint_as_float(q.y); d[2] = __uint_as_float(q.z); d[3] = __uint_as_float(q.w);
+}
+
+// cooperative store of a TH x TW staged tile (row pitch TW elements) with 16-byte vectors
+template <typename Tout>
+__device__ __forceinline__ void store_tile(const Tout* __restrict__ s_out, Tout* __restrict__ dst, int h, int w,
+                                           int x0, int y0) {
+    constexpr int VEC = 16 / sizeof(Tout);
+    constexpr int VPR = TW / VEC;
+    const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    for (int v = threadIdx.x; v < TH * VPR; v += kThreads) {
+        const int ty = v / VPR, vx = v - ty * VPR;
+        const int gy = y0 + ty, gx = x0 + vx * VEC;
+        if (gy >= h || gx >= w) continue;
+        const Tout* sp = s_out + ty * TW + vx * VEC;
+        Tout* d = dst + (int64_t)gy * w + gx;
+        if (row_aligned && gx + VEC <= w) {
+            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+        } else {
+            for (int i = 0; i < VEC && gx + i < w; i++) d[i] = sp[i];
+        }
+    }
+}
+
+template <typename Tin, typename Tout, int KS, int FEPI>
+__global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict__ src, Tout* __restrict__ dst,
+                                                          int h, int w, TapsF taps, int border, int idelta) {
+    constexpr int VEC = 16 / sizeof(Tin);
+    constexpr int R = KS / 2;
+    constexpr int RA = round_up_c(R, VEC > 4 ? VEC : 4);
+    constexpr int SW = TW + 2 * RA;
+    constexpr int ROWS = TH + 2 * R;
+    constexpr int OFF = (RA - R) & 3;                 // misalignment of the first tap inside a float4
+    constexpr int NV = (OFF + 8 + 2 * R + 3) / 4;     // float4 loads per 8 outputs
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_in = reinterpret_cast<float*>(smem_raw);
+    float* s_t = s_in + ROWS * SW + 8;                // +8 floats slack: the last item may read past its row
+    Tout* s_out = reinterpret_cast<Tout*>(s_t + ROWS * TW);
+    src += (int64_t)blockIdx.z * h * w;
+    dst += (int64_t)blockIdx.z * h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+
+    // ---- load + convert
+    {
+        constexpr int VPR = SW / VEC;
+        const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        for (int v = threadIdx.x; v < ROWS * VPR; v += kThreads) {
+            const int ry = v / VPR, vx = v - ry * VPR;
+            const int gy = yam_border(y0 - R + ry, h, border);
+            const int gx = x0 - RA + vx * VEC;
+            const Tin* row = src + (int64_t)gy * w;
+            float f[VEC];
+            if (row_aligned && gx >= 0 && gx + VEC <= w) {
+                const uint4 q = *reinterpret_cast<const uint4*>(row + gx);
+                vec_to_f32<Tin>(q, f);
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < VEC; i++) f[i] = (float)row[yam_border(gx + i, w, border)];
+            }
+            float* d = s_in + ry * SW + vx * VEC;
+#pragma unroll
+            for (int i = 0; i < VEC; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal pass: 8 outputs per item
+    {
+        constexpr int GROUPS = TW / 8;
+        for (int item = threadIdx.x; item < ROWS * GROUPS; item += kThreads) {
+            const int ry = item / GROUPS, cg = item - ry * GROUPS;
+            const float* p = s_in + ry * SW + cg * 8 + (RA - R) - OFF;
+            float e[NV * 4];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const float4 q = *reinterpret_cast<const float4*>(p + 4 * v);
+                e[4 * v] = q.x; e[4 * v + 1] = q.y; e[4 * v + 2] = q.z; e[4 * v + 3] = q.w;
+            }
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = row_dot<KS>(e + OFF + j, taps, KS);
+            float* t = s_t + ry * TW + cg * 8;
+            *reinterpret_cast<float4*>(t) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(t + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical pass: lane -> column pair, warp -> RB rows
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int cx = 2 * lane;
+        const int r0 = warp * RB;
+        float c0[RB + KS - 1], c1[RB + KS - 1];
+#pragma unroll
+        for (int i = 0; i < RB + KS - 1; i++) {
+            const float2 v = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TW + cx);
+            c0[i] = v.x;
+            c1[i] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+            float a = __fmul_rn(taps.v[R], c0[j + R]);
+            float b = __fmul_rn(taps.v[R], c1[j + R]);
+#pragma unroll
+            for (int q = 1; q <= R; q++) {
+                a = __fmaf_rn(__fadd_rn(c0[j + R + q], c0[j + R - q]), taps.v[R + q], a);
+                b = __fmaf_rn(__fadd_rn(c1[j + R + q], c1[j + R - q]), taps.v[R + q], b);
+            }
+            if (FEPI == FEPI_ADAPTIVE) {
+                // mean = rint(blur) (round-half-even via the 1.5*2^23 add; blur is a convex
+                // combination of pixel values so saturation can never trigger);
+                // dst = (src - mean > -idelta) ? 255 : 0, all values exact integers in float
+                const float2 sp = *reinterpret_cast<const float2*>(s_in + (r0 + j + R) * SW + RA + cx);
+                const float m0 = __fadd_rn(__fadd_rn(a, 12582912.0f), -12582912.0f);
+                const float m1 = __fadd_rn(__fadd_rn(b, 12582912.0f), -12582912.0f);
+                const float nd = -(float)idelta;
+                const uint32_t o0 = (__fadd_rn(sp.x, -m0) > nd) ? 255u : 0u;
+                const uint32_t o1 = (__fadd_rn(sp.y, -m1) > nd) ? 255u : 0u;
+                *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(s_out) + (r0 + j) * TW + cx) = (uint16_t)(o0 | (o1 << 8));
+            } else {
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_out) + (r0 + j) * TW + cx) = make_float2(a, b);
+            }
+        }
+    }
+    __syncthreads();
+    store_tile<Tout>(s_out, dst, h, w, x0, y0);
+}
+
+// ----------------------------------------------------------------------------------------------
 // median 3x3 / 5x5 (cv2.medianBlur, BORDER_REPLICATE): exact rank filter via min/max exchanges
 template <typename T, int KS>
 __global__ void __launch_bounds__(kThreads) median_kernel(const T* __restrict__ src, T* __restrict__ dst,
@@ -394,7 +563,7 @@ template <typename T>
 size_t fixed_smem(int ks) {
     const int VEC = 16 / sizeof(T);
     const int R = ks / 2, RA = round_up_c(R, VEC), SW = TW + 2 * RA, ROWS = TH + 2 * R;
-    return (size_t)round_up_c(ROWS * SW * (int)sizeof(T), 16) + (size_t)ROWS * TW * 4;
+    return (size_t)round_up_c(ROWS * SW * (int)sizeof(T), 16) + (size_t)ROWS * TW * 4 + (size_t)TH * TW * sizeof(T);
 }
 
 template <typename Tin>
@@ -402,6 +571,13 @@ size_t f32_smem(int ks) {
     const int VEC = 16 / sizeof(Tin);
     const int R = ks / 2, RA = round_up_c(R, VEC), SW = TW + 2 * RA, ROWS = TH + 2 * R;
     return (size_t)ROWS * SW * 4 + (size_t)ROWS * TW * 4;
+}
+
+template <typename Tin, typename Tout>
+size_t f32_tiled_smem(int ks) {
+    const int VEC = 16 / sizeof(Tin);
+    const int R = ks / 2, RA = round_up_c(R, VEC > 4 ? VEC : 4), SW = TW + 2 * RA, ROWS = TH + 2 * R;
+    return ((size_t)ROWS * SW + 8 + (size_t)ROWS * TW) * 4 + (size_t)TH * TW * sizeof(Tout);
 }
 
 template <typename K>
@@ -455,9 +631,10 @@ int launch_f32(yam_ctx* ctx, const Tin* src, Tout* dst, int64_t n, int64_t h, in
     const size_t smem = f32_smem<Tin>(ks);
 #define YAM_F32_CASE(K)                                                                              \
     case K: {                                                                                        \
-        if (int rc = set_smem(sep_f32_kernel<Tin, Tout, K, FEPI>, smem)) return rc;                  \
-        sep_f32_kernel<Tin, Tout, K, FEPI><<<grid, kThreads, smem, ctx->stream>>>(                  \
-            src, dst, (int)h, (int)w, taps, ks, border, sat_hi, idelta);                             \
+        const size_t tsmem = f32_tiled_smem<Tin, Tout>(K);                                           \
+        if (int rc = set_smem(sep_f32_tiled<Tin, Tout, K, FEPI>, tsmem)) return rc;                  \
+        sep_f32_tiled<Tin, Tout, K, FEPI><<<grid, kThreads, tsmem, ctx->stream>>>(                   \
+            src, dst, (int)h, (int)w, taps, border, idelta);                                         \
         break;                                                                                       \
     }
     switch (ks) {
