@@ -117,11 +117,54 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_
     return off + incl - v;
 }
 
-// ---- 1. pack: bits + per-block segment counts --------------------------------------------------
+// In-place exclusive scan of data[0..n) by ONE block (all kThreads threads); total -> *total_out.
+__device__ void block_scan_array(uint32_t* __restrict__ data, int64_t n, uint32_t* __restrict__ total_out,
+                                 uint32_t* s_tmp, uint32_t* s_carry) {
+    if (threadIdx.x == 0) *s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += kThreads * 4) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? __ldcg(data + i0 + k) : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t run = *s_carry + block_excl_scan_u32(mine, s_tmp);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) data[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) *s_carry = run;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = *s_carry;
+}
+
+// "last block done" election: returns true in every thread of the block that finishes last.
+// `counter` must be 0 on entry and is reset to 0 by the elected block.
+__device__ bool last_block_done(unsigned int* counter, unsigned int nblocks, int* s_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        *s_flag = (ticket == nblocks - 1);
+        if (*s_flag) *counter = 0;
+    }
+    __syncthreads();
+    if (*s_flag) __threadfence();
+    return *s_flag != 0;
+}
+
+// ---- 1. pack: bits + per-block segment counts; the last block scans the counts ------------------
 __global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __restrict__ mask, CclGeom g,
                                                             uint32_t* __restrict__ bits,
-                                                            uint32_t* __restrict__ block_counts) {
+                                                            uint32_t* __restrict__ block_counts,
+                                                            uint32_t* __restrict__ total_nodes,
+                                                            unsigned int* __restrict__ counter) {
     __shared__ uint32_t s_tmp[kThreads / 32];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_flag;
     const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = 0;
     if (gw < g.total_words) {
@@ -148,216 +191,195 @@ __global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __res
     }
     const uint32_t total = block_sum_u32(__popc(seg_starts(b)), s_tmp);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+    if (last_block_done(counter, gridDim.x, &s_flag))
+        block_scan_array(block_counts, gridDim.x, total_nodes, s_tmp, &s_carry);
 }
 
-// ---- exclusive scan of a u32 array in place (single block); total -> *total_out ------------------
-__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ data, int64_t n,
-                                                        uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 4096) {
-        // 4 consecutive elements per thread
-        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
-        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t wv = s_warp[lane];
-            uint32_t wi = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += up;
-            }
-            s_warp[lane] = wi - wv;
-        }
-        __syncthreads();
-        uint32_t run = s_carry + s_warp[warp] + incl - mine;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (i0 + k < n) data[i0 + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = run;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = s_carry;
-}
-
-// ---- 3. node base per word + parent init -----------------------------------------------------------
+// ---- 2. node base per word; parent init; node -> (word, start bit) ----------------------------------
 __global__ void __launch_bounds__(kThreads) ccl_nodebase_kernel(const uint32_t* __restrict__ bits, CclGeom g,
                                                                 const uint32_t* __restrict__ block_offsets,
-                                                                uint32_t* __restrict__ nbase, int* __restrict__ P) {
+                                                                uint32_t* __restrict__ nbase, int* __restrict__ P,
+                                                                uint32_t* __restrict__ node_info) {
     __shared__ uint32_t s_tmp[kThreads / 32];
     const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b = gw < g.total_words ? bits[gw] : 0u;
-    const uint32_t cnt = __popc(seg_starts(b));
-    const uint32_t base = block_offsets[blockIdx.x] + block_excl_scan_u32(cnt, s_tmp);
+    uint32_t starts = seg_starts(b);
+    const uint32_t base = block_offsets[blockIdx.x] + block_excl_scan_u32(__popc(starts), s_tmp);
     if (gw < g.total_words) {
         nbase[gw] = base;
-        for (uint32_t k = 0; k < cnt; k++) P[base + k] = (int)(base + k);
+        uint32_t k = 0;
+        while (starts) {
+            const int sbit = __ffs(starts) - 1;
+            starts &= starts - 1;
+            P[base + k] = (int)(base + k);
+            node_info[base + k] = ((uint32_t)gw << 5) | (uint32_t)sbit;
+            k++;
+        }
     }
 }
 
-// ---- 4. union ----------------------------------------------------------------------------------
+// ---- 3. union: one thread per segment ----------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) ccl_union_kernel(const uint32_t* __restrict__ bits,
-                                                             const uint32_t* __restrict__ nbase, CclGeom g,
+                                                             const uint32_t* __restrict__ nbase,
+                                                             const uint32_t* __restrict__ node_info, CclGeom g,
+                                                             const uint32_t* __restrict__ total_nodes,
                                                              int* __restrict__ P) {
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gw >= g.total_words) return;
-    const uint32_t b = bits[gw];
-    if (!b) return;
-    const int64_t row_id = gw / g.wpr;
-    const int j = (int)(gw - row_id * g.wpr);
-    const int y = (int)(row_id % g.h);
-    const int my_base = (int)nbase[gw];
-    // horizontal: the segment at bit 0 continues the segment that ends at bit 31 of the previous word
-    if ((b & 1u) && j > 0) {
-        const uint32_t pv = bits[gw - 1];
-        if (pv >> 31) unite(P, my_base, (int)nbase[gw - 1] + seg_index(pv, 31));
-    }
-    if (y == 0) return;
-    // vertical: 34-column window of the row above; bit k of `above` <-> column 32*j + k - 1
-    const uint32_t u = bits[gw - g.wpr];
-    const uint32_t up = j > 0 ? bits[gw - g.wpr - 1] : 0u;
-    const uint32_t un = j + 1 < g.wpr ? bits[gw - g.wpr + 1] : 0u;
-    const unsigned long long above =
-        (unsigned long long)(up >> 31) | ((unsigned long long)u << 1) | ((unsigned long long)(un & 1u) << 33);
-    if (!above) return;
-    const int base_u = u ? (int)nbase[gw - g.wpr] : 0;
-    uint32_t starts = seg_starts(b);
-    int k = 0;
-    while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
+    const int total = (int)*total_nodes;
+    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < total; node += gridDim.x * blockDim.x) {
+        const uint32_t info = node_info[node];
+        const int64_t gw = info >> 5;
+        const int s = (int)(info & 31u);
+        const uint32_t b = bits[gw];
+        const int64_t row_id = gw / g.wpr;
+        const int j = (int)(gw - row_id * g.wpr);
+        const int y = (int)(row_id % g.h);
+        // horizontal: a segment at bit 0 continues the segment that ends at bit 31 of the previous word
+        if (s == 0 && j > 0) {
+            const uint32_t pv = bits[gw - 1];
+            if (pv >> 31) unite(P, node, (int)nbase[gw - 1] + seg_index(pv, 31));
+        }
+        if (y == 0) continue;
+        // vertical: 34-column window of the row above; bit k of `above` <-> column 32*j + k - 1
+        const uint32_t u = bits[gw - g.wpr];
+        const uint32_t up = j > 0 ? bits[gw - g.wpr - 1] : 0u;
+        const uint32_t un = j + 1 < g.wpr ? bits[gw - g.wpr + 1] : 0u;
+        const unsigned long long above =
+            (unsigned long long)(up >> 31) | ((unsigned long long)u << 1) | ((unsigned long long)(un & 1u) << 33);
         const uint32_t from_s = b >> s;
         const int len = (~from_s) ? __ffs(~from_s) - 1 : 32 - s;
         const int e = s + len - 1;
-        // window bits s .. e+2
-        const unsigned long long wmask = ((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull);
+        const unsigned long long wmask = ((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull);  // bits s .. e+2
         unsigned long long m = above & wmask;
+        if (!m) continue;
+        const int base_u = u ? (int)nbase[gw - g.wpr] : 0;
         while (m) {
             const int k0 = __ffsll((long long)m) - 1;
             m &= m + (1ull << k0);  // clear the lowest run of ones
-            int node;
+            int other;
             if (k0 == 0) {
-                node = (int)nbase[gw - g.wpr - 1] + seg_index(up, 31);
+                other = (int)nbase[gw - g.wpr - 1] + seg_index(up, 31);
             } else if (k0 == 33) {
-                node = (int)nbase[gw - g.wpr + 1];  // bit 0 of the next word starts its first segment
+                other = (int)nbase[gw - g.wpr + 1];  // bit 0 of the next word starts its first segment
             } else {
-                node = base_u + seg_index(u, k0 - 1);
+                other = base_u + seg_index(u, k0 - 1);
             }
-            unite(P, my_base + k, node);
+            unite(P, node, other);
         }
-        k++;
     }
 }
 
-// ---- 5. flatten + per-block root counts -------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_flatten_kernel(const uint32_t* __restrict__ bits,
-                                                               const uint32_t* __restrict__ nbase, CclGeom g,
+// ---- 4. flatten (one thread per node) + root counts per 256-node chunk; last block scans them ---------
+__global__ void __launch_bounds__(kThreads) ccl_flatten_kernel(const uint32_t* __restrict__ total_nodes,
                                                                int* __restrict__ P,
-                                                               uint32_t* __restrict__ block_roots) {
+                                                               uint32_t* __restrict__ chunk_roots,
+                                                               uint32_t* __restrict__ total_roots,
+                                                               unsigned int* __restrict__ counter) {
     __shared__ uint32_t s_tmp[kThreads / 32];
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t roots = 0;
-    if (gw < g.total_words) {
-        const uint32_t cnt = __popc(seg_starts(bits[gw]));
-        if (cnt) {
-            const int base = (int)nbase[gw];
-            for (uint32_t k = 0; k < cnt; k++) {
-                const int node = base + (int)k;
-                const int r = find_root_ro(P, node);
-                if (r == node) roots++;
-                else P[node] = r;
-            }
+    __shared__ uint32_t s_carry;
+    __shared__ int s_flag;
+    const int total = (int)*total_nodes;
+    const int chunks = (total + kThreads - 1) / kThreads;
+    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+        const int node = c * kThreads + threadIdx.x;
+        uint32_t is_root = 0;
+        if (node < total) {
+            const int r = find_root_ro(P, node);
+            if (r == node) is_root = 1;
+            else P[node] = r;
         }
+        const uint32_t t = block_sum_u32(is_root, s_tmp);
+        if (threadIdx.x == 0) chunk_roots[c] = t;
+        __syncthreads();
     }
-    const uint32_t total = block_sum_u32(roots, s_tmp);
-    if (threadIdx.x == 0) block_roots[blockIdx.x] = total;
+    if (last_block_done(counter, gridDim.x, &s_flag))
+        block_scan_array(chunk_roots, chunks, total_roots, s_tmp, &s_carry);
 }
 
-// ---- 7. root labels: P[root] = -(rank + 1); rbase[word] = roots before this word --------------------
-__global__ void __launch_bounds__(kThreads) ccl_rootlabel_kernel(const uint32_t* __restrict__ bits,
-                                                                 const uint32_t* __restrict__ nbase, CclGeom g,
-                                                                 const uint32_t* __restrict__ block_root_offsets,
-                                                                 int* __restrict__ P, uint32_t* __restrict__ rbase) {
+// ---- 5. root labels: P[root] = -(rank + 1) ---------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ccl_rootlabel_kernel(const uint32_t* __restrict__ total_nodes,
+                                                                 const uint32_t* __restrict__ chunk_offsets,
+                                                                 int* __restrict__ P) {
     __shared__ uint32_t s_tmp[kThreads / 32];
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t rootbits = 0, cnt = 0;
-    int base = 0;
-    if (gw < g.total_words) {
-        cnt = __popc(seg_starts(bits[gw]));
-        if (cnt) {
-            base = (int)nbase[gw];
-            for (uint32_t k = 0; k < cnt; k++)
-                if (__ldcg(P + base + (int)k) == base + (int)k) rootbits |= 1u << k;
-        }
-    }
-    const uint32_t before = block_root_offsets[blockIdx.x] + block_excl_scan_u32(__popc(rootbits), s_tmp);
-    if (gw < g.total_words) {
-        rbase[gw] = before;
-        uint32_t rank = before;
-        while (rootbits) {
-            const int k = __ffs(rootbits) - 1;
-            rootbits &= rootbits - 1;
-            P[base + k] = -(int)(rank + 1);
-            rank++;
-        }
+    const int total = (int)*total_nodes;
+    const int chunks = (total + kThreads - 1) / kThreads;
+    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+        const int node = c * kThreads + threadIdx.x;
+        const uint32_t is_root = (node < total && __ldcg(P + node) == node) ? 1u : 0u;
+        const uint32_t rank = chunk_offsets[c] + block_excl_scan_u32(is_root, s_tmp);
+        if (is_root) P[node] = -(int)(rank + 1);
+        __syncthreads();
     }
 }
 
-// ---- 8. final labels ----------------------------------------------------------------------------
-// block = 256 words = 8192 pixels; labels are staged in shared memory (swizzled at int4
-// granularity: both the per-thread row writes and the coalesced read-out are conflict free)
-__global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __restrict__ bits,
-                                                             const uint32_t* __restrict__ nbase,
-                                                             const uint32_t* __restrict__ rbase, CclGeom g,
-                                                             const int* __restrict__ P, int32_t* __restrict__ labels,
-                                                             const uint32_t* __restrict__ total_roots,
-                                                             int32_t* __restrict__ counts) {
-    __shared__ int4 s_out[kThreads * 8];
-    const int64_t gw0 = (int64_t)blockIdx.x * blockDim.x;
+// ---- 6. per-frame root offsets and component counts (one thread per frame) ---------------------------------
+__global__ void ccl_frame_offsets_kernel(const uint32_t* __restrict__ nbase, CclGeom g,
+                                         const uint32_t* __restrict__ total_nodes,
+                                         const uint32_t* __restrict__ total_roots,
+                                         const uint32_t* __restrict__ chunk_offsets, const int* __restrict__ P,
+                                         uint32_t* __restrict__ frame_off, int32_t* __restrict__ counts) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= g.frames) return;
+    auto roots_before_frame = [&](int frame) -> uint32_t {
+        if (frame >= g.frames) return *total_roots;
+        const uint32_t n0 = nbase[(int64_t)frame * g.words_per_frame];
+        if (n0 >= *total_nodes) return *total_roots;
+        uint32_t r = chunk_offsets[n0 / kThreads];
+        for (uint32_t i = (n0 / kThreads) * kThreads; i < n0; i++) r += (P[i] < 0) ? 1u : 0u;
+        return r;
+    };
+    const uint32_t here = roots_before_frame(f), next = roots_before_frame(f + 1);
+    frame_off[f] = here;
+    if (counts) counts[f] = (int32_t)(next - here);
+}
+
+// ---- 7. final labels ----------------------------------------------------------------------------
+// block = kFinalThreads words; labels are staged in shared memory (swizzled at int4 granularity:
+// both the per-thread row writes and the coalesced read-out are conflict free)
+constexpr int kFinalThreads = 128;
+
+__global__ void __launch_bounds__(kFinalThreads) ccl_final_kernel(const uint32_t* __restrict__ bits,
+                                                                  const uint32_t* __restrict__ nbase,
+                                                                  const uint32_t* __restrict__ frame_off, CclGeom g,
+                                                                  const int* __restrict__ P,
+                                                                  int32_t* __restrict__ labels) {
+    __shared__ int4 s_out[kFinalThreads * 8];
+    const int64_t gw0 = (int64_t)blockIdx.x * kFinalThreads;
     const int64_t gw = gw0 + threadIdx.x;
     const int t = threadIdx.x;
     uint32_t b = 0;
-    int frame_off = 0;
+    int off = 0, base = 0;
     if (gw < g.total_words) {
         b = bits[gw];
-        const int64_t frame = gw / g.words_per_frame;
-        if (b && frame > 0) frame_off = (int)rbase[frame * g.words_per_frame];
-        // per-frame component counts (one thread per frame boundary word)
-        if (counts && gw == frame * g.words_per_frame) {
-            const uint32_t here = rbase[gw];
-            const uint32_t next = (frame + 1 < g.frames) ? rbase[(frame + 1) * g.words_per_frame] : *total_roots;
-            counts[frame] = (int32_t)(next - here);
+        if (b) {
+            base = (int)nbase[gw];
+            if (g.frames > 1) off = (int)frame_off[gw / g.words_per_frame];
         }
     }
     int32_t out[32];
     if (b) {
-        const int base = (int)nbase[gw];
+        // first-level loads for up to 4 segments are issued together; more segments are rare
+        uint32_t starts = seg_starts(b);
+        const int nseg = __popc(starts);
+        int lab[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) lab[k] = k < nseg ? __ldg(P + base + k) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (lab[k] >= 0) lab[k] = __ldg(P + lab[k]);  // non-root: its root holds -(label)
         int cur = 0, k = 0;
 #pragma unroll
         for (int i = 0; i < 32; i++) {
             const bool set = (b >> i) & 1u;
             const bool start = set && (i == 0 || !((b >> (i - 1)) & 1u));
             if (start) {
-                int v = __ldg(P + base + k);
-                if (v >= 0) v = __ldg(P + v);  // non-root: follow to the root, which holds -(label)
-                cur = -v - frame_off;
+                int v;
+                if (k < 4) {
+                    v = k == 0 ? lab[0] : k == 1 ? lab[1] : k == 2 ? lab[2] : lab[3];
+                } else {
+                    v = __ldg(P + base + k);
+                    if (v >= 0) v = __ldg(P + v);
+                }
+                cur = -v - off;
                 k++;
             }
             out[i] = set ? cur : 0;
@@ -371,14 +393,14 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
         s_out[t * 8 + ((q + t) & 7)] = make_int4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
     __syncthreads();
     if ((g.w & 31) == 0 && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0)) {
-        // rows are whole words: the block's 256 words are 8192 consecutive labels
+        // rows are whole words: the block's words are consecutive labels
         int4* dst = reinterpret_cast<int4*>(labels + gw0 * 32);
-        const int64_t valid_words = g.total_words - gw0 < kThreads ? g.total_words - gw0 : kThreads;
+        const int64_t valid_words = g.total_words - gw0 < kFinalThreads ? g.total_words - gw0 : kFinalThreads;
 #pragma unroll
         for (int it = 0; it < 8; it++) {
-            const int idx = it * kThreads + t;  // int4 index inside the block tile
+            const int idx = it * kFinalThreads + t;  // int4 index inside the block tile
             const int wd = idx >> 3, q = idx & 7;
-            if (wd < valid_words) dst[idx] = s_out[wd * 8 + ((q + wd) & 7)];
+            if (wd < valid_words) __stcs(dst + idx, s_out[wd * 8 + ((q + wd) & 7)]);
         }
     } else if (gw < g.total_words) {
         const int64_t row_id = gw / g.wpr;
@@ -540,42 +562,50 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
     g.frames = (int)n;
     YAM_REQUIRE(g.words_per_frame * 32 < (1ll << 31), "ccl: frame too large for int32 labels (%lld x %lld)",
                 (long long)h, (long long)w);
-    YAM_REQUIRE(g.total_words * 16 < (1ll << 31), "ccl: stack too large for one call (%lld words); split the stack",
-                (long long)g.total_words);
+    YAM_REQUIRE(g.total_words * 16 < (1ll << 31) && g.total_words < (1ll << 27),
+                "ccl: stack too large for one call (%lld words); split the stack", (long long)g.total_words);
     const int64_t nblocks = (g.total_words + kThreads - 1) / kThreads;
-    // scratch layout: bits | nbase | rbase | blockA | blockB | totals[2] | counts | P (<= 16 nodes per word)
+    const int64_t max_nodes = g.total_words * 16;  // at most 16 run segments per 32-pixel word
+    const int64_t max_chunks = (max_nodes + kThreads - 1) / kThreads;
+    // scratch: bits | nbase | blockA | chunkB | frame_off | misc(totals[2], counter) | counts | node_info | P
     const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
     const size_t blk_bytes = yam_align_up((size_t)nblocks * 4, 256);
-    const size_t cnt_bytes = yam_align_up((size_t)n * 4, 256);
-    const size_t p_bytes = yam_align_up((size_t)g.total_words * 16 * 4, 256);
+    const size_t chunk_bytes = yam_align_up((size_t)max_chunks * 4, 256);
+    const size_t frame_bytes = yam_align_up((size_t)n * 4, 256);
+    const size_t node_bytes = yam_align_up((size_t)max_nodes * 4, 256);
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, 3 * words_bytes + 2 * blk_bytes + 256 + cnt_bytes + p_bytes, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, 2 * words_bytes + blk_bytes + chunk_bytes + 2 * frame_bytes + 256 + 2 * node_bytes, &scratch)) return rc;
     char* sp = (char*)scratch;
-    uint32_t* bits = (uint32_t*)sp;
-    uint32_t* nbase = (uint32_t*)(sp + words_bytes);
-    uint32_t* rbase = (uint32_t*)(sp + 2 * words_bytes);
-    uint32_t* blockA = (uint32_t*)(sp + 3 * words_bytes);
-    uint32_t* blockB = (uint32_t*)(sp + 3 * words_bytes + blk_bytes);
-    uint32_t* totals = (uint32_t*)(sp + 3 * words_bytes + 2 * blk_bytes);
-    int32_t* counts = counts_dev ? counts_dev : (int32_t*)(sp + 3 * words_bytes + 2 * blk_bytes + 256);
-    int* P = (int*)(sp + 3 * words_bytes + 2 * blk_bytes + 256 + cnt_bytes);
+    uint32_t* bits = (uint32_t*)sp; sp += words_bytes;
+    uint32_t* nbase = (uint32_t*)sp; sp += words_bytes;
+    uint32_t* blockA = (uint32_t*)sp; sp += blk_bytes;
+    uint32_t* chunkB = (uint32_t*)sp; sp += chunk_bytes;
+    uint32_t* frame_off = (uint32_t*)sp; sp += frame_bytes;
+    uint32_t* totals = (uint32_t*)sp;            // [0] nodes, [1] roots
+    unsigned int* counter = (unsigned int*)(sp + 16); sp += 256;
+    int32_t* counts = counts_dev ? counts_dev : (int32_t*)sp; sp += frame_bytes;
+    uint32_t* node_info = (uint32_t*)sp; sp += node_bytes;
+    int* P = (int*)sp;
 
+    // the election counter is self-resetting, but scratch is shared with other operators
+    YAM_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), ctx->stream));
     const unsigned gblocks = (unsigned)nblocks;
-    ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits, blockA);
+    const unsigned pgrid = (unsigned)(ctx->num_sms * 8);  // persistent grids for the node-parallel kernels
+    ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits, blockA, totals, counter);
     YAM_LAUNCHED(ctx);
-    scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(blockA, nblocks, totals);
+    ccl_nodebase_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, nbase, P, node_info);
     YAM_LAUNCHED(ctx);
-    ccl_nodebase_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, nbase, P);
+    ccl_union_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(bits, nbase, node_info, g, totals, P);
     YAM_LAUNCHED(ctx);
-    ccl_union_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, P);
+    ccl_flatten_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(totals, P, chunkB, totals + 1, counter);
     YAM_LAUNCHED(ctx);
-    ccl_flatten_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, P, blockB);
+    ccl_rootlabel_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(totals, chunkB, P);
     YAM_LAUNCHED(ctx);
-    scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(blockB, nblocks, totals + 1);
+    ccl_frame_offsets_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(nbase, g, totals, totals + 1, chunkB, P,
+                                                                                 frame_off, counts);
     YAM_LAUNCHED(ctx);
-    ccl_rootlabel_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, g, blockB, P, rbase);
-    YAM_LAUNCHED(ctx);
-    ccl_final_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, nbase, rbase, g, P, labels, totals + 1, counts);
+    const unsigned fblocks = (unsigned)((g.total_words + kFinalThreads - 1) / kFinalThreads);
+    ccl_final_kernel<<<fblocks, kFinalThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels);
     YAM_LAUNCHED(ctx);
     if (counts_host) {
         YAM_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));

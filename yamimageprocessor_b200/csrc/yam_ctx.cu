@@ -270,27 +270,36 @@ void yam_host_structuring_element(int shape, int k, uint8_t* out) {
 
 int yam_host_otsu(const uint64_t* h, int bins) {
     // cv2 getThreshVal_Otsu_{8u,16u}: fp64 recurrence, strict '>' keeps the first maximum.
-    // volatile-free plain doubles: this TU is compiled without FMA contraction (-ffp-contract=off).
-    double total = 0;
-    for (int i = 0; i < bins; i++) total += (double)h[i];
-    if (total <= 0) return 0;
-    double scale = 1.0 / total;
-    double mu = 0;
-    for (int i = 0; i < bins; i++) mu += (double)i * (double)h[i];
+    // This TU is compiled without FMA contraction (-ffp-contract=off).
+    double total = 0, mu = 0;
+    int first = -1, last = -1;
+    for (int i = 0; i < bins; i++) {
+        if (h[i]) {
+            if (first < 0) first = i;
+            last = i;
+            total += (double)h[i];          // integer-valued: exact in any order
+            mu += (double)i * (double)h[i];
+        }
+    }
+    if (first < 0) return 0;
+    const double scale = 1.0 / total;
     mu *= scale;
     double mu1 = 0, q1 = 0, max_sigma = 0;
     int max_val = 0;
     const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
-    for (int i = 0; i < bins; i++) {
-        double p_i = (double)h[i] * scale;
+    // Bins before the first occupied one leave (mu1, q1) = (0, 0) and `continue`; bins after the last
+    // occupied one have q1 ~ 1 (> 1 - eps) and `continue`: both ranges are skipped without changing
+    // the result.  Empty bins in between are NOT skippable (mu1 = (mu1*q1)/q1 re-rounds).
+    for (int i = first; i <= last; i++) {
+        const double p_i = (double)h[i] * scale;
         mu1 *= q1;
         q1 += p_i;
-        double q2 = 1.0 - q1;
-        double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
+        const double q2 = 1.0 - q1;
+        const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
         if (mn < eps || mx > 1.0 - eps) continue;
         mu1 = (mu1 + (double)i * p_i) / q1;
-        double mu2 = (mu - q1 * mu1) / q2;
-        double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+        const double mu2 = (mu - q1 * mu1) / q2;
+        const double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
         if (sigma > max_sigma) {
             max_sigma = sigma;
             max_val = i;

@@ -12,6 +12,10 @@
 // 8-bit histograms use per-warp privatised 256-bin shared histograms.
 #include <math.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "yam_common.cuh"
 #include "yam_host.h"
 
@@ -490,6 +494,33 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const T* __restrict__ 
     }
 }
 
+// Otsu recurrence for several frames on host threads (the fp64 recurrence is sequential per frame).
+void otsu_scan_frames_host(const uint64_t* hists, int bins, int64_t n, int32_t* out) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const int64_t nt = n < (int64_t)hw ? n : (int64_t)(hw < 32 ? hw : 32);
+    if (nt <= 1) {
+        for (int64_t f = 0; f < n; f++) out[f] = yam_host_otsu(hists + f * bins, bins);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t f = next.fetch_add(1);
+            if (f >= n) break;
+            out[f] = yam_host_otsu(hists + f * bins, bins);
+        }
+    };
+    std::vector<std::thread> pool;
+    try {
+        for (int64_t t = 1; t < nt; t++) pool.emplace_back(work);
+    } catch (...) {
+        // could not start (all) helpers: the calling thread finishes whatever is left
+    }
+    work();
+    for (auto& th : pool) th.join();
+}
+
 int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
               unsigned long long* hist) {
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
@@ -543,17 +574,26 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     unsigned long long* hist = (unsigned long long*)scratch;
     int32_t* t_dev = thresh_dev ? thresh_dev : (int32_t*)((char*)scratch + yam_align_up(hist_bytes, 256));
     if (int rc = hist_into(ctx, src, n, h, w, dtype, hist)) return rc;
-    // scan: host for few frames of 16-bit bins (sequential fp64 recurrence), device otherwise
-    const bool host_scan = (dtype == YAM_U16 && n < 8);
+    // scan: the fp64 recurrence is sequential per frame.  65536 dependent divisions take ~0.3 ms on
+    // a CPU core and ~6 ms on one GPU thread, so 16-bit histograms are scanned on host threads
+    // (chunks of <= 64 frames through a pinned buffer); 256-bin histograms stay on the device.
+    const bool host_scan = (dtype == YAM_U16);
     if (host_scan) {
+        const int64_t chunk = 64;
         void* pinned = nullptr;
-        if (int rc = yam_pinned(ctx, hist_bytes + sizeof(int32_t) * n, &pinned)) return rc;
-        YAM_CUDA(cudaMemcpyAsync(pinned, hist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        YAM_CUDA(cudaStreamSynchronize(ctx->stream));
-        int32_t* t_host = (int32_t*)((char*)pinned + hist_bytes);
-        for (int64_t f = 0; f < n; f++) t_host[f] = yam_host_otsu((const uint64_t*)pinned + f * bins, bins);
-        YAM_CUDA(cudaMemcpyAsync(t_dev, t_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-        if (thresh_host) memcpy(thresh_host, t_host, sizeof(int32_t) * n);
+        const int64_t first = n < chunk ? n : chunk;
+        if (int rc = yam_pinned(ctx, (size_t)first * (sizeof(unsigned long long) * bins + sizeof(int32_t)), &pinned)) return rc;
+        int32_t* t_stage = (int32_t*)((char*)pinned + (size_t)first * sizeof(unsigned long long) * bins);
+        for (int64_t f0 = 0; f0 < n; f0 += chunk) {
+            const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
+            YAM_CUDA(cudaMemcpyAsync(pinned, hist + f0 * bins, sizeof(unsigned long long) * bins * nf,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            YAM_CUDA(cudaStreamSynchronize(ctx->stream));
+            otsu_scan_frames_host((const uint64_t*)pinned, bins, nf, t_stage);
+            YAM_CUDA(cudaMemcpyAsync(t_dev + f0, t_stage, sizeof(int32_t) * nf, cudaMemcpyHostToDevice, ctx->stream));
+            if (thresh_host) memcpy(thresh_host + f0, t_stage, sizeof(int32_t) * nf);
+            if (f0 + chunk < n) YAM_CUDA(cudaStreamSynchronize(ctx->stream));  // t_stage is reused
+        }
     } else {
         otsu_scan_kernel<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(hist, bins, n, t_dev);
         YAM_LAUNCHED(ctx);
