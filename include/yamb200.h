@@ -150,6 +150,17 @@ int yam_equalize_hist(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64
 int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
               double clip_limit, int tiles_x, int tiles_y);
 
+/* CLAHE split in two for row-strip sharding of a mosaic (each rank computes the LUTs of the tile
+ * rows it owns, LUTs are all-gathered, every rank applies them to its rows with GLOBAL geometry):
+ * yam_clahe_luts  -> luts_dev[tiles_y][tiles_x][bins] (source dtype) for the single image `src`;
+ * yam_clahe_apply -> `rows` x w pixels whose first row is global row y_offset of an image tiled
+ *                    tiles_x x tiles_y with tiles of tile_w x tile_h pixels. */
+int yam_clahe_luts(yam_ctx* ctx, const void* src, int64_t h, int64_t w, int dtype, double clip_limit,
+                   int tiles_x, int tiles_y, void* luts_dev);
+int yam_clahe_apply(yam_ctx* ctx, const void* src, void* dst, int64_t rows, int64_t w, int dtype,
+                    const void* luts_dev, int tiles_x, int tiles_y, int tile_w, int tile_h,
+                    int64_t y_offset);
+
 /* ---- K10 connected components --------------------------------------------------------------
  * 8-connectivity, background 0, labels 1..N per frame numbered in raster order of each
  * component's first pixel (skimage.measure.label order — core/extraction.py:60,73; same partition
@@ -157,6 +168,10 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
  * labels I32.  counts_dev[n] int32 on device (optional), counts_host[n] optional. */
 int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
                   int32_t* counts_dev, int32_t* counts_host);
+
+/* labels[i] = remap_dev[labels[i]] for labels in (0, remap_size); used by the cross-strip label merge */
+int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev,
+                int64_t remap_size);
 
 /* ---- K11 region properties -----------------------------------------------------------------
  * skimage.measure.regionprops restated (core/extraction.py:61,74): for a single labelled frame

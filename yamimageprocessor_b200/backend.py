@@ -353,6 +353,49 @@ class Backend:
                    int(tile_grid[0]), int(tile_grid[1]))
         return out
 
+    def clahe_luts(self, img, clip_limit: float = 2.0, tile_grid: Tuple[int, int] = (8, 8)):
+        """Per-tile CLAHE LUTs of a single image: tensor (tiles_y, tiles_x, bins) in the image dtype."""
+        torch = _torch()
+        img = self._check(img, ndim=(2,), dtypes=(torch.uint8, torch.uint16))
+        h, w = int(img.shape[0]), int(img.shape[1])
+        bins = 256 if img.dtype == torch.uint8 else 65536
+        luts = torch.empty((int(tile_grid[1]), int(tile_grid[0]), bins), dtype=img.dtype, device=self.device)
+        self._call("yam_clahe_luts", self._p(img), h, w, _dtype_code(img), float(clip_limit), int(tile_grid[0]),
+                   int(tile_grid[1]), self._p(luts))
+        return luts
+
+    def clahe_apply(self, rows, luts, tile_size: Tuple[int, int], y_offset: int = 0):
+        """Blend precomputed LUTs over `rows` (a block of rows starting at global row y_offset);
+        luts is (tiles_y, tiles_x, bins), tile_size = (tile_w, tile_h) of the WHOLE image."""
+        torch = _torch()
+        rows = self._check(rows, ndim=(2,), dtypes=(torch.uint8, torch.uint16))
+        if luts.dtype != rows.dtype or luts.dim() != 3:
+            raise TypeError("luts must be (tiles_y, tiles_x, bins) in the image dtype")
+        luts = luts.contiguous()
+        out = torch.empty_like(rows)
+        self._call("yam_clahe_apply", self._p(rows), self._p(out), int(rows.shape[0]), int(rows.shape[1]),
+                   _dtype_code(rows), self._p(luts), int(luts.shape[1]), int(luts.shape[0]), int(tile_size[0]),
+                   int(tile_size[1]), int(y_offset))
+        return out
+
+    def relabel(self, labels, remap):
+        """In place: labels = remap[labels] (remap int32 on device, remap[0] must be 0)."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(2, 3), dtypes=(torch.int32,), name="labels")
+        if remap.dtype != torch.int32 or remap.device != self.device:
+            raise TypeError("remap must be an int32 CUDA tensor")
+        remap = remap.contiguous()
+        self._call("yam_relabel", self._p(labels), labels.numel(), self._p(remap), remap.numel())
+        return labels
+
+    def otsu_from_histogram(self, hist: np.ndarray) -> int:
+        """cv2's Otsu recurrence on a host histogram (int64/uint64 counts); host-only helper."""
+        h = np.ascontiguousarray(hist, dtype=np.uint64)
+        t = C.c_int()
+        _lib.check("yam_otsu_from_hist", self.lib.yam_otsu_from_hist(h.ctypes.data_as(C.c_void_p), int(h.size),
+                                                                      C.cast(C.byref(t), C.c_void_p)))
+        return int(t.value)
+
     # ------------------------------------------------------------------ K10 / K11
     def ccl_label(self, mask):
         """Returns (labels int32 like mask, counts int32[n] on device)."""

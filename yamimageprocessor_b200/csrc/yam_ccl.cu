@@ -544,9 +544,47 @@ __global__ void __launch_bounds__(kThreads) props_kernel(const int32_t* __restri
     }
 }
 
+__global__ void __launch_bounds__(kThreads) relabel_kernel(int32_t* __restrict__ labels, int64_t count,
+                                                           const int32_t* __restrict__ remap, int64_t remap_size) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
+    int64_t done = 0;
+    if (aligned) {
+        const int64_t groups = count / 4;
+        for (int64_t g = tid; g < groups; g += stride) {
+            int4 v = reinterpret_cast<int4*>(labels)[g];
+            if (v.x | v.y | v.z | v.w) {
+                v.x = (v.x > 0 && v.x < remap_size) ? __ldg(remap + v.x) : 0;
+                v.y = (v.y > 0 && v.y < remap_size) ? __ldg(remap + v.y) : 0;
+                v.z = (v.z > 0 && v.z < remap_size) ? __ldg(remap + v.z) : 0;
+                v.w = (v.w > 0 && v.w < remap_size) ? __ldg(remap + v.w) : 0;
+                reinterpret_cast<int4*>(labels)[g] = v;
+            }
+        }
+        done = groups * 4;
+    }
+    for (int64_t i = done + tid; i < count; i += stride) {
+        const int v = labels[i];
+        if (v) labels[i] = (v > 0 && v < remap_size) ? remap[v] : 0;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev, int64_t remap_size) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(labels && remap_dev && count > 0 && remap_size > 0, "relabel: bad arguments");
+    int64_t bx = (count / 4 + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    relabel_kernel<<<(unsigned)bx, kThreads, 0, ctx->stream>>>(labels, count, remap_dev, remap_size);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
 
 int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
                   int32_t* counts_dev, int32_t* counts_host) {

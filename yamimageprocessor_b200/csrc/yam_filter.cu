@@ -51,8 +51,10 @@ __device__ __forceinline__ void store_tile(const Tout* __restrict__ s_out, Tout*
 // TS = smem element type (T itself, or float when Tin is converted on load).
 template <typename T, typename TS>
 __device__ __forceinline__ void load_tile(const T* __restrict__ src, TS* __restrict__ s_in, int h, int w,
-                                          int x0, int y0, int r, int ra, int SW, int rows, int border) {
+                                          int x0, int y0, int r, int ra, int SW, int rows, int border,
+                                          int pitch = 0) {
     constexpr int VEC = 16 / sizeof(T);
+    if (pitch == 0) pitch = SW;  // SW = loaded width; pitch = row stride in shared memory
     const int vec_per_row = SW / VEC;
     const int total = rows * vec_per_row;
     const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -61,7 +63,7 @@ __device__ __forceinline__ void load_tile(const T* __restrict__ src, TS* __restr
         const int vx = v - ry * vec_per_row;
         const int gy = yam_border(y0 - r + ry, h, border);
         const int gx = x0 - ra + vx * VEC;
-        TS* d = s_in + ry * SW + vx * VEC;
+        TS* d = s_in + ry * pitch + vx * VEC;
         const T* row = src + (int64_t)gy * w;
         if (row_aligned && gx >= 0 && gx + VEC <= w) {
             uint4 q = *reinterpret_cast<const uint4*>(row + gx);
@@ -90,7 +92,12 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
     constexpr int VEC = 16 / sizeof(T);
     constexpr int R = KS / 2;
     constexpr int RA = round_up_c(R, VEC);
-    constexpr int SW = TW + 2 * RA;
+    constexpr int SW0 = TW + 2 * RA;
+    // u16: pitches padded so that a quarter-warp of 4 column groups x 2 rows is bank-conflict free
+    // (input pitch 96 px = 12 x 16 B == 4 mod 8, intermediate pitch 68 words == 1 mod 8 groups)
+    constexpr bool PAIR = (sizeof(T) == 2) && (SW0 == 80);
+    constexpr int SW = PAIR ? 96 : SW0;
+    constexpr int TWP = PAIR ? TW + 4 : TW;
     constexpr int ROWS = TH + 2 * R;
     constexpr int NV = 1 + 2 * RA / VEC;  // aligned vectors covering VEC outputs + halo
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -102,13 +109,23 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
     dst += frame * (int64_t)h * w;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
 
-    load_tile<T, T>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, border);
+    load_tile<T, T>(src, s_in, h, w, x0, y0, R, RA, SW0, ROWS, border, SW);
     __syncthreads();
 
     // horizontal pass: VEC outputs per item, exact integer, symmetric pairs share one multiply
     constexpr int GROUPS = TW / VEC;
-    for (int item = threadIdx.x; item < ROWS * GROUPS; item += kThreads) {
-        const int ry = item / GROUPS, cg = item - ry * GROUPS;
+    constexpr int ITEMS = PAIR ? ((ROWS + 1) / 2) * 16 : ROWS * GROUPS;
+    for (int item = threadIdx.x; item < ITEMS; item += kThreads) {
+        int ry, cg;
+        if (PAIR) {
+            const int l = item & 7, q = item >> 3;
+            cg = (q & 1) * 4 + (l & 3);
+            ry = 2 * (q >> 1) + (l >> 2);
+            if (ry >= ROWS) continue;
+        } else {
+            ry = item / GROUPS;
+            cg = item - ry * GROUPS;
+        }
         const T* p = s_in + ry * SW + cg * VEC;
         uint32_t e[NV * VEC];
 #pragma unroll
@@ -127,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
             for (int i = 1; i <= R; i++) acc += taps.v[R + i] * (e[c - i] + e[c + i]);
             out[j] = acc;
         }
-        uint32_t* t = s_t + ry * TW + cg * VEC;
+        uint32_t* t = s_t + ry * TWP + cg * VEC;
 #pragma unroll
         for (int j = 0; j < VEC; j += 4)
             *reinterpret_cast<uint4*>(t + j) = make_uint4(out[j], out[j + 1], out[j + 2], out[j + 3]);
@@ -143,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
     for (int j = 0; j < RB; j++) acc0[j] = acc1[j] = 0;
 #pragma unroll
     for (int i = 0; i < RB + 2 * R; i++) {
-        const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TW + cx);
+        const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TWP + cx);
 #pragma unroll
         for (int j = 0; j < RB; j++) {
             const int k = i - j;  // tap index for output row j
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
             }
         }
     }
-    T* s_out = reinterpret_cast<T*>(s_t + ROWS * TW);
+    T* s_out = reinterpret_cast<T*>(s_t + ROWS * TWP);
 #pragma unroll
     for (int j = 0; j < RB; j++) {
         uint32_t o0, o1;
@@ -425,12 +442,18 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
     constexpr int RA = round_up_c(R, VEC > 4 ? VEC : 4);
     constexpr int SW = TW + 2 * RA;
     constexpr int ROWS = TH + 2 * R;
+    // Row pitches are padded so that a quarter-warp made of 4 column groups x 2 consecutive rows hits
+    // 8 distinct 16-byte bank groups: input pitch == 4 (mod 8) float4-groups... i.e. SWP/4 odd,
+    // intermediate pitch TWP/4 odd.  ncu (profiles/r01_ncu_c2_v1.txt): 45 % of the shared wavefronts
+    // of the unpadded layout were bank conflicts and the LSU data pipe was the limiter (78 %).
+    constexpr int SWP = ((SW / 4) % 2 == 0) ? SW + 4 : SW;
+    constexpr int TWP = TW + 4;
     constexpr int OFF = (RA - R) & 3;                 // misalignment of the first tap inside a float4
     constexpr int NV = (OFF + 8 + 2 * R + 3) / 4;     // float4 loads per 8 outputs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_in = reinterpret_cast<float*>(smem_raw);
-    float* s_t = s_in + ROWS * SW + 8;                // +8 floats slack: the last item may read past its row
-    Tout* s_out = reinterpret_cast<Tout*>(s_t + ROWS * TW);
+    float* s_t = s_in + ROWS * SWP + 8;               // +8 floats slack: the last item may read past its row
+    Tout* s_out = reinterpret_cast<Tout*>(s_t + ROWS * TWP);
     src += (int64_t)blockIdx.z * h * w;
     dst += (int64_t)blockIdx.z * h * w;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -452,7 +475,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
 #pragma unroll 4
                 for (int i = 0; i < VEC; i++) f[i] = (float)row[yam_border(gx + i, w, border)];
             }
-            float* d = s_in + ry * SW + vx * VEC;
+            float* d = s_in + ry * SWP + vx * VEC;
 #pragma unroll
             for (int i = 0; i < VEC; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
         }
@@ -461,10 +484,15 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
 
     // ---- horizontal pass: 8 outputs per item
     {
-        constexpr int GROUPS = TW / 8;
-        for (int item = threadIdx.x; item < ROWS * GROUPS; item += kThreads) {
-            const int ry = item / GROUPS, cg = item - ry * GROUPS;
-            const float* p = s_in + ry * SW + cg * 8 + (RA - R) - OFF;
+        static_assert(TW / 8 == 8, "quarter-warp mapping below assumes 8 column groups per row");
+        constexpr int ROW_PAIRS = (ROWS + 1) / 2;
+        for (int item = threadIdx.x; item < ROW_PAIRS * 16; item += kThreads) {
+            // 8 consecutive items = 4 column groups x 2 rows (conflict-free 128-bit accesses)
+            const int l = item & 7, q = item >> 3;
+            const int cg = (q & 1) * 4 + (l & 3);
+            const int ry = 2 * (q >> 1) + (l >> 2);
+            if (ry >= ROWS) continue;
+            const float* p = s_in + ry * SWP + cg * 8 + (RA - R) - OFF;
             float e[NV * 4];
 #pragma unroll
             for (int v = 0; v < NV; v++) {
@@ -474,7 +502,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) o[j] = row_dot<KS>(e + OFF + j, taps, KS);
-            float* t = s_t + ry * TW + cg * 8;
+            float* t = s_t + ry * TWP + cg * 8;
             *reinterpret_cast<float4*>(t) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(t + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
@@ -489,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
         float c0[RB + KS - 1], c1[RB + KS - 1];
 #pragma unroll
         for (int i = 0; i < RB + KS - 1; i++) {
-            const float2 v = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TW + cx);
+            const float2 v = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TWP + cx);
             c0[i] = v.x;
             c1[i] = v.y;
         }
@@ -506,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
                 // mean = rint(blur) (round-half-even via the 1.5*2^23 add; blur is a convex
                 // combination of pixel values so saturation can never trigger);
                 // dst = (src - mean > -idelta) ? 255 : 0, all values exact integers in float
-                const float2 sp = *reinterpret_cast<const float2*>(s_in + (r0 + j + R) * SW + RA + cx);
+                const float2 sp = *reinterpret_cast<const float2*>(s_in + (r0 + j + R) * SWP + RA + cx);
                 const float m0 = __fadd_rn(__fadd_rn(a, 12582912.0f), -12582912.0f);
                 const float m1 = __fadd_rn(__fadd_rn(b, 12582912.0f), -12582912.0f);
                 const float nd = -(float)idelta;
@@ -563,7 +591,9 @@ template <typename T>
 size_t fixed_smem(int ks) {
     const int VEC = 16 / sizeof(T);
     const int R = ks / 2, RA = round_up_c(R, VEC), SW = TW + 2 * RA, ROWS = TH + 2 * R;
-    return (size_t)round_up_c(ROWS * SW * (int)sizeof(T), 16) + (size_t)ROWS * TW * 4 + (size_t)TH * TW * sizeof(T);
+    // upper bound covering the padded pitches of the tiled u16 kernel (96 px, 68 words)
+    const int SWP = SW < 96 ? 96 : SW, TWP = TW + 4;
+    return (size_t)round_up_c(ROWS * SWP * (int)sizeof(T), 16) + (size_t)ROWS * TWP * 4 + (size_t)TH * TW * sizeof(T);
 }
 
 template <typename Tin>
@@ -577,7 +607,8 @@ template <typename Tin, typename Tout>
 size_t f32_tiled_smem(int ks) {
     const int VEC = 16 / sizeof(Tin);
     const int R = ks / 2, RA = round_up_c(R, VEC > 4 ? VEC : 4), SW = TW + 2 * RA, ROWS = TH + 2 * R;
-    return ((size_t)ROWS * SW + 8 + (size_t)ROWS * TW) * 4 + (size_t)TH * TW * sizeof(Tout);
+    const int SWP = ((SW / 4) % 2 == 0) ? SW + 4 : SW, TWP = TW + 4;
+    return ((size_t)ROWS * SWP + 8 + (size_t)ROWS * TWP) * 4 + (size_t)TH * TW * sizeof(Tout);
 }
 
 template <typename K>

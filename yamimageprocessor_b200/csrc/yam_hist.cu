@@ -251,6 +251,7 @@ struct ClaheGeom {
     int clip;            // 0 = no clipping
     float lut_scale;     // (histSize-1)/area
     float inv_tw, inv_th;
+    int y_off;           // global row index of local row 0 (row-strip sharding; 0 for whole images)
 };
 
 // u16: one CTA per tile at a time (persistent CTAs loop over the tiles of a frame chunk):
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const T* __restrict__ 
     dst += (int64_t)blockIdx.z * frame_px;
     luts += (int64_t)blockIdx.z * g.tiles_x * g.tiles_y * BINS;
     const int y = blockIdx.x;
-    const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+    const float tyf = __fsub_rn(__fmul_rn((float)(y + g.y_off), g.inv_th), 0.5f);
     int ty1 = (int)floorf(tyf);
     const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
     const int ty2 = min(ty1 + 1, g.tiles_y - 1);
@@ -519,6 +520,37 @@ void otsu_scan_frames_host(const uint64_t* hists, int bins, int64_t n, int32_t* 
     }
     work();
     for (auto& th : pool) th.join();
+}
+
+// cv2 CLAHE geometry: pad right/bottom (REFLECT_101) when either side is not divisible by the grid
+// (both sides get padded then), tile area, clip limit, LUT scale
+int clahe_geometry(int64_t h, int64_t w, int dtype, double clip_limit, int tiles_x, int tiles_y, ClaheGeom* out) {
+    const int bins = dtype == YAM_U8 ? 256 : kBins16;
+    int64_t pw = w, ph = h;
+    if (w % tiles_x || h % tiles_y) {
+        pw = w + (tiles_x - w % tiles_x);
+        ph = h + (tiles_y - h % tiles_y);
+    }
+    ClaheGeom g;
+    g.h = (int)h;
+    g.w = (int)w;
+    g.tiles_x = tiles_x;
+    g.tiles_y = tiles_y;
+    g.tw = (int)(pw / tiles_x);
+    g.th = (int)(ph / tiles_y);
+    const long long area = (long long)g.tw * g.th;
+    YAM_REQUIRE(area < (1ll << 31), "clahe: tile area too large");
+    g.lut_scale = (float)(bins - 1) / (float)area;
+    g.clip = 0;
+    if (clip_limit > 0) {
+        int c = (int)(clip_limit * (double)area / bins);
+        g.clip = c < 1 ? 1 : c;
+    }
+    g.inv_tw = 1.0f / (float)g.tw;
+    g.inv_th = 1.0f / (float)g.th;
+    g.y_off = 0;
+    *out = g;
+    return YAM_OK;
 }
 
 int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
@@ -639,29 +671,8 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
     YAM_REQUIRE(tiles_x >= 1 && tiles_y >= 1 && tiles_x <= 256 && tiles_y <= 256, "clahe: bad tile grid %dx%d", tiles_x, tiles_y);
     YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "clahe: image side too large");
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
-    // cv2: pad right/bottom (REFLECT_101) when either side is not divisible — both sides get padded
-    int64_t pw = w, ph = h;
-    if (w % tiles_x || h % tiles_y) {
-        pw = w + (tiles_x - w % tiles_x);
-        ph = h + (tiles_y - h % tiles_y);
-    }
     ClaheGeom g;
-    g.h = (int)h;
-    g.w = (int)w;
-    g.tiles_x = tiles_x;
-    g.tiles_y = tiles_y;
-    g.tw = (int)(pw / tiles_x);
-    g.th = (int)(ph / tiles_y);
-    const long long area = (long long)g.tw * g.th;
-    YAM_REQUIRE(area < (1ll << 31), "clahe: tile area too large");
-    g.lut_scale = (float)(bins - 1) / (float)area;
-    g.clip = 0;
-    if (clip_limit > 0) {
-        int c = (int)(clip_limit * (double)area / bins);
-        g.clip = c < 1 ? 1 : c;
-    }
-    g.inv_tw = 1.0f / (float)g.tw;
-    g.inv_th = 1.0f / (float)g.th;
+    if (int rc = clahe_geometry(h, w, dtype, clip_limit, tiles_x, tiles_y, &g)) return rc;
     const int64_t tiles = (int64_t)tiles_x * tiles_y;
     const size_t lut_bytes = (size_t)n * tiles * bins * yam_dtype_size(dtype);
     if (dtype == YAM_U16) {
@@ -708,6 +719,60 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
         clahe_apply_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, g, luts);
         YAM_LAUNCHED(ctx);
     }
+    return YAM_OK;
+}
+
+int yam_clahe_luts(yam_ctx* ctx, const void* src, int64_t h, int64_t w, int dtype, double clip_limit, int tiles_x,
+                   int tiles_y, void* luts_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && luts_dev && h > 0 && w > 0, "clahe_luts: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "clahe_luts: unsupported dtype %d", dtype);
+    YAM_REQUIRE(tiles_x >= 1 && tiles_y >= 1 && tiles_x <= 256 && tiles_y <= 256, "clahe_luts: bad tile grid");
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "clahe_luts: image side too large");
+    ClaheGeom g;
+    if (int rc = clahe_geometry(h, w, dtype, clip_limit, tiles_x, tiles_y, &g)) return rc;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y;
+    if (dtype == YAM_U16) {
+        const int slots = ctx->num_sms;
+        const size_t ovf_bytes = (size_t)slots * kBins16 * sizeof(uint32_t);
+        void* scratch = nullptr;
+        if (int rc = yam_scratch(ctx, ovf_bytes, &scratch)) return rc;
+        YAM_CUDA(cudaMemsetAsync(scratch, 0, ovf_bytes, ctx->stream));
+        YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+        const unsigned gridx = (unsigned)(tiles < slots ? tiles : slots);
+        clahe_lut16_kernel<<<gridx, kHistThreads, kSmem16, ctx->stream>>>((const uint16_t*)src, g, 1, (uint32_t*)scratch,
+                                                                        (uint16_t*)luts_dev);
+    } else {
+        clahe_lut8_kernel<<<dim3((unsigned)tiles, 1, 1), 256, 0, ctx->stream>>>((const uint8_t*)src, g, (uint8_t*)luts_dev);
+    }
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+int yam_clahe_apply(yam_ctx* ctx, const void* src, void* dst, int64_t rows, int64_t w, int dtype, const void* luts_dev,
+                    int tiles_x, int tiles_y, int tile_w, int tile_h, int64_t y_offset) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && src != dst && luts_dev && rows > 0 && w > 0, "clahe_apply: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "clahe_apply: unsupported dtype %d", dtype);
+    YAM_REQUIRE(tiles_x >= 1 && tiles_y >= 1 && tile_w >= 1 && tile_h >= 1 && y_offset >= 0, "clahe_apply: bad geometry");
+    ClaheGeom g;
+    g.h = (int)rows;
+    g.w = (int)w;
+    g.tiles_x = tiles_x;
+    g.tiles_y = tiles_y;
+    g.tw = tile_w;
+    g.th = tile_h;
+    g.clip = 0;
+    g.lut_scale = 0.f;
+    g.inv_tw = 1.0f / (float)tile_w;
+    g.inv_th = 1.0f / (float)tile_h;
+    g.y_off = (int)y_offset;
+    dim3 grid((unsigned)rows, 1, 1);
+    if (dtype == YAM_U16)
+        clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, g, (const uint16_t*)luts_dev);
+    else
+        clahe_apply_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, g, (const uint8_t*)luts_dev);
+    YAM_LAUNCHED(ctx);
     return YAM_OK;
 }
 

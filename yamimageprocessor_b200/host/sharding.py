@@ -102,4 +102,60 @@ def merge_label_strips(strips: Sequence[np.ndarray], counts: Sequence[int]) -> T
     return remap[rooted].astype(np.int32), int(len(uniq))
 
 
-__all__ = ["allreduce_histogram", "frame_block", "gather_tables", "merge_label_strips", "row_strip"]
+
+
+def boundary_remaps(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], counts: Sequence[int]):
+    """Cross-strip label merge from boundary rows only (what the ranks exchange).
+
+    ``tops[r]`` / ``bottoms[r]`` are the first / last label row of strip ``r`` (per-strip canonical
+    labels 1..counts[r]).  Components touching across a strip boundary (8-connectivity) are united;
+    global labels are assigned in raster-first order: a merged component keeps the position of its
+    part in the earliest strip, whose per-strip label order already is raster order.
+    Returns ``(remaps, total)`` with ``remaps[r]`` an int32 table of size counts[r]+1 mapping local
+    to global labels (entry 0 stays 0).
+    """
+    world = len(counts)
+    offs = np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64))])
+    total_local = int(offs[-1])
+    parent = np.arange(total_local + 1, dtype=np.int64)
+
+    def find(x: int) -> int:
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for r in range(world - 1):
+        up = bottoms[r].astype(np.int64)
+        down = tops[r + 1].astype(np.int64)
+        w = up.shape[0]
+        pairs = []
+        for dx in (-1, 0, 1):
+            a = up[max(0, -dx): w - max(0, dx)]
+            b = down[max(0, dx): w - max(0, -dx)]
+            both = (a > 0) & (b > 0)
+            if both.any():
+                pairs.append(np.stack([a[both] + offs[r], b[both] + offs[r + 1]], axis=1))
+        if not pairs:
+            continue
+        for la, lb in np.unique(np.concatenate(pairs, axis=0), axis=0).tolist():
+            ra, rb = find(la), find(lb)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+    # full compression (vectorised pointer jumping)
+    root = parent.copy()
+    while True:
+        nxt = root[root]
+        if np.array_equal(nxt, root):
+            break
+        root = nxt
+    is_root = root == np.arange(total_local + 1)
+    is_root[0] = False
+    rank = np.cumsum(is_root)  # global label of a root = number of roots up to and including it
+    glob = rank[root].astype(np.int32)
+    glob[0] = 0
+    remaps = [np.concatenate([[0], glob[offs[r] + 1: offs[r + 1] + 1]]).astype(np.int32) for r in range(world)]
+    return remaps, int(is_root.sum())
+
+
+__all__ = ["allreduce_histogram", "boundary_remaps", "frame_block", "gather_tables", "merge_label_strips", "row_strip"]
