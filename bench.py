@@ -39,6 +39,10 @@ WORKLOADS = {
                name="segmentation: adaptive threshold(11,2) -> open 5x5 -> close 5x5 -> connected components, 8192x8192 uint16"),
     "c3": dict(h=8192, w=8192, frames=1, bpp=6.0,
                name="extraction: per-region area/centroid/bbox/mean-intensity on the labelled 8192x8192 frame (~99k nuclei)"),
+    "c4": dict(h=65536, w=65536, frames=1, bpp=28.0,
+               name="mosaic: 65536x65536 uint16, preprocess (Gaussian k=11 -> CLAHE 8x8 -> Otsu) + segment (adaptive -> "
+                    "open/close 5x5 -> connected components) in 8 row strips of whole CLAHE tile rows, halo over-fetch, "
+                    "LUT all-gather, histogram all-reduce, cross-strip label merge"),
     "c5": dict(h=2048, w=2048, frames=32, bpp=34.0,
                name="time-lapse: preprocess+segment+extract on a batch of 2048x2048 uint16 frames, frame-sharded"),
 }
@@ -66,7 +70,7 @@ def _cpu_pipeline(workload: str):
         return lambda fr, aux: [P.segment(f) for f in fr], P
     if workload == "c3":
         return lambda fr, aux: [P.extract(l, f) for f, l in zip(fr, aux)], P
-    return lambda fr, aux: [P.full_chain(f) for f in fr], P
+    return lambda fr, aux: [P.full_chain(f) for f in fr], P  # c4 / c5
 
 
 def _cpu_inputs(workload: str, cfg, sample_frames: int, sample_hw):
@@ -315,9 +319,144 @@ def e2e_callable(workload: str, be, frames_np):
     return call, host_in.nbytes, pm
 
 
+class _Shape:
+    def __init__(self, h, w):
+        self.shape = (h, w)
+
+
+def mosaic_rows(size: int, r0: int, r1: int, tile: int, tiles: list) -> np.ndarray:
+    """Rows [r0, r1) of the synthetic mosaic: a size x size grid of `tile`-sized frames drawn from a
+    small set of distinct seeded frames (pattern (7*ty + 3*tx) % len(tiles))."""
+    out = np.empty((r1 - r0, size), np.uint16)
+    y = r0
+    while y < r1:
+        ty = y // tile
+        y_end = min(r1, (ty + 1) * tile)
+        for tx in range(size // tile):
+            t = tiles[(7 * ty + 3 * tx) % len(tiles)]
+            out[y - r0: y_end - r0, tx * tile: (tx + 1) * tile] = t[y - ty * tile: y_end - ty * tile]
+        y = y_end
+    return out
+
+
+def run_gpu_mosaic(args):
+    import torch
+    import torch.distributed as dist
+
+    from yamimageprocessor_b200.backend import get_backend
+    from yamimageprocessor_b200.host import mosaic
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = get_backend(local_rank)
+    cfg = WORKLOADS["c4"]
+    size = int(args.mosaic_size)
+    strips_total = 8
+    if strips_total % world:
+        raise SystemExit("c4 needs 1, 2, 4 or 8 ranks")
+    local = strips_total // world
+    tile = min(4096, size // 8)
+    tiles = [synth.nuclei(tile, tile, seed=100 + i) for i in range(4)]
+    shape = _Shape(size, size)
+    p = mosaic.MosaicParams()
+    host_strips, dev_strips = [], []
+    for li in range(local):
+        s = rank * local + li
+        r0, r1 = mosaic.input_rows(size, s, strips_total, p)
+        hs = mosaic_rows(size, r0, r1, tile, tiles)
+        host_strips.append(hs)
+        dev_strips.append(be.to_device(hs))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(device_sources):
+        return mosaic.run_local_strips(be, shape, local, world > 1, p, with_props=False, device_sources=device_sources)
+
+    for _ in range(max(3, args.warmup)):
+        res = step(dev_strips)
+    n_components = res[0].n_components
+    del res
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    be.launch_count(reset=True)
+    times = []
+    for _ in range(args.steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = step(dev_strips)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+        del res
+    barrier()
+    launches = be.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(times))
+    # end to end: host strips in, labels + Otsu mask out (pageable host memory of this size is not pinned)
+    barrier()
+    t0 = time.perf_counter()
+    res = mosaic.run_local_strips(be, shape, local, world > 1, p, with_props=False,
+                                  device_sources=[be.to_device(h) for h in host_strips])
+    outs = [(be.to_host(r.labels), be.to_host(r.otsu_mask)) for r in res]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(h.nbytes for h in host_strips)
+    d2h = sum(a_.nbytes + b_.nbytes for a_, b_ in outs)
+    del outs, res
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=be.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        v = torch.tensor([h2d, d2h], dtype=torch.int64, device=be.device)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(v[0]), int(v[1])
+    if rank == 0:
+        peak, peak_src = _peaks()
+        px = size * size
+        ms_per_step = total_ms / args.steps
+        value = px / MP / (ms_per_step / 1e3)
+        achieved = px * cfg["bpp"] / (ms_per_step / 1e3) / 1e9
+        cpu, _ = cpu_measure("c5", cfg, 2, 1, (4096, 4096), 1)
+        line = {
+            "metric": "megapixels/s per pipeline", "value": value, "unit": "megapixels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": cfg["name"] if size == 65536 else cfg["name"].replace("65536x65536", f"{size}x{size}"),
+                       "mosaic": [size, size], "strips": strips_total, "strips_per_gpu": local,
+                       "components": int(n_components), "algorithmic_bytes_per_px": cfg["bpp"],
+                       "l2": "every strip (>= 1 GiB at 65536^2) exceeds the 126 MB L2", "seed": "tiles 100..103"},
+            "roofline": {"bound": "hbm", "kernel": "whole mosaic pipeline (all kernels of all strips of the slowest rank)",
+                         "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
+                         "traffic": None, "peak_source": peak_src, "per_gpu": True},
+            "cpu_baseline": cpu,
+            "e2e": {"value": px / MP / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "api": "host.mosaic.run_local_strips(host strips) -> labels + Otsu mask"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+
+    if args.workload == "c4":
+        return run_gpu_mosaic(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -470,6 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--mosaic-size", type=int, default=65536, help="side of the c4 mosaic (multiple of 64)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -479,7 +619,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
                str(Path(__file__).resolve()), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--workload", args.workload]
+               "--warmup", str(args.warmup), "--workload", args.workload, "--mosaic-size", str(args.mosaic_size)]
         return subprocess.call(cmd)
     return run_gpu(args)
 

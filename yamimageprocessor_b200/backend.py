@@ -173,10 +173,11 @@ class Backend:
             out._yam_host_ref = a  # type: ignore[attr-defined]
             return out
         nbytes = a.nbytes
-        stage = self._staging("h2d", nbytes)
-        torch.cuda.current_stream(self.device).synchronize()  # previous user of the staging buffer
-        stage.numpy()[:nbytes] = a.reshape(-1).view(np.uint8)
-        out.view(torch.uint8).reshape(-1).copy_(stage[:nbytes], non_blocking=True)
+        with self._lock:  # fill + enqueue must be atomic with respect to other host threads
+            stage = self._staging("h2d", nbytes)
+            torch.cuda.current_stream(self.device).synchronize()  # previous user of the staging buffer
+            stage.numpy()[:nbytes] = a.reshape(-1).view(np.uint8)
+            out.view(torch.uint8).reshape(-1).copy_(stage[:nbytes], non_blocking=True)
         return out
 
     def to_host(self, t) -> np.ndarray:

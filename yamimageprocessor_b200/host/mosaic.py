@@ -1,0 +1,342 @@
+"""Row-strip sharded mosaic pipeline (BASELINE config 4: preprocess + segment a huge uint16 mosaic).
+
+One process per GPU (``torch.distributed``).  Rank ``r`` owns a contiguous strip of whole CLAHE
+tile rows and produces, for its rows, exactly the pixels the dense single-GPU run produces
+(the reference's dense path, ``PipelineManager.apply(ndarray)``, is the parity target — its tiled
+path has no halo, ``SURVEY.md`` §0 fact 5):
+
+  source rows (+ halo)  --Gaussian k-->  g
+  g core rows           --tile histograms -> LUTs-->   all-gather LUTs (tiles x 128 KiB)
+  g (+ halo)            --CLAHE apply with GLOBAL geometry-->  c
+  c core rows           --histogram--> all-reduce (65536 x int64)  --Otsu scan-->  t, Otsu mask
+  c (+ halo)            --adaptive threshold -> open -> close-->  mask (cropped to the core)
+  mask core             --CCL-->  per-strip labels; boundary rows all-gathered, equivalences
+                          united, labels renumbered in global raster-first order (relabel kernel)
+  labels, c             --region props--> partial tables, all-reduced (sum / min / max)
+
+Halo rows are over-fetched from the shared source once (Gaussian r + adaptive r + 4 morphology r
+rows) and recomputed locally, so no mid-pipeline halo exchange is needed; the only collectives are
+the LUT all-gather, the histogram all-reduce, the boundary-row all-gather and the table all-reduce
+(all tiny: latency-, not bandwidth-bound).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..backend import Backend
+from . import sharding
+
+
+@dataclass
+class MosaicParams:
+    gauss_ksize: int = 11
+    clip_limit: float = 2.0
+    tile_grid: Tuple[int, int] = (8, 8)
+    block_size: int = 11
+    C: float = 2.0
+    morph_ksize: int = 5
+
+
+@dataclass
+class StripResult:
+    rows: Tuple[int, int]          # [start, stop) rows of the mosaic owned by this rank
+    clahe: Any                     # device tensors for the core rows
+    otsu_mask: Any
+    labels: Any
+    otsu_threshold: int
+    n_components: int              # global count
+    props: Optional[Any] = None    # int64 [n_components, 8] (global, reduced) when requested
+
+
+class TorchComm:
+    """Collectives over torch.distributed (NCCL on the GPU box)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_gather(self, tensor):
+        import torch
+
+        # integer payloads travel as bytes: NCCL does not take every unsigned dtype
+        raw = tensor.contiguous().view(torch.uint8)
+        parts = [torch.empty_like(raw) for _ in range(self.world)]
+        self.dist.all_gather(parts, raw, group=self.group)
+        return [p.view(tensor.dtype).reshape(tensor.shape) for p in parts]
+
+    def all_reduce(self, tensor, op: str = "sum"):
+        ops = {"sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX}
+        self.dist.all_reduce(tensor, op=ops[op], group=self.group)
+        return tensor
+
+
+class LocalComm:
+    """In-process stand-in: `world` threads, one per emulated rank, meet at a barrier.
+
+    Lets the whole sharded pipeline (halo over-fetch, LUT gather, histogram reduce, label merge)
+    run against the dense result on a single GPU; the collectives are plain tensor ops."""
+
+    def __init__(self, world: int):
+        import threading
+
+        self.world = world
+        self._slots = [None] * world
+        self._barrier = threading.Barrier(world)
+
+    def bind(self, rank: int) -> "_BoundLocalComm":
+        return _BoundLocalComm(self, rank)
+
+
+class _BoundLocalComm:
+    def __init__(self, parent: LocalComm, rank: int):
+        self.parent, self.rank, self.world = parent, rank, parent.world
+
+    def all_gather(self, tensor):
+        p = self.parent
+        p._slots[self.rank] = tensor
+        p._barrier.wait()
+        out = [t.clone() for t in p._slots]
+        p._barrier.wait()
+        return out
+
+    def all_reduce(self, tensor, op: str = "sum"):
+        import torch
+
+        parts = self.all_gather(tensor)
+        stacked = torch.stack(parts)
+        red = stacked.sum(0) if op == "sum" else (stacked.min(0).values if op == "min" else stacked.max(0).values)
+        tensor.copy_(red)
+        return tensor
+
+
+class HybridComm:
+    """`local` strip-threads in this process x `nproc` processes (torch.distributed): lets one GPU
+    own several strips (a 65536^2 mosaic on 1, 2, 4 or 8 GPUs always runs as 8 strips of whole CLAHE
+    tile rows; with fewer GPUs each GPU works through several strips, in lock-step threads).
+    Global strip index = process_rank * local + local_index."""
+
+    def __init__(self, local: int, use_dist: bool):
+        import threading
+
+        self.local = local
+        self.dist = None
+        self.nproc = 1
+        self.prank = 0
+        if use_dist:
+            import torch.distributed as dist
+
+            self.dist = dist
+            self.nproc = dist.get_world_size()
+            self.prank = dist.get_rank()
+        self.world = self.local * self.nproc
+        self._slots = [None] * local
+        self._result = None
+        self._barrier = threading.Barrier(local)
+
+    def bind(self, local_index: int) -> "_BoundHybridComm":
+        return _BoundHybridComm(self, local_index)
+
+
+class _BoundHybridComm:
+    def __init__(self, parent: HybridComm, li: int):
+        self.parent, self.li = parent, li
+        self.world = parent.world
+        self.rank = parent.prank * parent.local + li
+
+    def all_gather(self, tensor):
+        import torch
+
+        p = self.parent
+        p._slots[self.li] = tensor.contiguous()
+        p._barrier.wait()
+        if self.li == 0:
+            local = torch.stack(p._slots)  # (local, ...)
+            if p.dist is not None:
+                raw = local.view(torch.uint8)
+                parts = [torch.empty_like(raw) for _ in range(p.nproc)]
+                p.dist.all_gather(parts, raw)
+                everything = torch.cat([q.view(local.dtype).reshape(local.shape) for q in parts], dim=0)
+            else:
+                everything = local
+            p._result = everything
+        p._barrier.wait()
+        out = [p._result[i] for i in range(self.world)]
+        p._barrier.wait()
+        return out
+
+    def all_reduce(self, tensor, op: str = "sum"):
+        import torch
+
+        stacked = torch.stack(self.all_gather(tensor))
+        red = stacked.sum(0) if op == "sum" else (stacked.min(0).values if op == "min" else stacked.max(0).values)
+        tensor.copy_(red)
+        return tensor
+
+
+def strip_rows(height: int, tiles_y: int, rank: int, world: int) -> Tuple[int, int]:
+    if height % tiles_y:
+        raise ValueError("mosaic height must be divisible by the CLAHE grid for strip sharding")
+    if tiles_y % world:
+        raise ValueError(f"CLAHE tile rows ({tiles_y}) must be divisible by the number of ranks ({world})")
+    th = height // tiles_y
+    per = tiles_y // world
+    return rank * per * th, (rank + 1) * per * th
+
+
+def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Optional[MosaicParams] = None,
+              with_props: bool = False, device_source=None, comm=None) -> StripResult:
+    """Process this rank's strip of ``source`` (an (H, W) uint16 array / memmap).
+
+    ``device_source`` may pass the already-uploaded rows [r0, r1) (benchmarks keep the input
+    resident); otherwise the rows are read from ``source`` and uploaded.
+    """
+    import torch
+
+    p = params or MosaicParams()
+    if world > 1 and comm is None:
+        comm = TorchComm()
+    if world == 1:
+        comm = None
+    H, W = int(source.shape[0]), int(source.shape[1])
+    tiles_x, tiles_y = p.tile_grid
+    if W % tiles_x:
+        raise ValueError("mosaic width must be divisible by the CLAHE grid for strip sharding")
+    c0, c1 = strip_rows(H, tiles_y, rank, world)
+    th, tw = H // tiles_y, W // tiles_x
+    hg = p.gauss_ksize // 2
+    halo_seg = p.block_size // 2 + 4 * (p.morph_ksize // 2)   # adaptive + erode,dilate,dilate,erode
+    a0, a1 = max(0, c0 - halo_seg), min(H, c1 + halo_seg)      # rows of CLAHE output needed
+    r0, r1 = max(0, a0 - hg), min(H, a1 + hg)                  # rows of input needed
+
+    x = device_source if device_source is not None else be.to_device(np.ascontiguousarray(source[r0:r1]))
+    g = be.gaussian(x, p.gauss_ksize, 0.0)                     # exact on [a0, a1): artificial edges are hg rows away
+
+    # CLAHE: LUTs of the tile rows this rank owns, gathered from every rank
+    luts_local = be.clahe_luts(g[c0 - r0: c1 - r0], p.clip_limit, (tiles_x, tiles_y // world))
+    luts = torch.cat(comm.all_gather(luts_local), dim=0) if comm is not None else luts_local
+    c = be.clahe_apply(g[a0 - r0: a1 - r0], luts, (tw, th), y_offset=a0)
+    c_core = c[c0 - a0: c1 - a0]
+
+    # Otsu on the global histogram
+    hist = be.histogram(c_core)[0]
+    if comm is not None:
+        comm.all_reduce(hist, "sum")
+    t = be.otsu_from_histogram(be.to_host(hist))
+    otsu_mask = be.threshold(c_core, float(t), 255)
+
+    # segmentation on the extended rows, cropped to the core
+    m = be.morph_open_close(be.adaptive_threshold(c, p.block_size, p.C), p.morph_ksize, 1)
+    mask_core = m[c0 - a0: c1 - a0].contiguous()
+    labels, counts = be.ccl_label(mask_core)
+    n_local = int(be.to_host(counts)[0])
+
+    # cross-strip merge from boundary rows
+    if comm is not None:
+        edge = torch.stack([labels[0], labels[-1]]).contiguous()
+        edges = comm.all_gather(edge)
+        cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
+        tops = [be.to_host(e[0]) for e in edges]
+        bottoms = [be.to_host(e[1]) for e in edges]
+        counts_all = [int(v.item()) for v in cnts]
+        remaps, total = sharding.boundary_remaps(tops, bottoms, counts_all)
+        be.relabel(labels, be.to_device(remaps[rank]))
+    else:
+        total = n_local
+
+    props = None
+    if with_props:
+        props = be.region_props(labels, c_core, total)
+        if total:
+            # strip-local row coordinates -> mosaic coordinates, then reduce across ranks
+            area = props[:, 0]
+            seen = area > 0
+            props[:, 1] += area * c0
+            props[:, 4] = torch.where(seen, props[:, 4] + c0, props[:, 4])
+            props[:, 6] = torch.where(seen, props[:, 6] + c0, props[:, 6])
+            if comm is not None:
+                sums = comm.all_reduce(props[:, 0:4].contiguous(), "sum")
+                mins = comm.all_reduce(props[:, 4:6].contiguous(), "min")
+                maxs = comm.all_reduce(props[:, 6:8].contiguous(), "max")
+                props = torch.cat([sums, mins, maxs], dim=1)
+    return StripResult((c0, c1), c_core, otsu_mask, labels, t, total, props)
+
+
+def input_rows(height: int, rank: int, world: int, params: Optional[MosaicParams] = None) -> Tuple[int, int]:
+    """Rows [r0, r1) of the source this rank reads (core + over-fetched halo)."""
+    p = params or MosaicParams()
+    c0, c1 = strip_rows(height, p.tile_grid[1], rank, world)
+    halo = p.block_size // 2 + 4 * (p.morph_ksize // 2) + p.gauss_ksize // 2
+    return max(0, c0 - halo), min(height, c1 + halo)
+
+
+def run_emulated(be: Backend, source, world: int, params: Optional[MosaicParams] = None, with_props: bool = False):
+    """Run all `world` strips on ONE GPU with in-process collectives (threads); returns the list of
+    StripResult in rank order.  Used by the single-GPU parity tests of the sharded path."""
+    import threading
+
+    import torch
+
+    comm = LocalComm(world)
+    results = [None] * world
+    errors = []
+
+    def work(r: int):
+        try:
+            torch.cuda.set_device(be.device)
+            results[r] = run_strip(be, source, r, world, params, with_props, comm=comm.bind(r))
+        except BaseException as exc:  # pragma: no cover - surfaced below
+            errors.append(exc)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def run_local_strips(be: Backend, source, local: int, use_dist: bool, params: Optional[MosaicParams] = None,
+                     with_props: bool = False, device_sources: Optional[Sequence[Any]] = None):
+    """Run this process's `local` strips (lock-step threads) of a mosaic split into
+    local x world_size strips; returns their StripResults in strip order."""
+    import threading
+
+    import torch
+
+    comm = HybridComm(local, use_dist)
+    results = [None] * local
+    errors = []
+
+    def work(li: int):
+        try:
+            torch.cuda.set_device(be.device)
+            bound = comm.bind(li)
+            dev = device_sources[li] if device_sources is not None else None
+            results[li] = run_strip(be, source, bound.rank, comm.world, params, with_props, device_source=dev,
+                                    comm=bound if comm.world > 1 else None)
+        except BaseException as exc:  # pragma: no cover
+            errors.append(exc)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(li,)) for li in range(local)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+__all__ = ["HybridComm", "LocalComm", "MosaicParams", "run_local_strips", "StripResult", "TorchComm", "input_rows", "run_emulated", "run_strip",
+           "strip_rows"]
