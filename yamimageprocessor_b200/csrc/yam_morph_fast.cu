@@ -24,20 +24,46 @@ __device__ __forceinline__ uint32_t mm3(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 // ---- horizontal pass: rows [row0, row0+NROWS), word groups [G0, G0+NG) of 4 words ------------------
+// Margin words come from the neighbouring lanes by shuffle (adjacent lanes hold adjacent groups of
+// the same row); only lanes at a row start / warp edge load them.  Scalar margin loads at a 16-byte
+// lane stride were 4-way bank conflicts and dominated the shared-memory wavefronts.
 template <int R, int DIL, int NROWS, int G0, int NG, int STRIDE>
 __device__ __forceinline__ void hpass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int row0) {
-    constexpr int C = (R + 1) / 2;  // margin words on each side
+    constexpr int C = (R + 1) / 2;  // margin words on each side (1 or 2)
+    static_assert(C <= 2, "fast path covers radii up to 4");
     constexpr int NW = 4 + 2 * C;
-    for (int item = threadIdx.x; item < NROWS * NG; item += kThreads) {
-        const int r = item / NG, g = item - r * NG;
+    constexpr int TOTAL = NROWS * NG;
+    const int lane = threadIdx.x & 31;
+    for (int item0 = 0; item0 < TOTAL; item0 += kThreads) {  // warp-uniform trip count (shuffles inside)
+        const int item = item0 + threadIdx.x;
+        const bool valid = item < TOTAL;
+        const int it = valid ? item : TOTAL - 1;
+        const int r = it / NG, g = it - r * NG;
         const int base = (row0 + r) * STRIDE + PADW + 4 * (G0 + g);
         uint32_t w[NW];
         const uint4 mid = *reinterpret_cast<const uint4*>(src + base);
         w[C] = mid.x; w[C + 1] = mid.y; w[C + 2] = mid.z; w[C + 3] = mid.w;
+        // left margin = last C words of the previous group, right margin = first C words of the next
+        uint32_t lft[2], rgt[2];
+        lft[0] = __shfl_up_sync(0xffffffffu, mid.w, 1);
+        rgt[0] = __shfl_down_sync(0xffffffffu, mid.x, 1);
+        if (C == 2) {
+            lft[1] = lft[0];
+            lft[0] = __shfl_up_sync(0xffffffffu, mid.z, 1);
+            rgt[1] = __shfl_down_sync(0xffffffffu, mid.y, 1);
+        }
+        if (lane == 0 || g == 0) {
+#pragma unroll
+            for (int i = 0; i < C; i++) lft[i] = src[base - C + i];
+        }
+        if (lane == 31 || g == NG - 1 || item + 1 >= TOTAL) {
+#pragma unroll
+            for (int i = 0; i < C; i++) rgt[i] = src[base + 4 + i];
+        }
 #pragma unroll
         for (int i = 0; i < C; i++) {
-            w[i] = src[base - C + i];
-            w[C + 4 + i] = src[base + 4 + i];
+            w[i] = lft[i];
+            w[C + 4 + i] = rgt[i];
         }
         uint32_t s[NW - 1];  // s[i] = pixels (hi of w[i], lo of w[i+1]) : shift by one pixel
 #pragma unroll
@@ -49,16 +75,13 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ src, uint32_t
             // operands for pixel offsets -R..R: even offset 2d -> w[c+d]; odd offset 2m+1 -> s[c+m]
             uint32_t ops[2 * R + 1];
 #pragma unroll
-            for (int o = -R; o <= R; o++) {
-                // floor division for negative odd o
-                ops[o + R] = (o & 1) ? s[c + ((o - 1) >> 1)] : w[c + (o >> 1)];
-            }
+            for (int o = -R; o <= R; o++) ops[o + R] = (o & 1) ? s[c + ((o - 1) >> 1)] : w[c + (o >> 1)];
             uint32_t acc = ops[0];
 #pragma unroll
             for (int i = 0; i < R; i++) acc = mm3<DIL>(acc, ops[2 * i + 1], ops[2 * i + 2]);
             out[k] = acc;
         }
-        *reinterpret_cast<uint4*>(dst + base) = make_uint4(out[0], out[1], out[2], out[3]);
+        if (valid) *reinterpret_cast<uint4*>(dst + base) = make_uint4(out[0], out[1], out[2], out[3]);
     }
 }
 
@@ -148,38 +171,38 @@ __global__ void __launch_bounds__(kThreads) morph_fast_kernel(const T* __restric
     const int gx_org = x0 - HA, gy_org = y0 - H;
     const bool border_tile = (gx_org < 0) || (gy_org < 0) || (x0 + TW + HA > w) || (y0 + TH + H > h);
 
-    // ---- load (outside the image = identity of stage 1)
+    // ---- load (outside the image = identity of stage 1); 8 pixels = 4 packed words per thread-item
     {
-        constexpr int VPR = (TW + 2 * HA) / VEC;   // vectors per row
-        constexpr int WPV = VEC / 2;                // words per vector
+        constexpr int UPR = (TW + 2 * HA) / 8;   // 8-pixel units per row
         const uint32_t id1 = D1 ? 0u : 0xffffu;
         const uint32_t idw = id1 | (id1 << 16);
-        const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        for (int v = threadIdx.x; v < BH * VPR; v += kThreads) {
-            const int by = v / VPR, vx = v - by * VPR;
-            const int gy = gy_org + by, gx = gx_org + vx * VEC;
-            uint32_t* d = bufA + by * STRIDE + PADW + vx * WPV;
-            uint32_t wd[WPV];
+        const bool row_aligned = ((w % 8) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        for (int v = threadIdx.x; v < BH * UPR; v += kThreads) {
+            const int by = v / UPR, ux = v - by * UPR;
+            const int gy = gy_org + by, gx = gx_org + ux * 8;
+            uint32_t wd[4];
             if ((unsigned)gy >= (unsigned)h) {
-#pragma unroll
-                for (int i = 0; i < WPV; i++) wd[i] = idw;
-            } else if (row_aligned && gx >= 0 && gx + VEC <= w) {
-                const uint4 q = *reinterpret_cast<const uint4*>(src + (int64_t)gy * w + gx);
-                const T* e = reinterpret_cast<const T*>(&q);
-#pragma unroll
-                for (int i = 0; i < WPV; i++) wd[i] = (uint32_t)e[2 * i] | ((uint32_t)e[2 * i + 1] << 16);
+                wd[0] = wd[1] = wd[2] = wd[3] = idw;
+            } else if (row_aligned && gx >= 0 && gx + 8 <= w) {
+                const T* p = src + (int64_t)gy * w + gx;
+                if (sizeof(T) == 2) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(p);
+                    wd[0] = q.x; wd[1] = q.y; wd[2] = q.z; wd[3] = q.w;
+                } else {
+                    const uint2 q = *reinterpret_cast<const uint2*>(p);
+                    wd[0] = __byte_perm(q.x, 0, 0x4140); wd[1] = __byte_perm(q.x, 0, 0x4342);
+                    wd[2] = __byte_perm(q.y, 0, 0x4140); wd[3] = __byte_perm(q.y, 0, 0x4342);
+                }
             } else {
 #pragma unroll
-                for (int i = 0; i < WPV; i++) {
+                for (int i = 0; i < 4; i++) {
                     const int xa = gx + 2 * i, xb = xa + 1;
                     const uint32_t a = (unsigned)xa < (unsigned)w ? (uint32_t)src[(int64_t)gy * w + xa] : id1;
                     const uint32_t b = (unsigned)xb < (unsigned)w ? (uint32_t)src[(int64_t)gy * w + xb] : id1;
                     wd[i] = a | (b << 16);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < WPV; i += 4)
-                *reinterpret_cast<uint4*>(d + i) = make_uint4(wd[i], wd[i + 1], wd[i + 2], wd[i + 3]);
+            *reinterpret_cast<uint4*>(bufA + by * STRIDE + PADW + ux * 4) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
     }
     __syncthreads();
@@ -191,35 +214,28 @@ __global__ void __launch_bounds__(kThreads) morph_fast_kernel(const T* __restric
     if (R3 > 0)
         stage<(R3 > 0 ? R3 : 1), D3, 0, H, HA, STRIDE, 1>(bufA, bufB, gy_org, gx_org, h, w, border_tile, 0u);
 
-    // ---- store the core
+    // ---- store the core, 8 pixels per thread-item
     {
-        constexpr int VPR = TW / VEC;
-        constexpr int WPV = VEC / 2;
-        const bool row_aligned = ((w % VEC) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        for (int v = threadIdx.x; v < TH * VPR; v += kThreads) {
-            const int ty = v / VPR, vx = v - ty * VPR;
-            const int gy = y0 + ty, gx = x0 + vx * VEC;
+        constexpr int UPR = TW / 8;
+        const bool row_aligned = ((w % 8) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        for (int v = threadIdx.x; v < TH * UPR; v += kThreads) {
+            const int ty = v / UPR, ux = v - ty * UPR;
+            const int gy = y0 + ty, gx = x0 + ux * 8;
             if (gy >= h || gx >= w) continue;
-            const uint32_t* s = bufA + (H + ty) * STRIDE + PADW + HA / 2 + vx * WPV;
-            uint32_t wd[WPV];
-#pragma unroll
-            for (int i = 0; i < WPV; i += 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(s + i);
-                wd[i] = q.x; wd[i + 1] = q.y; wd[i + 2] = q.z; wd[i + 3] = q.w;
-            }
+            const uint4 q = *reinterpret_cast<const uint4*>(bufA + (H + ty) * STRIDE + PADW + HA / 2 + ux * 4);
             T* d = dst + (int64_t)gy * w + gx;
-            if (row_aligned && gx + VEC <= w) {
-                uint4 q;
-                T* e = reinterpret_cast<T*>(&q);
-#pragma unroll
-                for (int i = 0; i < WPV; i++) {
-                    e[2 * i] = (T)(wd[i] & 0xffffu);
-                    e[2 * i + 1] = (T)(wd[i] >> 16);
+            if (row_aligned && gx + 8 <= w) {
+                if (sizeof(T) == 2) {
+                    *reinterpret_cast<uint4*>(d) = q;
+                } else {
+                    // low bytes of the four packed pixels pairs -> 8 bytes
+                    const uint32_t lo = __byte_perm(q.x, q.y, 0x6420), hi = __byte_perm(q.z, q.w, 0x6420);
+                    *reinterpret_cast<uint2*>(d) = make_uint2(lo, hi);
                 }
-                *reinterpret_cast<uint4*>(d) = q;
             } else {
+                const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int i = 0; i < WPV; i++) {
+                for (int i = 0; i < 4; i++) {
                     if (gx + 2 * i < w) d[2 * i] = (T)(wd[i] & 0xffffu);
                     if (gx + 2 * i + 1 < w) d[2 * i + 1] = (T)(wd[i] >> 16);
                 }

@@ -76,6 +76,10 @@ class TorchComm:
         self.dist.all_reduce(tensor, op=ops[op], group=self.group)
         return tensor
 
+    def once(self, fn):
+        """Host work whose inputs are identical on every strip of this process: run it once."""
+        return fn()
+
 
 class LocalComm:
     """In-process stand-in: `world` threads, one per emulated rank, meet at a barrier.
@@ -114,6 +118,15 @@ class _BoundLocalComm:
         red = stacked.sum(0) if op == "sum" else (stacked.min(0).values if op == "min" else stacked.max(0).values)
         tensor.copy_(red)
         return tensor
+
+    def once(self, fn):
+        p = self.parent
+        if self.rank == 0:
+            p._shared = fn()
+        p._barrier.wait()
+        out = p._shared
+        p._barrier.wait()
+        return out
 
 
 class HybridComm:
@@ -179,6 +192,15 @@ class _BoundHybridComm:
         tensor.copy_(red)
         return tensor
 
+    def once(self, fn):
+        p = self.parent
+        if self.li == 0:
+            p._shared = fn()
+        p._barrier.wait()
+        out = p._shared
+        p._barrier.wait()
+        return out
+
 
 def strip_rows(height: int, tiles_y: int, rank: int, world: int) -> Tuple[int, int]:
     if height % tiles_y:
@@ -228,7 +250,9 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     hist = be.histogram(c_core)[0]
     if comm is not None:
         comm.all_reduce(hist, "sum")
-    t = be.otsu_from_histogram(be.to_host(hist))
+        t = comm.once(lambda: be.otsu_from_histogram(be.to_host(hist)))
+    else:
+        t = be.otsu_from_histogram(be.to_host(hist))
     otsu_mask = be.threshold(c_core, float(t), 255)
 
     # segmentation on the extended rows, cropped to the core
@@ -242,10 +266,12 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         edge = torch.stack([labels[0], labels[-1]]).contiguous()
         edges = comm.all_gather(edge)
         cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
-        tops = [be.to_host(e[0]) for e in edges]
-        bottoms = [be.to_host(e[1]) for e in edges]
-        counts_all = [int(v.item()) for v in cnts]
-        remaps, total = sharding.boundary_remaps(tops, bottoms, counts_all)
+        def merge():
+            tops = [be.to_host(e[0]) for e in edges]
+            bottoms = [be.to_host(e[1]) for e in edges]
+            return sharding.boundary_remaps(tops, bottoms, [int(v.item()) for v in cnts])
+
+        remaps, total = comm.once(merge)
         be.relabel(labels, be.to_device(remaps[rank]))
     else:
         total = n_local

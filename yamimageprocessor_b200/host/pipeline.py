@@ -312,8 +312,19 @@ class PipelineManager:
     def apply(self, image: PipelineImage) -> PipelineImage:
         if isinstance(image, TiledPipelineImage):
             return self._apply_tiled(image)
-        current: PipelineImage = image.copy() if isinstance(image, np.ndarray) else image
-        return self._run_steps(list(self.iter_enabled_steps()), current)
+        active = list(self.iter_enabled_steps())
+        current: PipelineImage = image
+        # The reference copies the input up front so that in-place CPU steps cannot touch the caller's
+        # array (processing/pipeline_manager.py:400).  A step routed to the GPU executor never mutates
+        # its input and always returns a fresh array, so the (full-frame) copy is skipped when the
+        # first enabled step goes to the executor; every other case keeps the defensive copy.
+        first_on_gpu = bool(active) and active[0].execution.requires_gpu and self._gpu_executor is not None
+        if isinstance(image, np.ndarray) and not first_on_gpu:
+            current = image.copy()
+        out = self._run_steps(active, current)
+        if out is image and isinstance(image, np.ndarray):
+            out = image.copy()  # nothing ran (or the executor returned None): still hand back a copy
+        return out
 
     def _run_steps(self, steps: Sequence[PipelineStep], current: PipelineImage) -> PipelineImage:
         chain = getattr(self._gpu_executor, "execute_chain", None)

@@ -112,43 +112,42 @@ def boundary_remaps(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], c
     global labels are assigned in raster-first order: a merged component keeps the position of its
     part in the earliest strip, whose per-strip label order already is raster order.
     Returns ``(remaps, total)`` with ``remaps[r]`` an int32 table of size counts[r]+1 mapping local
-    to global labels (entry 0 stays 0).
+    to global labels (entry 0 stays 0).  Vectorised: minimum-label propagation over the unique
+    boundary pairs with pointer jumping (iterations ~ number of strips a component crosses).
     """
     world = len(counts)
     offs = np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64))])
     total_local = int(offs[-1])
-    parent = np.arange(total_local + 1, dtype=np.int64)
-
-    def find(x: int) -> int:
-        while parent[x] != x:
-            parent[x] = parent[parent[x]]
-            x = parent[x]
-        return x
-
+    pair_list = []
     for r in range(world - 1):
-        up = bottoms[r].astype(np.int64)
-        down = tops[r + 1].astype(np.int64)
+        up = np.asarray(bottoms[r]).astype(np.int64)
+        down = np.asarray(tops[r + 1]).astype(np.int64)
         w = up.shape[0]
-        pairs = []
         for dx in (-1, 0, 1):
             a = up[max(0, -dx): w - max(0, dx)]
             b = down[max(0, dx): w - max(0, -dx)]
             both = (a > 0) & (b > 0)
             if both.any():
-                pairs.append(np.stack([a[both] + offs[r], b[both] + offs[r + 1]], axis=1))
-        if not pairs:
-            continue
-        for la, lb in np.unique(np.concatenate(pairs, axis=0), axis=0).tolist():
-            ra, rb = find(la), find(lb)
-            if ra != rb:
-                parent[max(ra, rb)] = min(ra, rb)
-    # full compression (vectorised pointer jumping)
-    root = parent.copy()
-    while True:
-        nxt = root[root]
-        if np.array_equal(nxt, root):
-            break
-        root = nxt
+                pair_list.append(np.stack([a[both] + offs[r], b[both] + offs[r + 1]], axis=1))
+    root = np.arange(total_local + 1, dtype=np.int64)
+    if pair_list:
+        pairs = np.unique(np.concatenate(pair_list, axis=0), axis=0)
+        pa, pb = pairs[:, 0], pairs[:, 1]
+        while True:
+            m = np.minimum(root[pa], root[pb])
+            new = root.copy()
+            np.minimum.at(new, pa, m)
+            np.minimum.at(new, pb, m)
+            new = new[new]  # pointer jumping
+            if np.array_equal(new, root):
+                break
+            root = new
+        # make every entry point at its final root
+        while True:
+            nxt = root[root]
+            if np.array_equal(nxt, root):
+                break
+            root = nxt
     is_root = root == np.arange(total_local + 1)
     is_root[0] = False
     rank = np.cumsum(is_root)  # global label of a root = number of roots up to and including it
