@@ -276,6 +276,16 @@ def test_clahe_counter_spill_and_stack(backend, rng):
     assert_same(got, want, "clahe spill")
 
 
+def test_clahe_huge_tiles_multi_cta(backend, rng):
+    """few tiles of >= 4 Mpx take the multi-CTA histogram path (mosaic strips): same LUTs, same output"""
+    from yamimageprocessor_b200 import synth
+
+    a = synth.nuclei(4096, 2048, seed=5)
+    for clip, grid in ((2.0, (1, 2)), (0.0, (2, 1))):
+        got = host(backend, backend.clahe(dev(backend, a), clip, grid))
+        assert_same(got, O.clahe(a, clip, grid), f"clahe huge tiles {clip} {grid}")
+
+
 # --------------------------------------------------------------------------- K10 / K11
 def _ccl_case(rng, shape, dens):
     return ((rng.random(shape) < dens).astype(np.uint8)) * 255

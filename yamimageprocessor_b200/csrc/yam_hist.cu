@@ -254,6 +254,107 @@ struct ClaheGeom {
     int y_off;           // global row index of local row 0 (row-strip sharding; 0 for whole images)
 };
 
+// counts of bin pair `wi` (bins 2*wi, 2*wi+1) from the packed shared histogram (+ spilled part)
+struct SmemCounts {
+    const uint32_t* sh;
+    const uint32_t* ovf;
+    bool use_ovf;
+    __device__ __forceinline__ void get(int wi, unsigned long long& c0, unsigned long long& c1) const {
+        const uint32_t wv = sh[wi];
+        c0 = wv & 0xffffu;
+        c1 = wv >> 16;
+        if (use_ovf) {
+            c0 += __ldcg(&ovf[2 * wi]);
+            c1 += __ldcg(&ovf[2 * wi + 1]);
+        }
+    }
+};
+// counts from a global 32-bit histogram (multi-CTA tiles)
+struct GlobalCounts {
+    const uint32_t* gh;
+    __device__ __forceinline__ void get(int wi, unsigned long long& c0, unsigned long long& c1) const {
+        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(gh) + wi);
+        c0 = v.x;
+        c1 = v.y;
+    }
+};
+
+// clip -> redistribute -> ordered prefix sum -> LUT for one tile; all kHistThreads threads take part.
+template <class Counts>
+__device__ __forceinline__ void clahe_lut_passes(const Counts& cnt, const ClaheGeom& g, uint16_t* __restrict__ lut,
+                                                 unsigned long long* s_red, unsigned long long* s_base) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long area = (long long)g.tw * g.th;
+    const int wbase = warp * 1024;  // each warp owns words [1024*warp, +1024); lane reads base+32*i+lane
+    const unsigned long long clipv = g.clip > 0 ? (unsigned long long)g.clip : ~0ull;
+    // pass 0: sum of clipped counts -> excess
+    unsigned long long part = 0;
+    for (int i = 0; i < 32; i++) {
+        const int wi = wbase + 32 * i + lane;
+        unsigned long long c0, c1;
+        cnt.get(wi, c0, c1);
+        part += (c0 < clipv ? c0 : clipv) + (c1 < clipv ? c1 : clipv);
+    }
+    part = yam_warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    unsigned long long clipped_total = 0;
+    for (int i = 0; i < 32; i++) clipped_total += s_red[i];
+    __syncthreads();
+    const unsigned long long excess = (unsigned long long)area - clipped_total;
+    const unsigned long long batch = g.clip > 0 ? excess / kBins16 : 0;
+    const uint32_t residual = g.clip > 0 ? (uint32_t)(excess - batch * kBins16) : 0;
+    const uint32_t step = residual ? max((uint32_t)kBins16 / residual, 1u) : 1u;
+
+    auto adjusted = [&](uint32_t bin, unsigned long long c) -> unsigned long long {
+        unsigned long long a = (c < clipv ? c : clipv) + batch;
+        if (residual && (bin % step) == 0 && (bin / step) < residual) a += 1;
+        return a;
+    };
+
+    // pass 1: warp totals of adjusted counts
+    part = 0;
+    for (int i = 0; i < 32; i++) {
+        const int wi = wbase + 32 * i + lane;
+        unsigned long long c0, c1;
+        cnt.get(wi, c0, c1);
+        part += adjusted(2 * wi, c0) + adjusted(2 * wi + 1, c1);
+    }
+    part = yam_warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run0 = 0;
+        for (int i = 0; i < 32; i++) {
+            s_base[i] = run0;
+            run0 += s_red[i];
+        }
+    }
+    __syncthreads();
+
+    // pass 2: ordered prefix sum -> LUT
+    unsigned long long run = s_base[warp];
+    for (int i = 0; i < 32; i++) {
+        const int wi = wbase + 32 * i + lane;
+        unsigned long long c0, c1;
+        cnt.get(wi, c0, c1);
+        const unsigned long long a0 = adjusted(2 * wi, c0), a1 = adjusted(2 * wi + 1, c1);
+        unsigned long long incl = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const unsigned long long before = run + incl - (a0 + a1);
+        const unsigned long long cum0 = before + a0, cum1 = cum0 + a1;
+        // cv2: saturate_cast<ushort>(sum * lutScale) with sum an int converted to float
+        const uint32_t l0 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum0, g.lut_scale), 65535);
+        const uint32_t l1 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum1, g.lut_scale), 65535);
+        reinterpret_cast<uint32_t*>(lut)[wi] = l0 | (l1 << 16);
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
 // u16: one CTA per tile at a time (persistent CTAs loop over the tiles of a frame chunk):
 // histogram -> clip -> redistribute -> scan -> LUT.  grid (min(tiles_total, SMs)); each CTA owns
 // one 256 KiB overflow slot that is all-zero between tiles.
@@ -268,10 +369,6 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint
     const int tiles_per_frame = g.tiles_x * g.tiles_y;
     const int total_tiles = tiles_per_frame * frames;
     uint32_t* ovf = overflow + (int64_t)blockIdx.x * kBins16;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long area = (long long)g.tw * g.th;
-    const int wbase = warp * 1024;  // each warp owns words [1024*warp, +1024); lane reads base+32*i+lane
-    const unsigned long long clipv = g.clip > 0 ? (unsigned long long)g.clip : ~0ull;
 
     for (int slot = blockIdx.x; slot < total_tiles; slot += gridDim.x) {
         const int frame = slot / tiles_per_frame, tile = slot - frame * tiles_per_frame;
@@ -288,83 +385,9 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint
         __syncthreads();
         const bool use_ovf = s_spilled != 0;
 
-        // pass 0: sum of clipped counts -> excess
-        unsigned long long part = 0;
-        for (int i = 0; i < 32; i++) {
-            const int wi = wbase + 32 * i + lane;
-            const uint32_t wv = sh[wi];
-            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
-            if (use_ovf) {
-                c0 += __ldcg(&ovf[2 * wi]);
-                c1 += __ldcg(&ovf[2 * wi + 1]);
-            }
-            part += (c0 < clipv ? c0 : clipv) + (c1 < clipv ? c1 : clipv);
-        }
-        part = yam_warp_sum(part);
-        if (lane == 0) s_red[warp] = part;
-        __syncthreads();
-        unsigned long long clipped_total = 0;
-        for (int i = 0; i < 32; i++) clipped_total += s_red[i];
-        __syncthreads();
-        const unsigned long long excess = (unsigned long long)area - clipped_total;
-        const unsigned long long batch = g.clip > 0 ? excess / kBins16 : 0;
-        const uint32_t residual = g.clip > 0 ? (uint32_t)(excess - batch * kBins16) : 0;
-        const uint32_t step = residual ? max((uint32_t)kBins16 / residual, 1u) : 1u;
-
-        auto adjusted = [&](uint32_t bin, unsigned long long c) -> unsigned long long {
-            unsigned long long a = (c < clipv ? c : clipv) + batch;
-            if (residual && (bin % step) == 0 && (bin / step) < residual) a += 1;
-            return a;
-        };
-
-        // pass 1: warp totals of adjusted counts
-        part = 0;
-        for (int i = 0; i < 32; i++) {
-            const int wi = wbase + 32 * i + lane;
-            const uint32_t wv = sh[wi];
-            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
-            if (use_ovf) {
-                c0 += __ldcg(&ovf[2 * wi]);
-                c1 += __ldcg(&ovf[2 * wi + 1]);
-            }
-            part += adjusted(2 * wi, c0) + adjusted(2 * wi + 1, c1);
-        }
-        part = yam_warp_sum(part);
-        if (lane == 0) s_red[warp] = part;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long run0 = 0;
-            for (int i = 0; i < 32; i++) {
-                s_base[i] = run0;
-                run0 += s_red[i];
-            }
-        }
-        __syncthreads();
-
-        // pass 2: ordered prefix sum -> LUT
-        unsigned long long run = s_base[warp];
-        for (int i = 0; i < 32; i++) {
-            const int wi = wbase + 32 * i + lane;
-            const uint32_t wv = sh[wi];
-            unsigned long long c0 = wv & 0xffffu, c1 = wv >> 16;
-            if (use_ovf) {
-                c0 += __ldcg(&ovf[2 * wi]);
-                c1 += __ldcg(&ovf[2 * wi + 1]);
-            }
-            const unsigned long long a0 = adjusted(2 * wi, c0), a1 = adjusted(2 * wi + 1, c1);
-            unsigned long long incl = a0 + a1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const unsigned long long before = run + incl - (a0 + a1);
-            const unsigned long long cum0 = before + a0, cum1 = cum0 + a1;
-            // cv2: saturate_cast<ushort>(sum * lutScale) with sum an int converted to float
-            const uint32_t l0 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum0, g.lut_scale), 65535);
-            const uint32_t l1 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum1, g.lut_scale), 65535);
-            reinterpret_cast<uint32_t*>(lut)[wi] = l0 | (l1 << 16);
-            run += __shfl_sync(0xffffffffu, incl, 31);
+        {
+            SmemCounts cnt{sh, ovf, use_ovf};
+            clahe_lut_passes(cnt, g, lut, s_red, s_base);
         }
         __syncthreads();
         // leave the overflow slot zero for the next tile / call
@@ -374,6 +397,44 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint
             __syncthreads();
         }
     }
+}
+
+// Big tiles (mosaic strips: 8 tiles of 67 Mpx) would leave most SMs idle with one CTA per tile:
+// `parts` CTAs per tile accumulate row slabs into packed shared counters and flush the non-zero
+// bins into the tile's 32-bit global histogram (zeroed by the caller); a second kernel builds the LUT.
+__global__ void __launch_bounds__(kHistThreads, 1) clahe_hist16_parts_kernel(const uint16_t* __restrict__ src_all,
+                                                                             ClaheGeom g,
+                                                                             uint32_t* __restrict__ ghist) {
+    extern __shared__ __align__(16) uint32_t sh[];
+    const int tiles_per_frame = g.tiles_x * g.tiles_y;
+    const int slot = blockIdx.y;
+    const int frame = slot / tiles_per_frame, tile = slot - frame * tiles_per_frame;
+    const int tyi = tile / g.tiles_x, txi = tile - tyi * g.tiles_x;
+    const uint16_t* src = src_all + (int64_t)frame * g.h * g.w;
+    uint32_t* gh = ghist + (int64_t)slot * kBins16;
+    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) sh[i] = 0;
+    __syncthreads();
+    const int parts = gridDim.x;
+    const int rows_per = (g.th + parts - 1) / parts;
+    const int r0 = tyi * g.th + blockIdx.x * rows_per;
+    const int r1 = min((tyi + 1) * g.th, r0 + rows_per);
+    accumulate16<uint32_t>(sh, gh, nullptr, src, g.h, g.w, txi * g.tw, (txi + 1) * g.tw, r0, r1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) {
+        const uint32_t wv = sh[i];
+        if (wv & 0xffffu) atomicAdd(&gh[2 * i], wv & 0xffffu);
+        if (wv >> 16) atomicAdd(&gh[2 * i + 1], wv >> 16);
+    }
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1) clahe_lut_from_hist_kernel(const uint32_t* __restrict__ ghist,
+                                                                              ClaheGeom g,
+                                                                              uint16_t* __restrict__ luts) {
+    __shared__ unsigned long long s_red[32];
+    __shared__ unsigned long long s_base[32];
+    const int slot = blockIdx.x;
+    GlobalCounts cnt{ghist + (int64_t)slot * kBins16};
+    clahe_lut_passes(cnt, g, luts + (int64_t)slot * kBins16, s_red, s_base);
 }
 
 // u8: one CTA (256 threads) per tile
@@ -553,6 +614,39 @@ int clahe_geometry(int64_t h, int64_t w, int dtype, double clip_limit, int tiles
     return YAM_OK;
 }
 
+// LUTs of `nf` frames starting at s_ptr into `luts` (tiles x 65536 u16 per frame).  `scratch_tail`
+// provides max(slots x 256 KiB overflow, tiles_total x 256 KiB histograms) of scratch.
+int clahe_luts16(yam_ctx* ctx, const uint16_t* s_ptr, const ClaheGeom& g, int64_t nf, uint16_t* luts, void* scratch_tail) {
+    const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
+    const int64_t total_tiles = tiles * nf;
+    const int slots = ctx->num_sms;
+    const long long area = (long long)g.tw * g.th;
+    static bool attr_set = false;
+    if (!attr_set) {
+        YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+        YAM_CUDA(cudaFuncSetAttribute(clahe_hist16_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+        attr_set = true;
+    }
+    if (total_tiles * 2 <= slots && area >= (4ll << 20)) {
+        // few huge tiles: split every tile over several CTAs
+        int64_t parts = (2 * (int64_t)slots + total_tiles - 1) / total_tiles;
+        if (parts > g.th) parts = g.th;
+        YAM_CUDA(cudaMemsetAsync(scratch_tail, 0, (size_t)total_tiles * kBins16 * sizeof(uint32_t), ctx->stream));
+        clahe_hist16_parts_kernel<<<dim3((unsigned)parts, (unsigned)total_tiles), kHistThreads, kSmem16, ctx->stream>>>(
+            s_ptr, g, (uint32_t*)scratch_tail);
+        YAM_LAUNCHED(ctx);
+        clahe_lut_from_hist_kernel<<<(unsigned)total_tiles, kHistThreads, 0, ctx->stream>>>((const uint32_t*)scratch_tail, g, luts);
+        YAM_LAUNCHED(ctx);
+        return YAM_OK;
+    }
+    // the kernel restores zeros after use, but scratch is shared with other ops: clear it
+    YAM_CUDA(cudaMemsetAsync(scratch_tail, 0, (size_t)slots * kBins16 * sizeof(uint32_t), ctx->stream));
+    const unsigned gridx = (unsigned)(total_tiles < slots ? total_tiles : slots);
+    clahe_lut16_kernel<<<gridx, kHistThreads, kSmem16, ctx->stream>>>(s_ptr, g, (int)nf, (uint32_t*)scratch_tail, luts);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
 int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype,
               unsigned long long* hist) {
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
@@ -682,29 +776,19 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
         int64_t chunk = (int64_t)((64u << 20) / lut_frame);
         if (chunk < 1) chunk = 1;
         if (chunk > n) chunk = n;
-        const int slots = ctx->num_sms;
-        const size_t ovf_bytes = (size_t)slots * kBins16 * sizeof(uint32_t);
+        const int64_t tail_slots = (tiles * chunk > ctx->num_sms) ? tiles * chunk : ctx->num_sms;
+        const size_t ovf_bytes = (size_t)tail_slots * kBins16 * sizeof(uint32_t);
         const size_t luts_bytes = yam_align_up(lut_frame * chunk, 256);
         void* scratch = nullptr;
         if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes, &scratch)) return rc;
         uint16_t* luts = (uint16_t*)scratch;
-        uint32_t* ovf = (uint32_t*)((char*)scratch + luts_bytes);
-        // the kernel restores zeros after use, but scratch is shared with other ops: clear it
-        YAM_CUDA(cudaMemsetAsync(ovf, 0, ovf_bytes, ctx->stream));
-        static bool attr_set = false;
-        if (!attr_set) {
-            YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
-            attr_set = true;
-        }
+        void* tail = (char*)scratch + luts_bytes;
         const int64_t frame_px = h * w;
         for (int64_t f0 = 0; f0 < n; f0 += chunk) {
             const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
             const uint16_t* s_ptr = (const uint16_t*)src + f0 * frame_px;
             uint16_t* d_ptr = (uint16_t*)dst + f0 * frame_px;
-            const int64_t total_tiles = tiles * nf;
-            const unsigned gridx = (unsigned)(total_tiles < slots ? total_tiles : slots);
-            clahe_lut16_kernel<<<gridx, kHistThreads, kSmem16, ctx->stream>>>(s_ptr, g, (int)nf, ovf, luts);
-            YAM_LAUNCHED(ctx);
+            if (int rc = clahe_luts16(ctx, s_ptr, g, nf, luts, tail)) return rc;
             dim3 grid((unsigned)h, 1, (unsigned)nf);
             clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, luts);
             YAM_LAUNCHED(ctx);
@@ -733,15 +817,10 @@ int yam_clahe_luts(yam_ctx* ctx, const void* src, int64_t h, int64_t w, int dtyp
     if (int rc = clahe_geometry(h, w, dtype, clip_limit, tiles_x, tiles_y, &g)) return rc;
     const int64_t tiles = (int64_t)tiles_x * tiles_y;
     if (dtype == YAM_U16) {
-        const int slots = ctx->num_sms;
-        const size_t ovf_bytes = (size_t)slots * kBins16 * sizeof(uint32_t);
+        const int64_t tail_slots = tiles > ctx->num_sms ? tiles : ctx->num_sms;
         void* scratch = nullptr;
-        if (int rc = yam_scratch(ctx, ovf_bytes, &scratch)) return rc;
-        YAM_CUDA(cudaMemsetAsync(scratch, 0, ovf_bytes, ctx->stream));
-        YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
-        const unsigned gridx = (unsigned)(tiles < slots ? tiles : slots);
-        clahe_lut16_kernel<<<gridx, kHistThreads, kSmem16, ctx->stream>>>((const uint16_t*)src, g, 1, (uint32_t*)scratch,
-                                                                        (uint16_t*)luts_dev);
+        if (int rc = yam_scratch(ctx, (size_t)tail_slots * kBins16 * sizeof(uint32_t), &scratch)) return rc;
+        return clahe_luts16(ctx, (const uint16_t*)src, g, 1, (uint16_t*)luts_dev, scratch);
     } else {
         clahe_lut8_kernel<<<dim3((unsigned)tiles, 1, 1), 256, 0, ctx->stream>>>((const uint8_t*)src, g, (uint8_t*)luts_dev);
     }

@@ -267,12 +267,24 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         edges = comm.all_gather(edge)
         cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
         def merge():
+            # host: only the labels on the strip boundaries; device: the O(all labels) prefix work
             tops = [be.to_host(e[0]) for e in edges]
             bottoms = [be.to_host(e[1]) for e in edges]
-            return sharding.boundary_remaps(tops, bottoms, [int(v.item()) for v in cnts])
+            involved, roots, offs = sharding.boundary_roots(tops, bottoms, [int(v.item()) for v in cnts])
+            total_local = int(offs[-1])
+            root = torch.arange(total_local + 1, dtype=torch.int64, device=be.device)
+            if involved.size:
+                root[torch.from_numpy(involved).to(be.device)] = torch.from_numpy(roots).to(be.device)
+            is_root = root == torch.arange(total_local + 1, dtype=torch.int64, device=be.device)
+            is_root[0] = False
+            rank = torch.cumsum(is_root.to(torch.int32), dim=0, dtype=torch.int32)
+            glob = rank[root]
+            glob[0] = 0
+            return glob, offs, int(rank[-1].item()) if total_local else 0
 
-        remaps, total = comm.once(merge)
-        be.relabel(labels, be.to_device(remaps[rank]))
+        glob, offs, total = comm.once(merge)
+        remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
+        be.relabel(labels, remap)
     else:
         total = n_local
 

@@ -104,20 +104,16 @@ def merge_label_strips(strips: Sequence[np.ndarray], counts: Sequence[int]) -> T
 
 
 
-def boundary_remaps(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], counts: Sequence[int]):
-    """Cross-strip label merge from boundary rows only (what the ranks exchange).
+def boundary_roots(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], counts: Sequence[int]):
+    """Union the components that touch across strip boundaries (8-connectivity).
 
-    ``tops[r]`` / ``bottoms[r]`` are the first / last label row of strip ``r`` (per-strip canonical
-    labels 1..counts[r]).  Components touching across a strip boundary (8-connectivity) are united;
-    global labels are assigned in raster-first order: a merged component keeps the position of its
-    part in the earliest strip, whose per-strip label order already is raster order.
-    Returns ``(remaps, total)`` with ``remaps[r]`` an int32 table of size counts[r]+1 mapping local
-    to global labels (entry 0 stays 0).  Vectorised: minimum-label propagation over the unique
-    boundary pairs with pointer jumping (iterations ~ number of strips a component crosses).
+    Works on the boundary rows only.  Labels are made globally unique as ``offs[r] + local``;
+    returns ``(involved, roots, offs)``: the sorted global ids that take part in any cross-strip
+    pair and, for each, the smallest global id of its merged set.  Every other label is its own root.
+    Vectorised minimum-label propagation with pointer jumping over the (few) involved labels.
     """
     world = len(counts)
     offs = np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64))])
-    total_local = int(offs[-1])
     pair_list = []
     for r in range(world - 1):
         up = np.asarray(bottoms[r]).astype(np.int64)
@@ -129,32 +125,45 @@ def boundary_remaps(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], c
             both = (a > 0) & (b > 0)
             if both.any():
                 pair_list.append(np.stack([a[both] + offs[r], b[both] + offs[r + 1]], axis=1))
+    if not pair_list:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), offs
+    pairs = np.unique(np.concatenate(pair_list, axis=0), axis=0)
+    involved, inv = np.unique(pairs.ravel(), return_inverse=True)
+    pa, pb = inv.reshape(-1, 2)[:, 0], inv.reshape(-1, 2)[:, 1]
+    root = np.arange(involved.size, dtype=np.int64)  # compact ids are ordered like the global ids
+    while True:
+        m = np.minimum(root[pa], root[pb])
+        new = root.copy()
+        np.minimum.at(new, pa, m)
+        np.minimum.at(new, pb, m)
+        new = new[new]
+        if np.array_equal(new, root):
+            break
+        root = new
+    while True:
+        nxt = root[root]
+        if np.array_equal(nxt, root):
+            break
+        root = nxt
+    return involved, involved[root], offs
+
+
+def boundary_remaps(tops: Sequence[np.ndarray], bottoms: Sequence[np.ndarray], counts: Sequence[int]):
+    """Host version of the cross-strip label merge: ``(remaps, total)`` with ``remaps[r]`` an int32
+    table of size counts[r]+1 mapping local to global labels (entry 0 stays 0).  Global labels are
+    assigned in raster-first order: a merged component keeps the position of its part in the
+    earliest strip, whose per-strip label order already is raster order."""
+    involved, roots, offs = boundary_roots(tops, bottoms, counts)
+    total_local = int(offs[-1])
     root = np.arange(total_local + 1, dtype=np.int64)
-    if pair_list:
-        pairs = np.unique(np.concatenate(pair_list, axis=0), axis=0)
-        pa, pb = pairs[:, 0], pairs[:, 1]
-        while True:
-            m = np.minimum(root[pa], root[pb])
-            new = root.copy()
-            np.minimum.at(new, pa, m)
-            np.minimum.at(new, pb, m)
-            new = new[new]  # pointer jumping
-            if np.array_equal(new, root):
-                break
-            root = new
-        # make every entry point at its final root
-        while True:
-            nxt = root[root]
-            if np.array_equal(nxt, root):
-                break
-            root = nxt
+    root[involved] = roots
     is_root = root == np.arange(total_local + 1)
     is_root[0] = False
-    rank = np.cumsum(is_root)  # global label of a root = number of roots up to and including it
+    rank = np.cumsum(is_root)
     glob = rank[root].astype(np.int32)
     glob[0] = 0
-    remaps = [np.concatenate([[0], glob[offs[r] + 1: offs[r + 1] + 1]]).astype(np.int32) for r in range(world)]
+    remaps = [np.concatenate([[0], glob[offs[r] + 1: offs[r + 1] + 1]]).astype(np.int32) for r in range(len(counts))]
     return remaps, int(is_root.sum())
 
 
-__all__ = ["allreduce_histogram", "boundary_remaps", "frame_block", "gather_tables", "merge_label_strips", "row_strip"]
+__all__ = ["allreduce_histogram", "boundary_remaps", "boundary_roots", "frame_block", "gather_tables", "merge_label_strips", "row_strip"]
