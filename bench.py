@@ -144,55 +144,63 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region by an NVML polling thread
+    (about every 2 ms; `nvidia-smi -lms` cannot sample a region of a few milliseconds)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.path = Path(f"/tmp/yam_clocks_{os.getpid()}.csv")
+        self.samples = []
+        self.reasons = set()
+        self._stop = None
+        self._thread = None
+        self.max_mhz = None
 
     def start(self):
+        import threading
+
         try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-free common case (identity)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
+        names = {
+            getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        self._stop = threading.Event()
+
+        def poll():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = int(get_reasons(h))
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop.wait(0.002)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx = [], []
-        reasons = set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.path.read_text().splitlines():
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        try:
-            self.path.unlink()
-        except OSError:
-            pass
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
         return out
 
 

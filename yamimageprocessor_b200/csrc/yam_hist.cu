@@ -583,6 +583,98 @@ void otsu_scan_frames_host(const uint64_t* hists, int bins, int64_t n, int32_t* 
     for (auto& th : pool) th.join();
 }
 
+// Interleaved LUTs for the apply pass on large 16-bit frames: quad[cell][v] holds the four LUT
+// values a pixel of interpolation cell (cy, cx) needs, so the apply kernel issues ONE 8-byte gather
+// per pixel instead of four 2-byte gathers (the gathers, not HBM, bound the plain apply kernel).
+// cell (cy, cx), cy in [0, tiles_y], cx in [0, tiles_x]: tiles (max(cy-1,0) | min(cy,ty-1)) x (max(cx-1,0) | min(cx,tx-1))
+__global__ void __launch_bounds__(256) clahe_quad_build_kernel(const uint16_t* __restrict__ luts, int tiles_x, int tiles_y,
+                                                              ushort4* __restrict__ quad) {
+    const int cell = blockIdx.y;
+    const int cy = cell / (tiles_x + 1), cx = cell - cy * (tiles_x + 1);
+    const int ty1 = max(cy - 1, 0), ty2 = min(cy, tiles_y - 1);
+    const int tx1 = max(cx - 1, 0), tx2 = min(cx, tiles_x - 1);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    ushort4 q;
+    q.x = luts[((int64_t)ty1 * tiles_x + tx1) * kBins16 + v];
+    q.y = luts[((int64_t)ty1 * tiles_x + tx2) * kBins16 + v];
+    q.z = luts[((int64_t)ty2 * tiles_x + tx1) * kBins16 + v];
+    q.w = luts[((int64_t)ty2 * tiles_x + tx2) * kBins16 + v];
+    quad[(int64_t)cell * kBins16 + v] = q;
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_quad_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+                                                              ClaheGeom g, const ushort4* __restrict__ quad) {
+    const int y = blockIdx.x;
+    const float tyf = __fsub_rn(__fmul_rn((float)(y + g.y_off), g.inv_th), 0.5f);
+    const int fy = (int)floorf(tyf);
+    const float ya = __fsub_rn(tyf, (float)fy), ya1 = __fsub_rn(1.0f, ya);
+    const int cy = min(max(fy + 1, 0), g.tiles_y);
+    const uint2* qrow = reinterpret_cast<const uint2*>(quad) + (int64_t)cy * (g.tiles_x + 1) * kBins16;
+    const uint16_t* srow = src + (int64_t)y * g.w;
+    uint16_t* drow = dst + (int64_t)y * g.w;
+    const bool aligned = ((g.w % 8) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+    const int groups = (g.w + 7) / 8;
+    for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+        const int x0 = gi * 8;
+        uint16_t in[8], out[8];
+        if (aligned) {
+            *reinterpret_cast<uint4*>(in) = yam_ld_stream(reinterpret_cast<const uint4*>(srow + x0));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) in[i] = (x0 + i < g.w) ? srow[x0 + i] : (uint16_t)0;
+        }
+        uint2 q[8];
+        float xa[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float txf = __fsub_rn(__fmul_rn((float)(x0 + i), g.inv_tw), 0.5f);
+            const int fx = (int)floorf(txf);
+            xa[i] = __fsub_rn(txf, (float)fx);
+            const int cx = min(max(fx + 1, 0), g.tiles_x);
+            q[i] = __ldg(qrow + (int64_t)cx * kBins16 + in[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float xa1 = __fsub_rn(1.0f, xa[i]);
+            const float l11 = (float)(q[i].x & 0xffffu), l12 = (float)(q[i].x >> 16);
+            const float l21 = (float)(q[i].y & 0xffffu), l22 = (float)(q[i].y >> 16);
+            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa[i]));
+            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa[i]));
+            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+            out[i] = (uint16_t)yam_rint_sat(res, 65535);
+        }
+        if (aligned) {
+            yam_st_stream(reinterpret_cast<uint4*>(drow + x0), *reinterpret_cast<const uint4*>(out));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (x0 + i < g.w) drow[x0 + i] = out[i];
+        }
+    }
+}
+
+constexpr int64_t kQuadMinPixels = 8ll << 20;  // below this the 40 MB quad build costs more than it saves
+constexpr int kQuadMaxCells = 128;
+
+inline bool clahe_use_quad(int64_t pixels, int tiles_x, int tiles_y) {
+    return pixels >= kQuadMinPixels && (tiles_x + 1) * (tiles_y + 1) <= kQuadMaxCells;
+}
+inline size_t clahe_quad_bytes(int tiles_x, int tiles_y) {
+    return (size_t)(tiles_x + 1) * (tiles_y + 1) * kBins16 * sizeof(ushort4);
+}
+
+// apply `rows` rows of one frame with the quad path: build quad from luts, then gather
+int clahe_apply16_quad(yam_ctx* ctx, const uint16_t* s_ptr, uint16_t* d_ptr, int64_t rows, const ClaheGeom& g,
+                       const uint16_t* luts, ushort4* quad) {
+    const int cells = (g.tiles_x + 1) * (g.tiles_y + 1);
+    clahe_quad_build_kernel<<<dim3(kBins16 / 256, (unsigned)cells), 256, 0, ctx->stream>>>(luts, g.tiles_x, g.tiles_y, quad);
+    YAM_LAUNCHED(ctx);
+    clahe_apply_quad_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, quad);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
 // cv2 CLAHE geometry: pad right/bottom (REFLECT_101) when either side is not divisible by the grid
 // (both sides get padded then), tile area, clip limit, LUT scale
 int clahe_geometry(int64_t h, int64_t w, int dtype, double clip_limit, int tiles_x, int tiles_y, ClaheGeom* out) {
@@ -776,22 +868,30 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
         int64_t chunk = (int64_t)((64u << 20) / lut_frame);
         if (chunk < 1) chunk = 1;
         if (chunk > n) chunk = n;
+        const bool quad_path = clahe_use_quad(h * w, tiles_x, tiles_y);
+        if (quad_path) chunk = 1;
         const int64_t tail_slots = (tiles * chunk > ctx->num_sms) ? tiles * chunk : ctx->num_sms;
-        const size_t ovf_bytes = (size_t)tail_slots * kBins16 * sizeof(uint32_t);
+        const size_t ovf_bytes = yam_align_up((size_t)tail_slots * kBins16 * sizeof(uint32_t), 256);
         const size_t luts_bytes = yam_align_up(lut_frame * chunk, 256);
+        const size_t quad_bytes = quad_path ? clahe_quad_bytes(tiles_x, tiles_y) : 0;
         void* scratch = nullptr;
-        if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes, &scratch)) return rc;
+        if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes + quad_bytes, &scratch)) return rc;
         uint16_t* luts = (uint16_t*)scratch;
         void* tail = (char*)scratch + luts_bytes;
+        ushort4* quad = (ushort4*)((char*)scratch + luts_bytes + ovf_bytes);
         const int64_t frame_px = h * w;
         for (int64_t f0 = 0; f0 < n; f0 += chunk) {
             const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
             const uint16_t* s_ptr = (const uint16_t*)src + f0 * frame_px;
             uint16_t* d_ptr = (uint16_t*)dst + f0 * frame_px;
             if (int rc = clahe_luts16(ctx, s_ptr, g, nf, luts, tail)) return rc;
-            dim3 grid((unsigned)h, 1, (unsigned)nf);
-            clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, luts);
-            YAM_LAUNCHED(ctx);
+            if (quad_path) {
+                if (int rc = clahe_apply16_quad(ctx, s_ptr, d_ptr, h, g, luts, quad)) return rc;
+            } else {
+                dim3 grid((unsigned)h, 1, (unsigned)nf);
+                clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, luts);
+                YAM_LAUNCHED(ctx);
+            }
         }
     } else {
         void* scratch = nullptr;
@@ -847,6 +947,11 @@ int yam_clahe_apply(yam_ctx* ctx, const void* src, void* dst, int64_t rows, int6
     g.inv_th = 1.0f / (float)tile_h;
     g.y_off = (int)y_offset;
     dim3 grid((unsigned)rows, 1, 1);
+    if (dtype == YAM_U16 && clahe_use_quad(rows * w, tiles_x, tiles_y)) {
+        void* scratch = nullptr;
+        if (int rc = yam_scratch(ctx, clahe_quad_bytes(tiles_x, tiles_y), &scratch)) return rc;
+        return clahe_apply16_quad(ctx, (const uint16_t*)src, (uint16_t*)dst, rows, g, (const uint16_t*)luts_dev, (ushort4*)scratch);
+    }
     if (dtype == YAM_U16)
         clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, g, (const uint16_t*)luts_dev);
     else
