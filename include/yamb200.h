@@ -52,6 +52,7 @@ extern "C" {
 #define YAM_MORPH_DILATE 1
 #define YAM_MORPH_OPEN 2
 #define YAM_MORPH_CLOSE 3
+#define YAM_MORPH_OPEN_CLOSE 4 /* open followed by close (bit-mask path) */
 #define YAM_SHAPE_RECT 0
 #define YAM_SHAPE_ELLIPSE 1
 #define YAM_SHAPE_CROSS 2
@@ -134,6 +135,21 @@ int yam_morph(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
 /* open(k,it) followed by close(k,it), rectangular SE, fused in one pass (segmentation config) */
 int yam_morph_open_close(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
                          int dtype, int ksize, int iterations);
+
+/* ---- fused binary segmentation path ----------------------------------------------------------
+ * A thresholded mask is binary, so adaptive threshold -> open -> close -> connected components can
+ * run on 1-bit-per-pixel masks (row-major uint32 words, wpr = ceil(w/32) words per row, bit i of
+ * word j = pixel 32*j+i, bits beyond the width are 0) without ever writing the 8-bit mask:
+ * yam_adaptive_threshold_bits = yam_adaptive_threshold with packed output (block 3,5,7,11,15);
+ * yam_bits_morph = cv2.erode/dilate/morphologyEx on a {0,255} mask, RECTANGULAR element;
+ * yam_bits_unpack = packed bits -> uint8 {0,255}; yam_ccl_label_bits = yam_ccl_label on bits. */
+int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h,
+                                int64_t w, int dtype, int block_size, double C);
+int yam_bits_morph(yam_ctx* ctx, const uint32_t* bits_in, uint32_t* bits_out, int64_t n, int64_t h,
+                   int64_t w, int op, int ksize, int iterations);
+int yam_bits_unpack(yam_ctx* ctx, const uint32_t* bits, void* mask_u8, int64_t n, int64_t h, int64_t w);
+int yam_ccl_label_bits(yam_ctx* ctx, const uint32_t* bits, int32_t* labels, int64_t n, int64_t h,
+                       int64_t w, int32_t* counts_dev, int32_t* counts_host);
 
 /* ---- K7/K8 histogram family ----------------------------------------------------------------
  * per-frame histogram: hist_dev[n][bins] of uint64, bins = 256 (U8) | 65536 (U16) */

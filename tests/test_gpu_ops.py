@@ -354,6 +354,58 @@ def test_region_props(backend, rng):
         assert_same(props[:, 4:8], want["bbox"], "bbox")
 
 
+# --------------------------------------------------------------------------- fused binary path
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_adaptive_bits_and_unpack(backend, rng, dt):
+    for shape in ((64, 64), (40, 72), (130, 257), (33, 71), (200, 1100)):
+        a = blobs(rng, shape, dt) if shape[0] > 40 else rnd(rng, shape, dt)
+        for block, C in ((11, 2), (5, 2), (15, -1)):
+            bits = backend.adaptive_threshold_bits(dev(backend, a), block, C)
+            got = host(backend, backend.bits_unpack(bits, shape[1]))
+            want = host(backend, backend.adaptive_threshold(dev(backend, a), block, C))
+            assert_same(got, want, f"adaptive bits {block},{C} {shape}")
+            raw = host(backend, bits).view(np.uint32)
+            if shape[1] % 32:  # bits beyond the width are zero
+                assert int((raw[:, -1] >> (shape[1] % 32)).max()) == 0
+
+
+@pytest.mark.parametrize("k,it", [(1, 1), (2, 1), (3, 1), (4, 2), (5, 1), (5, 3), (9, 2), (15, 3), (31, 2)])
+def test_bits_morph(backend, rng, k, it):
+    for shape in ((64, 64), (33, 71), (130, 257), (70, 1200)):
+        m = ((rng.random(shape) < 0.55).astype(np.uint8)) * 255
+        m[5:25, 3:60] = 255
+        # pack through the adaptive-bits unpack round trip's inverse: build bits on the host
+        wpr = (shape[1] + 31) // 32
+        padded = np.zeros((shape[0], wpr * 32), np.uint8)
+        padded[:, : shape[1]] = m > 0
+        bits_np = np.packbits(padded.reshape(shape[0], wpr, 32), axis=2, bitorder="little").view(np.uint32).reshape(shape[0], wpr)
+        bits = dev(backend, bits_np.view(np.int32))
+        for op, fn in ((0, O.erode), (1, O.dilate), (2, O.morph_open), (3, O.morph_close)):
+            got = host(backend, backend.bits_unpack(backend.bits_morph(bits, shape[1], op, k, it), shape[1]))
+            assert_same(got, fn(m, "Rectangular", k, it), f"bits morph op={op} k={k} it={it} {shape}")
+        got = host(backend, backend.bits_unpack(backend.bits_morph(bits, shape[1], 4, k, it), shape[1]))
+        want = O.morph_close(O.morph_open(m, "Rectangular", k, it), "Rectangular", k, it)
+        assert_same(got, want, f"bits open+close k={k} it={it} {shape}")
+
+
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_segment_fused_equals_unfused_chain(backend, rng, dt):
+    for shape in ((64, 64), (130, 257), (300, 520), (96, 1111)):
+        a = blobs(rng, shape, dt)
+        labels, counts = backend.segment_fused(dev(backend, a), 11, 2, 5, 1)
+        m = O.morph_close(O.morph_open(O.adaptive_threshold(a, 11, 2), "Rectangular", 5, 1), "Rectangular", 5, 1)
+        n_want, want = O.ccl_label(m)
+        assert int(host(backend, counts)[0]) == n_want
+        assert_same(host(backend, labels), want, f"fused segmentation {shape}")
+    stack = np.stack([blobs(rng, (80, 96), dt) for _ in range(3)])
+    labels, counts = backend.segment_fused(dev(backend, stack), 11, 2, 5, 1)
+    for i in range(3):
+        m = O.morph_close(O.morph_open(O.adaptive_threshold(stack[i], 11, 2), "Rectangular", 5, 1), "Rectangular", 5, 1)
+        n_want, want = O.ccl_label(m)
+        assert int(host(backend, counts)[i]) == n_want
+        assert_same(host(backend, labels)[i], want, f"fused segmentation stack {i}")
+
+
 # --------------------------------------------------------------------------- errors
 def test_errors_are_python_exceptions(backend, rng):
     from yamimageprocessor_b200.backend import YamError

@@ -54,7 +54,7 @@ def _ctype_of(decl: str):
     stars = d.count("*")
     base = d.replace("*", " ").split()
     # drop the parameter name when present
-    known = {"int", "int64_t", "int32_t", "uint8_t", "uint64_t", "double", "void", "char", "yam_ctx"}
+    known = {"int", "int64_t", "int32_t", "uint8_t", "uint32_t", "uint64_t", "double", "void", "char", "yam_ctx"}
     tokens = [t for t in base if t in known]
     if not tokens:
         raise ValueError(f"cannot parse C declaration: {decl!r}")

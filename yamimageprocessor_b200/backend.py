@@ -397,6 +397,58 @@ class Backend:
                                                                       C.cast(C.byref(t), C.c_void_p)))
         return int(t.value)
 
+    # ------------------------------------------------------------------ fused binary segmentation
+    def adaptive_threshold_bits(self, img, block_size: int = 11, C_: float = 2.0):
+        """Adaptive threshold with a 1-bit-per-pixel result: int32 tensor (..., h, ceil(w/32))."""
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        wpr = (w + 31) // 32
+        shape = (h, wpr) if img.dim() == 2 else (n, h, wpr)
+        bits = torch.empty(shape, dtype=torch.int32, device=self.device)
+        self._call("yam_adaptive_threshold_bits", self._p(img), self._p(bits), n, h, w, _dtype_code(img),
+                   int(block_size), float(C_))
+        return bits
+
+    def bits_morph(self, bits, width: int, op: int, kernel_size: int = 3, iterations: int = 1):
+        """Rectangular erode / dilate / open / close / open+close (op = MORPH_* or 4) on packed bits."""
+        torch = _torch()
+        bits = self._check(bits, dtypes=(torch.int32,), name="bits")
+        n, h, wpr = self._nhw(bits)
+        if wpr != (int(width) + 31) // 32:
+            raise ValueError("bits tensor does not match the image width")
+        out = torch.empty_like(bits)
+        self._call("yam_bits_morph", self._p(bits), self._p(out), n, h, int(width), int(op), int(kernel_size),
+                   int(iterations))
+        return out
+
+    def bits_unpack(self, bits, width: int):
+        torch = _torch()
+        bits = self._check(bits, dtypes=(torch.int32,), name="bits")
+        n, h, wpr = self._nhw(bits)
+        shape = (h, int(width)) if bits.dim() == 2 else (n, h, int(width))
+        mask = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        self._call("yam_bits_unpack", self._p(bits), self._p(mask), n, h, int(width))
+        return mask
+
+    def ccl_label_bits(self, bits, width: int):
+        torch = _torch()
+        bits = self._check(bits, dtypes=(torch.int32,), name="bits")
+        n, h, wpr = self._nhw(bits)
+        shape = (h, int(width)) if bits.dim() == 2 else (n, h, int(width))
+        labels = torch.empty(shape, dtype=torch.int32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._call("yam_ccl_label_bits", self._p(bits), self._p(labels), n, h, int(width), self._p(counts), None)
+        return labels, counts
+
+    def segment_fused(self, img, block_size: int = 11, C_: float = 2.0, morph_ksize: int = 5, iterations: int = 1):
+        """adaptive threshold -> open -> close (rectangular) -> connected components, the mask never
+        leaving its 1-bit-per-pixel form.  Same labels as the unfused chain."""
+        w = int(img.shape[-1])
+        bits = self.adaptive_threshold_bits(img, block_size, C_)
+        bits = self.bits_morph(bits, w, 4, morph_ksize, iterations)
+        return self.ccl_label_bits(bits, w)
+
     # ------------------------------------------------------------------ K10 / K11
     def ccl_label(self, mask):
         """Returns (labels int32 like mask, counts int32[n] on device)."""

@@ -195,6 +195,22 @@ __global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __res
         block_scan_array(block_counts, gridDim.x, total_nodes, s_tmp, &s_carry);
 }
 
+// ---- 1b. the same bookkeeping when the mask already is bit-packed (fused segmentation path) --------
+__global__ void __launch_bounds__(kThreads) ccl_count_kernel(const uint32_t* __restrict__ bits, CclGeom g,
+                                                             uint32_t* __restrict__ block_counts,
+                                                             uint32_t* __restrict__ total_nodes,
+                                                             unsigned int* __restrict__ counter) {
+    __shared__ uint32_t s_tmp[kThreads / 32];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_flag;
+    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = gw < g.total_words ? bits[gw] : 0u;
+    const uint32_t total = block_sum_u32(__popc(seg_starts(b)), s_tmp);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+    if (last_block_done(counter, gridDim.x, &s_flag))
+        block_scan_array(block_counts, gridDim.x, total_nodes, s_tmp, &s_carry);
+}
+
 // ---- 2. node base per word; parent init; node -> (word, start bit) ----------------------------------
 __global__ void __launch_bounds__(kThreads) ccl_nodebase_kernel(const uint32_t* __restrict__ bits, CclGeom g,
                                                                 const uint32_t* __restrict__ block_offsets,
@@ -586,10 +602,10 @@ int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* rem
     return YAM_OK;
 }
 
-int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
-                  int32_t* counts_dev, int32_t* counts_host) {
+static int ccl_label_impl(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, int32_t* labels, int64_t n,
+                          int64_t h, int64_t w, int32_t* counts_dev, int32_t* counts_host) {
     if (int rc = yam_enter(ctx)) return rc;
-    YAM_REQUIRE(mask && labels && n > 0 && h > 0 && w > 0, "ccl: bad arguments");
+    YAM_REQUIRE((mask || bits_in) && labels && n > 0 && h > 0 && w > 0, "ccl: bad arguments");
     YAM_REQUIRE(n <= 65535, "ccl: at most 65535 frames per call");
     CclGeom g;
     g.h = (int)h;
@@ -614,7 +630,8 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
     void* scratch = nullptr;
     if (int rc = yam_scratch(ctx, 2 * words_bytes + blk_bytes + chunk_bytes + 2 * frame_bytes + 256 + 2 * node_bytes, &scratch)) return rc;
     char* sp = (char*)scratch;
-    uint32_t* bits = (uint32_t*)sp; sp += words_bytes;
+    uint32_t* bits_scratch = (uint32_t*)sp; sp += words_bytes;
+    const uint32_t* bits = bits_in ? bits_in : bits_scratch;
     uint32_t* nbase = (uint32_t*)sp; sp += words_bytes;
     uint32_t* blockA = (uint32_t*)sp; sp += blk_bytes;
     uint32_t* chunkB = (uint32_t*)sp; sp += chunk_bytes;
@@ -629,7 +646,10 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
     YAM_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), ctx->stream));
     const unsigned gblocks = (unsigned)nblocks;
     const unsigned pgrid = (unsigned)(ctx->num_sms * 8);  // persistent grids for the node-parallel kernels
-    ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits, blockA, totals, counter);
+    if (bits_in)
+        ccl_count_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, totals, counter);
+    else
+        ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits_scratch, blockA, totals, counter);
     YAM_LAUNCHED(ctx);
     ccl_nodebase_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, nbase, P, node_info);
     YAM_LAUNCHED(ctx);
@@ -650,6 +670,18 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
         YAM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return YAM_OK;
+}
+
+int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
+                  int32_t* counts_dev, int32_t* counts_host) {
+    YAM_REQUIRE(mask != nullptr, "ccl: mask is NULL");
+    return ccl_label_impl(ctx, mask, nullptr, labels, n, h, w, counts_dev, counts_host);
+}
+
+int yam_ccl_label_bits(yam_ctx* ctx, const uint32_t* bits, int32_t* labels, int64_t n, int64_t h, int64_t w,
+                       int32_t* counts_dev, int32_t* counts_host) {
+    YAM_REQUIRE(bits != nullptr, "ccl: bits is NULL");
+    return ccl_label_impl(ctx, nullptr, bits, labels, n, h, w, counts_dev, counts_host);
 }
 
 int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t h,

@@ -25,7 +25,7 @@ struct TapsF {
 };
 
 enum { EPI_SHIFT = 0, EPI_BOX = 1 };
-enum { FEPI_STORE = 0, FEPI_ADAPTIVE = 1 };
+enum { FEPI_STORE = 0, FEPI_ADAPTIVE = 1, FEPI_ADAPTIVE_BITS = 2 };
 
 template <typename T>
 struct FixedTraits;
@@ -436,7 +436,8 @@ __device__ __forceinline__ void store_tile(const Tout* __restrict__ s_out, Tout*
 
 template <typename Tin, typename Tout, int KS, int FEPI>
 __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict__ src, Tout* __restrict__ dst,
-                                                          int h, int w, TapsF taps, int border, int idelta) {
+                                                          int h, int w, TapsF taps, int border, int idelta,
+                                                          uint32_t* __restrict__ bits_out, int wpr) {
     constexpr int VEC = 16 / sizeof(Tin);
     constexpr int R = KS / 2;
     constexpr int RA = round_up_c(R, VEC > 4 ? VEC : 4);
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
     float* s_t = s_in + ROWS * SWP + 8;               // +8 floats slack: the last item may read past its row
     Tout* s_out = reinterpret_cast<Tout*>(s_t + ROWS * TWP);
     src += (int64_t)blockIdx.z * h * w;
-    dst += (int64_t)blockIdx.z * h * w;
+    if (FEPI != FEPI_ADAPTIVE_BITS) dst += (int64_t)blockIdx.z * h * w;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
 
     // ---- load + convert
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
                 a = __fmaf_rn(__fadd_rn(c0[j + R + q], c0[j + R - q]), taps.v[R + q], a);
                 b = __fmaf_rn(__fadd_rn(c1[j + R + q], c1[j + R - q]), taps.v[R + q], b);
             }
-            if (FEPI == FEPI_ADAPTIVE) {
+            if (FEPI == FEPI_ADAPTIVE || FEPI == FEPI_ADAPTIVE_BITS) {
                 // mean = rint(blur) (round-half-even via the 1.5*2^23 add; blur is a convex
                 // combination of pixel values so saturation can never trigger);
                 // dst = (src - mean > -idelta) ? 255 : 0, all values exact integers in float
@@ -547,7 +548,28 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
         }
     }
     __syncthreads();
-    store_tile<Tout>(s_out, dst, h, w, x0, y0);
+    if (FEPI == FEPI_ADAPTIVE_BITS) {
+        // pack the 64x64 byte tile to 2 words per row: 1 bit per pixel, bits beyond the image are 0
+        static_assert(TW == 64, "bit packing assumes two words per tile row");
+        uint32_t* bits = bits_out + (int64_t)blockIdx.z * h * wpr;
+        const uint8_t* s8 = reinterpret_cast<const uint8_t*>(s_out);
+        for (int t = threadIdx.x; t < TH * 2; t += kThreads) {
+            const int row = t >> 1, half = t & 1;
+            const int gy = y0 + row, gw = (x0 >> 5) + half;
+            if (gy >= h || gw >= wpr) continue;
+            const uint4 q0 = *reinterpret_cast<const uint4*>(s8 + row * TW + half * 32);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(s8 + row * TW + half * 32 + 16);
+            const uint32_t wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            uint32_t word = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) word |= (((wd[i] & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+            const int valid = w - gw * 32;
+            if (valid < 32) word &= (1u << valid) - 1u;
+            bits[(int64_t)gy * wpr + gw] = word;
+        }
+    } else {
+        store_tile<Tout>(s_out, dst, h, w, x0, y0);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -657,7 +679,7 @@ int launch_fixed(yam_ctx* ctx, const T* src, T* dst, int64_t n, int64_t h, int64
 
 template <typename Tin, typename Tout, int FEPI>
 int launch_f32(yam_ctx* ctx, const Tin* src, Tout* dst, int64_t n, int64_t h, int64_t w, const TapsF& taps,
-               int ks, int border, int sat_hi, int idelta) {
+               int ks, int border, int sat_hi, int idelta, uint32_t* bits_out = nullptr, int wpr = 0) {
     dim3 grid = tile_grid(n, h, w);
     const size_t smem = f32_smem<Tin>(ks);
 #define YAM_F32_CASE(K)                                                                              \
@@ -665,7 +687,7 @@ int launch_f32(yam_ctx* ctx, const Tin* src, Tout* dst, int64_t n, int64_t h, in
         const size_t tsmem = f32_tiled_smem<Tin, Tout>(K);                                           \
         if (int rc = set_smem(sep_f32_tiled<Tin, Tout, K, FEPI>, tsmem)) return rc;                  \
         sep_f32_tiled<Tin, Tout, K, FEPI><<<grid, kThreads, tsmem, ctx->stream>>>(                   \
-            src, dst, (int)h, (int)w, taps, border, idelta);                                         \
+            src, dst, (int)h, (int)w, taps, border, idelta, bits_out, wpr);                          \
         break;                                                                                       \
     }
     switch (ks) {
@@ -675,8 +697,13 @@ int launch_f32(yam_ctx* ctx, const Tin* src, Tout* dst, int64_t n, int64_t h, in
         YAM_F32_CASE(11)
         YAM_F32_CASE(15)
         default: {
-            if (int rc = set_smem(sep_f32_kernel<Tin, Tout, 0, FEPI>, smem)) return rc;
-            sep_f32_kernel<Tin, Tout, 0, FEPI><<<grid, kThreads, smem, ctx->stream>>>(
+            if (FEPI == FEPI_ADAPTIVE_BITS) {
+                yam_set_error("adaptive_threshold_bits: block size %d has no fused kernel (use 3, 5, 7, 11 or 15)", ks);
+                return YAM_EINVAL;
+            }
+            constexpr int GEPI = FEPI == FEPI_ADAPTIVE_BITS ? FEPI_ADAPTIVE : FEPI;
+            if (int rc = set_smem(sep_f32_kernel<Tin, Tout, 0, GEPI>, smem)) return rc;
+            sep_f32_kernel<Tin, Tout, 0, GEPI><<<grid, kThreads, smem, ctx->stream>>>(
                 src, dst, (int)h, (int)w, taps, ks, border, sat_hi, idelta);
         }
     }
@@ -761,6 +788,26 @@ int yam_adaptive_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, 
     YAM_REQUIRE(dtype == YAM_U16, "adaptive_threshold: unsupported dtype %d", dtype);
     return launch_f32<uint16_t, uint8_t, FEPI_ADAPTIVE>(ctx, (const uint16_t*)src, (uint8_t*)dst, n, h, w, taps,
                                                         block_size, YAM_BORDER_REPLICATE, 65535, idelta);
+}
+
+int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h, int64_t w,
+                                int dtype, int block_size, double C) {
+    if (int rc = yam_enter(ctx)) return rc;
+    if (int rc = check_shape(src, bits_out, n, h, w, "adaptive_threshold_bits")) return rc;
+    YAM_REQUIRE((block_size & 1) && block_size >= 3 && block_size <= YAM_MAX_TAPS,
+                "adaptive_threshold_bits: block_size must be odd in [3,%d], got %d", YAM_MAX_TAPS, block_size);
+    double kf[YAM_MAX_TAPS];
+    yam_host_gaussian_taps(block_size, 0.0, kf);
+    TapsF taps;
+    for (int i = 0; i < block_size; i++) taps.v[i] = (float)kf[i];
+    const int idelta = (int)ceil(C);
+    const int wpr = (int)((w + 31) / 32);
+    if (dtype == YAM_U8)
+        return launch_f32<uint8_t, uint8_t, FEPI_ADAPTIVE_BITS>(ctx, (const uint8_t*)src, (uint8_t*)nullptr, n, h, w, taps,
+                                                                block_size, YAM_BORDER_REPLICATE, 255, idelta, bits_out, wpr);
+    YAM_REQUIRE(dtype == YAM_U16, "adaptive_threshold_bits: unsupported dtype %d", dtype);
+    return launch_f32<uint16_t, uint8_t, FEPI_ADAPTIVE_BITS>(ctx, (const uint16_t*)src, (uint8_t*)nullptr, n, h, w, taps,
+                                                             block_size, YAM_BORDER_REPLICATE, 65535, idelta, bits_out, wpr);
 }
 
 int yam_median(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype, int ksize) {
