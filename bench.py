@@ -229,19 +229,31 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         return x, run, ops
 
     if workload == "c2":
+        # Fused schedule: the thresholded mask is binary, so it stays 1 bit/pixel from the threshold
+        # kernel through open/close into the labelling (same labels as the step-by-step chain, which
+        # is listed under roofline.ops_unfused and is what the e2e PipelineManager path dispatches).
         def run(inp):
-            m = be.adaptive_threshold(inp, 11, 2)
-            m = be.morph_open_close(m, 5, 1)
-            return be.ccl_label(m)[0]
+            return be.segment_fused(inp, 11, 2, 5, 1)[0]
 
         def ops(inp):
+            wd = int(inp.shape[-1])
+            bits = be.adaptive_threshold_bits(inp, 11, 2)
+            bits2 = be.bits_morph(bits, wd, 4, 5, 1)
+            return [
+                ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(inp, 11, 2)),
+                ("bits_morph open+close 5x5 (bit_morph_chain_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
+                ("ccl_label_bits (count, nodebase, union, flatten, rootlabel, frame_offsets, final)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
+            ]
+
+        def ops_unfused(inp):
             m = be.adaptive_threshold(inp, 11, 2)
             m2 = be.morph_open_close(m, 5, 1)
             return [
-                ("adaptive_threshold_u16_b11 (sep_f32_kernel)", 3.0, lambda: be.adaptive_threshold(inp, 11, 2)),
-                ("morph_open_close_5x5_u8 (morph_rect_chain_kernel)", 4.0, lambda: be.morph_open_close(m, 5, 1)),
-                ("ccl_label (pack, union, flatten, scan, prefix, final)", 5.0, lambda: be.ccl_label(m2)),
+                ("adaptive_threshold_u16_b11 (sep_f32_tiled)", 3.0, lambda: be.adaptive_threshold(inp, 11, 2)),
+                ("morph_open_close_5x5_u8 (morph_fast_kernel)", 4.0, lambda: be.morph_open_close(m, 5, 1)),
+                ("ccl_label (pack, nodebase, union, flatten, rootlabel, frame_offsets, final)", 5.0, lambda: be.ccl_label(m2)),
             ]
+        ops.unfused = ops_unfused
         return x, run, ops
 
     if workload == "c3":
@@ -515,22 +527,26 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # per-op breakdown for the roofline of the dominant op (device-resident, L2 flushed)
-    breakdown = []
-    for name, bpp, fn in ops(inp):
-        for _ in range(2):
-            fn()
-        reps = max(3, min(args.steps, 10))
-        evs = []
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
-        breakdown.append((name, bpp, ms))
+    def measure_ops(op_list):
+        rows = []
+        for name, bpp, fn in op_list:
+            for _ in range(2):
+                fn()
+            reps = max(3, min(args.steps, 10))
+            evs = []
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            rows.append((name, bpp, statistics.mean(a.elapsed_time(b) for a, b in evs)))
+        return rows
+
+    breakdown = measure_ops(ops(inp))
+    breakdown_unfused = measure_ops(ops.unfused(inp)) if hasattr(ops, "unfused") else []
 
     # end to end through the reference-facing API, host buffers, wall clock
     call, h2d_bytes, _pm = e2e_callable(args.workload, be, frames_np)
@@ -596,6 +612,8 @@ def run_gpu(args):
                 "pipeline_frac": pipe_achieved / peak,
                 "ops": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_per_rank * b / (m / 1e3) / 1e9,
                          "frac": px_per_rank * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown],
+                "ops_unfused": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_per_rank * b / (m / 1e3) / 1e9,
+                                 "frac": px_per_rank * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown_unfused],
             },
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d_bytes),
