@@ -20,6 +20,8 @@ for _ in range(3):
         y = be.clahe(x, 2.0, (8, 8))
     elif op == "otsu":
         y = be.otsu_threshold(x, 255)
+    elif op == "fused":
+        y = be.segment_fused(x, 11, 2, 5, 1)
     elif op == "ccl":
         m = be.morph_open_close(be.adaptive_threshold(x, 11, 2), 5, 1); y = be.ccl_label(m)
 be.synchronize()
