@@ -329,6 +329,55 @@ def test_ccl_structures(backend):
         assert_same(backend.to_host(labels), want, f"ccl structure {i}")
 
 
+def _snake(h, w):
+    """One long serpentine line: a single component whose union chain visits every tile."""
+    m = np.zeros((h, w), np.uint8)
+    m[::2, :] = 255
+    m[1::4, w - 1] = 255
+    m[3::4, 0] = 255
+    return m
+
+
+@pytest.mark.parametrize("case", ["blobs", "sparse", "dense", "snake", "vsnake", "hstripes", "vstripes", "checker", "full"])
+def test_ccl_multi_tile(backend, rng, case):
+    """Frames larger than one 32-row x 1024-px union-find tile: tile-local pass + border links + chained scans."""
+    for shape in ((70, 1100), (33, 2100), (200, 3000), (129, 1025)):
+        h, w = shape
+        if case == "blobs":
+            m = (blobs(rng, shape, U8) > 140).astype(np.uint8) * 255
+        elif case == "sparse":
+            m = _ccl_case(rng, shape, 0.08)
+        elif case == "dense":
+            m = _ccl_case(rng, shape, 0.55)        # > 4096 segments per tile: global-parent path
+        elif case == "snake":
+            m = _snake(h, w)
+        elif case == "vsnake":
+            m = np.ascontiguousarray(_snake(w, h).T)
+        elif case == "hstripes":
+            m = np.zeros(shape, np.uint8); m[::3, :] = 255; m[:, 1023:1026] = 255
+        elif case == "vstripes":
+            m = np.zeros(shape, np.uint8); m[:, ::3] = 255; m[31:33, :] = 255
+        elif case == "checker":
+            yy, xx = np.mgrid[0:h, 0:w]
+            m = (((yy // 16) + (xx // 16)) % 2 == 0).astype(np.uint8) * 255  # squares touching at corners (8-conn)
+        else:
+            m = np.full(shape, 255, np.uint8)
+        labels, counts = backend.ccl_label(dev(backend, m))
+        n_want, want = O.ccl_label(m)
+        assert int(host(backend, counts)[0]) == n_want, f"{case} {shape}"
+        assert_same(host(backend, labels), want, f"ccl multi-tile {case} {shape}")
+
+
+def test_ccl_stack_multi_tile(backend, rng):
+    m = np.stack([_ccl_case(rng, (40, 1300), d) for d in (0.1, 0.5, 0.0, 0.3, 1.0)])
+    labels, counts = backend.ccl_label(dev(backend, m))
+    got = host(backend, labels)
+    for i in range(m.shape[0]):
+        n_want, want = O.ccl_label(m[i])
+        assert int(host(backend, counts)[i]) == n_want
+        assert_same(got[i], want, f"ccl stack frame {i}")
+
+
 def test_ccl_stack(backend, rng):
     m = np.stack([_ccl_case(rng, (70, 96), d) for d in (0.2, 0.5, 0.0, 0.8)])
     labels, counts = backend.ccl_label(dev(backend, m))
@@ -369,9 +418,9 @@ def test_adaptive_bits_and_unpack(backend, rng, dt):
                 assert int((raw[:, -1] >> (shape[1] % 32)).max()) == 0
 
 
-@pytest.mark.parametrize("k,it", [(1, 1), (2, 1), (3, 1), (4, 2), (5, 1), (5, 3), (9, 2), (15, 3), (31, 2)])
+@pytest.mark.parametrize("k,it", [(1, 1), (2, 1), (3, 1), (3, 2), (3, 3), (4, 2), (5, 1), (7, 1), (5, 3), (9, 2), (15, 3), (31, 2)])
 def test_bits_morph(backend, rng, k, it):
-    for shape in ((64, 64), (33, 71), (130, 257), (70, 1200)):
+    for shape in ((64, 64), (33, 71), (130, 257), (70, 1200), (37, 2000)):
         m = ((rng.random(shape) < 0.55).astype(np.uint8)) * 255
         m[5:25, 3:60] = 255
         # pack through the adaptive-bits unpack round trip's inverse: build bits on the host

@@ -118,6 +118,133 @@ __global__ void __launch_bounds__(kThreads) bit_morph_chain_kernel(const uint32_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident fast path (odd k x k rectangles, summed radius <= 12 per side).
+// One WARP owns a column of 30 output words x TRR output rows: lane l holds word column
+// (30*warp_col - 1 + l) for every buffer row in registers (lanes 0 / 31 are the halo words).  The
+// horizontal pass takes its neighbour words by warp shuffle, the vertical pass is a compile-time
+// sliding window over the register column (doubling: windows of 2, 4, 8 rows combined with one
+// overlapping AND/OR), every stage of the chain stays in registers: no shared memory, no barriers.
+// The "wrongness travels <= summed radius" argument of the kernel above holds unchanged.
+template <bool DIL>
+__device__ __forceinline__ uint32_t bcomb(uint32_t a, uint32_t b) { return DIL ? (a | b) : (a & b); }
+
+template <bool DIL, int RAD, int BH>
+__device__ __forceinline__ void reg_stage(uint32_t (&v)[BH], uint32_t next_id, uint32_t vm_lane, int y_first, int h) {
+    uint32_t t[BH];
+#pragma unroll
+    for (int i = 0; i < BH; i++) {
+        const uint32_t cur = v[i];
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        const uint32_t next = __shfl_down_sync(0xffffffffu, cur, 1);
+        uint32_t acc = cur;
+#pragma unroll
+        for (int s = 1; s <= RAD; s++) {
+            acc = bcomb<DIL>(acc, __funnelshift_r(cur, next, s));  // pixel x + s
+            acc = bcomb<DIL>(acc, __funnelshift_l(prev, cur, s));  // pixel x - s
+        }
+        t[i] = acc;
+    }
+    constexpr int K = 2 * RAD + 1;
+    constexpr int P = K >= 8 ? 8 : (K >= 4 ? 4 : 2);
+    uint32_t wp[BH];
+#pragma unroll
+    for (int i = 0; i < BH; i++) wp[i] = t[i];
+#pragma unroll
+    for (int step = 1; step < P; step <<= 1) {
+#pragma unroll
+        for (int i = 0; i + step < BH; i++) wp[i] = bcomb<DIL>(wp[i], wp[i + step]);  // window 2*step starting at i
+    }
+#pragma unroll
+    for (int i = 0; i < BH; i++) {
+        uint32_t acc = t[i];
+        if (i >= RAD && i + RAD < BH) acc = bcomb<DIL>(wp[i - RAD], wp[i + RAD - P + 1]);
+        const uint32_t m = ((unsigned)(y_first + i) < (unsigned)h) ? vm_lane : 0u;
+        v[i] = (acc & m) | (next_id & ~m);
+    }
+}
+
+template <int OP, int A>
+struct RegChain {
+    static constexpr int HALO = OP == YAM_MORPH_OPEN_CLOSE ? 4 * A : (OP == YAM_MORPH_OPEN || OP == YAM_MORPH_CLOSE) ? 2 * A : A;
+};
+
+constexpr int kRegWarps = 4;  // warps per block (independent: no block-level cooperation)
+
+template <int OP, int A, int TRR>
+__global__ void __launch_bounds__(kRegWarps * 32) bit_morph_reg_kernel(const uint32_t* __restrict__ in,
+                                                                       uint32_t* __restrict__ out, int h, int w,
+                                                                       int wpr, int col_groups) {
+    constexpr int HALO = RegChain<OP, A>::HALO;
+    constexpr int BH = TRR + 2 * HALO;
+    constexpr uint32_t ONES = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int cgp = blockIdx.x * kRegWarps + (threadIdx.x >> 5);
+    if (cgp >= col_groups) return;  // surplus warp of the last block (warp-uniform exit)
+    const int band = blockIdx.y;
+    in += (int64_t)blockIdx.z * h * wpr;
+    out += (int64_t)blockIdx.z * h * wpr;
+    const int gj = cgp * 30 - 1 + lane;
+    const int y_first = band * TRR - HALO;
+    const uint32_t vm_lane = ((unsigned)gj < (unsigned)wpr) ? valid_mask(gj, w) : 0u;
+    constexpr bool first_dil = (OP == YAM_MORPH_DILATE || OP == YAM_MORPH_CLOSE);
+    const uint32_t id0 = first_dil ? 0u : ONES;
+    uint32_t v[BH];
+#pragma unroll
+    for (int i = 0; i < BH; i++) {
+        const int gy = y_first + i;
+        uint32_t x = 0u, m = 0u;
+        if ((unsigned)gy < (unsigned)h && vm_lane) {
+            x = __ldg(in + (int64_t)gy * wpr + gj);
+            m = vm_lane;
+        }
+        v[i] = (x & m) | (id0 & ~m);
+    }
+    if (OP == YAM_MORPH_ERODE) {
+        reg_stage<false, A, BH>(v, 0u, vm_lane, y_first, h);
+    } else if (OP == YAM_MORPH_DILATE) {
+        reg_stage<true, A, BH>(v, 0u, vm_lane, y_first, h);
+    } else if (OP == YAM_MORPH_OPEN) {
+        reg_stage<false, A, BH>(v, 0u, vm_lane, y_first, h);
+        reg_stage<true, A, BH>(v, 0u, vm_lane, y_first, h);
+    } else if (OP == YAM_MORPH_CLOSE) {
+        reg_stage<true, A, BH>(v, ONES, vm_lane, y_first, h);
+        reg_stage<false, A, BH>(v, 0u, vm_lane, y_first, h);
+    } else {  // open then close: erode A, dilate 2A, erode A
+        reg_stage<false, A, BH>(v, 0u, vm_lane, y_first, h);
+        reg_stage<true, 2 * A, BH>(v, ONES, vm_lane, y_first, h);
+        reg_stage<false, A, BH>(v, 0u, vm_lane, y_first, h);
+    }
+    if (lane >= 1 && lane <= 30 && gj < wpr) {
+#pragma unroll
+        for (int i = 0; i < TRR; i++) {
+            const int gy = band * TRR + i;
+            if (gy < h) out[(int64_t)gy * wpr + gj] = v[HALO + i] & vm_lane;
+        }
+    }
+}
+
+template <int OP, int A, int TRR>
+int launch_bit_reg(yam_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int64_t h, int64_t w) {
+    const int wpr = (int)((w + 31) / 32);
+    const int col_groups = (wpr + 29) / 30;
+    // grid.x blocks of kRegWarps warps cover the col_groups of one band; surplus warps exit
+    dim3 grid((unsigned)((col_groups + kRegWarps - 1) / kRegWarps), (unsigned)((h + TRR - 1) / TRR), (unsigned)n);
+    bit_morph_reg_kernel<OP, A, TRR><<<grid, kRegWarps * 32, 0, ctx->stream>>>(in, out, (int)h, (int)w, wpr, col_groups);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+template <int OP>
+int dispatch_bit_reg(yam_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int64_t h, int64_t w, int a) {
+    switch (a) {
+        case 1: return launch_bit_reg<OP, 1, 16>(ctx, in, out, n, h, w);
+        case 2: return launch_bit_reg<OP, 2, 16>(ctx, in, out, n, h, w);
+        case 3: return launch_bit_reg<OP, 3, 16>(ctx, in, out, n, h, w);
+    }
+    return -1;
+}
+
 // bits -> u8 mask {0, 255}: 32 pixels per thread
 __global__ void __launch_bounds__(kThreads) bits_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __restrict__ mask,
                                                                int64_t rows, int w, int wpr) {
@@ -217,6 +344,17 @@ int yam_bits_morph(yam_ctx* ctx, const uint32_t* bits_in, uint32_t* bits_out, in
     YAM_REQUIRE(ksize >= 1 && ksize <= 31 && iterations >= 1 && iterations <= 64, "bits_morph: bad kernel size / iterations");
     const int a = ksize / 2;
     const int L = a * iterations, R = (ksize - 1 - a) * iterations;
+    if ((ksize & 1) && L >= 1 && L <= 3 && h < (1 << 30)) {
+        // register-resident kernel (n iterations of a k x k rectangle = one window of radius n*(k/2))
+        switch (op) {
+            case YAM_MORPH_ERODE: return dispatch_bit_reg<YAM_MORPH_ERODE>(ctx, bits_in, bits_out, n, h, w, L);
+            case YAM_MORPH_DILATE: return dispatch_bit_reg<YAM_MORPH_DILATE>(ctx, bits_in, bits_out, n, h, w, L);
+            case YAM_MORPH_OPEN: return dispatch_bit_reg<YAM_MORPH_OPEN>(ctx, bits_in, bits_out, n, h, w, L);
+            case YAM_MORPH_CLOSE: return dispatch_bit_reg<YAM_MORPH_CLOSE>(ctx, bits_in, bits_out, n, h, w, L);
+            case YAM_MORPH_OPEN_CLOSE: return dispatch_bit_reg<YAM_MORPH_OPEN_CLOSE>(ctx, bits_in, bits_out, n, h, w, L);
+            default: break;
+        }
+    }
     BitStage st[4];
     int ns = 0;
     switch (op) {

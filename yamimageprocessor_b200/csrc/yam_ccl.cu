@@ -1,21 +1,26 @@
 // K10 connected-component labelling and K11 region properties.
 //
 // CCL (8-connectivity, raster-first canonical numbering) as a union-find over RUN SEGMENTS:
-//   pack      the u8 mask is packed to 1 bit/pixel; every maximal run of set bits inside one 32-pixel
-//             word is a node.  Nodes are numbered COMPACTLY in raster order (exclusive prefix sum of
-//             the per-word segment counts), so the parent array has one int per segment (~1-2 % of
-//             the pixels) and every union-find access stays in L2.
-//   union     one thread per word links each of its segments to the segment that continues it in
-//             the previous word and to every 8-connected segment in the row above (lock-free union
-//             by minimum index with atomicMin, path halving in find).
-//   flatten   parent[node] = root(node); roots are counted per word.
-//   rootlabel exclusive prefix of the root counts = rank of every root.  Linking by minimum index
-//             makes the root the segment holding the component's first pixel in raster order, so
-//             rank(root) + 1 IS the canonical label; it is stored negated in the root's slot.
+//   pack      (u8 masks only) the mask is packed to 1 bit/pixel; the fused path hands bits in directly.
+//   scan      every maximal run of set bits inside one 32-pixel word is a node.  Nodes are numbered
+//             COMPACTLY in raster order by a single-pass chained scan (decoupled look-back) of the
+//             per-word segment counts, so the parent array has one int per segment (~1-2 % of the
+//             pixels) and every union-find access stays in L2.
+//   tile      one CTA per 32-row x 32-word tile (32 x 1024 px): the tile's nodes get local ids, all
+//             links between words of the tile are resolved by a union-find that lives entirely in
+//             SHARED memory (atomicMin linking to the minimum index, path halving), and the flattened
+//             result is written as global parent pointers.  Tiles with more than kTileCap nodes
+//             (dense noise) run the same links on the global parent array instead.
+//   border    only the links that cross a tile edge (top rows and the two edge word-columns of every
+//             tile, ~3 % of the words) go through global atomics.
+//   rank      one pass over the nodes: walk to the root (read-only), store it, count roots and rank
+//             them with a chained scan.  Linking by minimum index makes the root the segment holding
+//             the component's first pixel in raster order, so rank(root) + 1 IS the canonical label;
+//             it is stored negated in the root's slot.
 //   final     one thread per word resolves its segments (at most two dependent loads) and the block
 //             writes the int32 labels through a swizzled shared-memory tile with 128-bit coalesced
 //             stores.
-// HBM traffic: 1 B/px mask read + 4 B/px label write + O(words) bookkeeping (12 B per 32 px).
+// HBM traffic: 1 B/px mask read (1/8 from bits) + 4 B/px label write + O(words) bookkeeping.
 //
 // Region properties: threads own an 8-pixel-wide column strip over a band of rows and keep the
 // current label's partial sums in registers; one set of 64-bit atomics per label change.
@@ -46,17 +51,6 @@ __device__ __forceinline__ int find_root(int* __restrict__ P, int x) {
     return x;
 }
 
-// read-only find for the flatten pass: there every slot is written by its owner only, so that
-// "parent == root" holds for all nodes afterwards (halving stores from other threads would race)
-__device__ __forceinline__ int find_root_ro(const int* __restrict__ P, int x) {
-    int p = __ldcg(P + x);
-    while (p != x) {
-        x = p;
-        p = __ldcg(P + x);
-    }
-    return x;
-}
-
 __device__ __forceinline__ void unite(int* __restrict__ P, int a, int b) {
     while (true) {
         a = find_root(P, a);
@@ -73,7 +67,35 @@ __device__ __forceinline__ void unite(int* __restrict__ P, int a, int b) {
     }
 }
 
+// the same union-find on a shared-memory parent array (tile-local node ids)
+__device__ __forceinline__ int s_find_root(volatile int* lp, int x) {
+    int p = lp[x];
+    while (p != x) {
+        const int gp = lp[p];
+        if (gp != p) lp[x] = gp;
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void s_unite(int* lp, int a, int b) {
+    while (true) {
+        a = s_find_root(lp, a);
+        b = s_find_root(lp, b);
+        if (a == b) return;
+        if (a > b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(lp + b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
 __device__ __forceinline__ uint32_t seg_starts(uint32_t b) { return b & ~(b << 1); }
+__device__ __forceinline__ int seg_count(uint32_t b) { return __popc(seg_starts(b)); }
 
 // start (bit index) of the run of ones in `wv` that contains bit `b` (bit b must be set)
 __device__ __forceinline__ int run_start(uint32_t wv, int b) {
@@ -87,20 +109,52 @@ __device__ __forceinline__ int seg_index(uint32_t wv, int b) {
     return __popc(seg_starts(wv) & ((1u << s) - 1u));
 }
 
-__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_tmp) {
-    v = yam_warp_sum(v);
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    if (threadIdx.x < 32) {
-        t = threadIdx.x < kThreads / 32 ? s_tmp[threadIdx.x] : 0u;
-        t = yam_warp_sum(t);
+// Links of one segment (start bit s, index k_self inside its word b) to the word on its left
+// (`left`, same row) and to the three words above it (`up` = column j-1, `u` = column j, `un` =
+// column j+1 of the previous row).  A neighbour that does not belong to the current pass is handed in
+// as 0.  link(kind, k_other):
+//   kind 0: last segment of `left`   kind 1: last segment of `up`
+//   kind 2: segment k_other of `u`   kind 3: first segment of `un`
+// A run of the row above that spans two of the words is linked through its first word only; the
+// horizontal link inside that row connects the rest.
+template <typename F>
+__device__ __forceinline__ void seg_links(uint32_t b, int s, uint32_t left, unsigned long long above, uint32_t u, F&& link) {
+    if (s == 0 && (left >> 31)) link(0, 0);
+    if (!above) return;
+    const uint32_t from_s = b >> s;
+    const int len = (~from_s) ? __ffs(~from_s) - 1 : 32 - s;
+    const int e = s + len - 1;
+    // 8-connectivity: columns s-1 .. e+1 of the row above = bits s .. e+2 of `above`
+    unsigned long long m = above & (((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull));
+    while (m) {
+        const int k0 = __ffsll((long long)m) - 1;
+        m &= m + (1ull << k0);  // clear the lowest run of ones
+        if (k0 == 0) link(1, 0);
+        else if (k0 == 33) link(3, 0);
+        else link(2, seg_index(u, k0 - 1));
     }
-    return t;  // valid in warp 0
+}
+__device__ __forceinline__ unsigned long long above_window(uint32_t up, uint32_t u, uint32_t un) {
+    return (unsigned long long)(up >> 31) | ((unsigned long long)u << 1) | ((unsigned long long)(un & 1u) << 33);
+}
+// all segments of a word: link(kind, k_self, k_other)
+template <typename F>
+__device__ __forceinline__ void word_links(uint32_t b, uint32_t left, uint32_t up, uint32_t u, uint32_t un, F&& link) {
+    const unsigned long long above = above_window(up, u, un);
+    uint32_t starts = seg_starts(b);
+    int k = 0;
+    while (starts) {
+        const int s = __ffs(starts) - 1;
+        starts &= starts - 1;
+        seg_links(b, s, left, above, u, [&](int kind, int ko) { link(kind, k, ko); });
+        k++;
+    }
 }
 
-// exclusive prefix of v within the block (kThreads threads); returns the prefix for this thread
-__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_tmp) {
+// exclusive prefix of v within a block of NT threads; *total (optional, shared) = block sum.
+// Ends with the data in s_tmp still live: callers separate two scans with __syncthreads().
+template <int NT = kThreads>
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_tmp, uint32_t* total = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -110,322 +164,641 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_
     }
     if (lane == 31) s_tmp[warp] = incl;
     __syncthreads();
-    uint32_t off = 0;
+    uint32_t off = 0, all = 0;
 #pragma unroll
-    for (int i = 0; i < kThreads / 32; i++)
-        if (i < warp) off += s_tmp[i];
+    for (int i = 0; i < NT / 32; i++) {
+        const uint32_t t = s_tmp[i];
+        if (i < warp) off += t;
+        all += t;
+    }
+    if (total && threadIdx.x == 0) *total = all;
     return off + incl - v;
 }
 
-// In-place exclusive scan of data[0..n) by ONE block (all kThreads threads); total -> *total_out.
-__device__ void block_scan_array(uint32_t* __restrict__ data, int64_t n, uint32_t* __restrict__ total_out,
-                                 uint32_t* s_tmp, uint32_t* s_carry) {
-    if (threadIdx.x == 0) *s_carry = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += kThreads * 4) {
-        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? __ldcg(data + i0 + k) : 0u;
-        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
-        uint32_t run = *s_carry + block_excl_scan_u32(mine, s_tmp);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (i0 + k < n) data[i0 + k] = run;
-            run += v[k];
+// ---- ordered chunk prefixes ---------------------------------------------------------------------------
+// The scans below run at most one chunk per SM, claimed in ticket order.  A chunk publishes its
+// aggregate in a 64-bit status word (bit 63 = valid, low 32 = value) and obtains its exclusive prefix
+// by summing the aggregates of ALL earlier chunks (<= num_sms values, one warp-parallel wait).  Every
+// earlier ticket is held by a block that is already running, so the wait cannot deadlock.
+constexpr unsigned long long kFlagValid = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by every thread of the block (contains __syncthreads); `aggregate` is read from thread 0.
+__device__ uint32_t ordered_exclusive(unsigned long long* status, int chunk, uint32_t aggregate, uint32_t* s_prefix) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0) st_status(status + chunk, kFlagValid | aggregate);
+        uint32_t excl = 0;
+        for (int idx = lane; idx < chunk; idx += 32) {
+            unsigned long long st = ld_status(status + idx);
+            while (!(st & kFlagValid)) st = ld_status(status + idx);
+            excl += (uint32_t)st;
         }
-        __syncthreads();
-        if (threadIdx.x == kThreads - 1) *s_carry = run;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total_out = *s_carry;
-}
-
-// "last block done" election: returns true in every thread of the block that finishes last.
-// `counter` must be 0 on entry and is reset to 0 by the elected block.
-__device__ bool last_block_done(unsigned int* counter, unsigned int nblocks, int* s_flag) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(counter, 1u);
-        *s_flag = (ticket == nblocks - 1);
-        if (*s_flag) *counter = 0;
+        excl = yam_warp_sum(excl);
+        if (lane == 0) *s_prefix = excl;
     }
     __syncthreads();
-    if (*s_flag) __threadfence();
-    return *s_flag != 0;
+    return *s_prefix;
 }
 
-// ---- 1. pack: bits + per-block segment counts; the last block scans the counts ------------------
+// ---- 0. pack a u8 mask to bits (the fused path skips this) --------------------------------------
 __global__ void __launch_bounds__(kThreads) ccl_pack_kernel(const uint8_t* __restrict__ mask, CclGeom g,
-                                                            uint32_t* __restrict__ bits,
-                                                            uint32_t* __restrict__ block_counts,
-                                                            uint32_t* __restrict__ total_nodes,
-                                                            unsigned int* __restrict__ counter) {
-    __shared__ uint32_t s_tmp[kThreads / 32];
-    __shared__ uint32_t s_carry;
-    __shared__ int s_flag;
+                                                            uint32_t* __restrict__ bits) {
     const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw >= g.total_words) return;
+    const int64_t row_id = gw / g.wpr;  // frame * h + y
+    const int j = (int)(gw - row_id * g.wpr);
+    const uint8_t* row = mask + row_id * (int64_t)g.w;
+    const int x0 = j * 32;
     uint32_t b = 0;
-    if (gw < g.total_words) {
-        const int64_t row_id = gw / g.wpr;  // frame * h + y
-        const int j = (int)(gw - row_id * g.wpr);
-        const uint8_t* row = mask + row_id * (int64_t)g.w;
-        const int x0 = j * 32;
-        if (x0 + 32 <= g.w && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
-            const uint4 q0 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0));
-            const uint4 q1 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0) + 1);
-            const uint32_t wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    if (x0 + 32 <= g.w && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
+        const uint4 q0 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0));
+        const uint4 q1 = yam_ld_stream(reinterpret_cast<const uint4*>(row + x0) + 1);
+        const uint32_t wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t v = wd[i];
-                b |= ((v & 0xffu) ? 1u : 0u) << (4 * i);
-                b |= ((v & 0xff00u) ? 1u : 0u) << (4 * i + 1);
-                b |= ((v & 0xff0000u) ? 1u : 0u) << (4 * i + 2);
-                b |= ((v & 0xff000000u) ? 1u : 0u) << (4 * i + 3);
-            }
-        } else {
-            for (int i = 0; i < 32 && x0 + i < g.w; i++) b |= (row[x0 + i] ? 1u : 0u) << i;
+        for (int i = 0; i < 8; i++) {
+            const uint32_t v = wd[i];
+            b |= ((v & 0xffu) ? 1u : 0u) << (4 * i);
+            b |= ((v & 0xff00u) ? 1u : 0u) << (4 * i + 1);
+            b |= ((v & 0xff0000u) ? 1u : 0u) << (4 * i + 2);
+            b |= ((v & 0xff000000u) ? 1u : 0u) << (4 * i + 3);
         }
-        bits[gw] = b;
+    } else {
+        for (int i = 0; i < 32 && x0 + i < g.w; i++) b |= (row[x0 + i] ? 1u : 0u) << i;
     }
-    const uint32_t total = block_sum_u32(__popc(seg_starts(b)), s_tmp);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-    if (last_block_done(counter, gridDim.x, &s_flag))
-        block_scan_array(block_counts, gridDim.x, total_nodes, s_tmp, &s_carry);
+    bits[gw] = b;
 }
 
-// ---- 1b. the same bookkeeping when the mask already is bit-packed (fused segmentation path) --------
-__global__ void __launch_bounds__(kThreads) ccl_count_kernel(const uint32_t* __restrict__ bits, CclGeom g,
-                                                             uint32_t* __restrict__ block_counts,
-                                                             uint32_t* __restrict__ total_nodes,
-                                                             unsigned int* __restrict__ counter) {
-    __shared__ uint32_t s_tmp[kThreads / 32];
-    __shared__ uint32_t s_carry;
-    __shared__ int s_flag;
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gw < g.total_words ? bits[gw] : 0u;
-    const uint32_t total = block_sum_u32(__popc(seg_starts(b)), s_tmp);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-    if (last_block_done(counter, gridDim.x, &s_flag))
-        block_scan_array(block_counts, gridDim.x, total_nodes, s_tmp, &s_carry);
+// ---- 1. scan: nbase[word] = number of segments in all earlier words -------------------------------
+constexpr int kBigThreads = 1024;
+constexpr int kScanWords = 16;                           // words per thread and sub-chunk
+constexpr int kScanSub = kBigThreads * kScanWords;       // words per sub-chunk
+
+// segment counts of kScanWords consecutive words, packed 8 bits each (a word has at most 16 segments)
+__device__ __forceinline__ void load_seg_counts(const uint32_t* __restrict__ bits, int64_t w0, int64_t end, bool aligned,
+                                                uint32_t (&c)[kScanWords / 4]) {
+    if (aligned && w0 + kScanWords <= end) {
+        uint4 q[kScanWords / 4];
+#pragma unroll
+        for (int v = 0; v < kScanWords / 4; v++) q[v] = __ldcg(reinterpret_cast<const uint4*>(bits + w0) + v);
+#pragma unroll
+        for (int v = 0; v < kScanWords / 4; v++)
+            c[v] = seg_count(q[v].x) | (seg_count(q[v].y) << 8) | (seg_count(q[v].z) << 16) | (seg_count(q[v].w) << 24);
+    } else {
+#pragma unroll
+        for (int v = 0; v < kScanWords / 4; v++) {
+            c[v] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (w0 + 4 * v + i < end) c[v] |= (uint32_t)seg_count(__ldcg(bits + w0 + 4 * v + i)) << (8 * i);
+        }
+    }
+}
+__device__ __forceinline__ uint32_t packed_sum(const uint32_t (&c)[kScanWords / 4]) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int v = 0; v < kScanWords / 4; v++) t += c[v];   // byte lanes: 4 x 16 <= 64 each, no carry
+    return (t & 0xffu) + ((t >> 8) & 0xffu) + ((t >> 16) & 0xffu) + (t >> 24);
 }
 
-// ---- 2. node base per word; parent init; node -> (word, start bit) ----------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_nodebase_kernel(const uint32_t* __restrict__ bits, CclGeom g,
-                                                                const uint32_t* __restrict__ block_offsets,
-                                                                uint32_t* __restrict__ nbase, int* __restrict__ P,
-                                                                uint32_t* __restrict__ node_info) {
+// grid = chunks (<= num_sms); chunk c owns words [c * per, (c + 1) * per), per a multiple of kScanSub
+__global__ void __launch_bounds__(kBigThreads) ccl_scan_kernel(const uint32_t* __restrict__ bits, int64_t total_words,
+                                                               int64_t per, uint32_t* __restrict__ nbase,
+                                                               unsigned long long* __restrict__ status,
+                                                               unsigned int* __restrict__ ticket,
+                                                               uint32_t* __restrict__ total_nodes) {
+    __shared__ uint32_t s_tmp[kBigThreads / 32];
+    __shared__ uint32_t s_prefix, s_total;
+    __shared__ int s_chunk;
+    if (threadIdx.x == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int chunk = s_chunk;
+    const int64_t begin = (int64_t)chunk * per;
+    const int64_t end = begin + per < total_words ? begin + per : total_words;
+    const bool aligned = (reinterpret_cast<uintptr_t>(bits) & 15) == 0;
+    // pass 1: segments in this chunk (the first sub-chunk's counts stay in registers for pass 2)
+    uint32_t c0[kScanWords / 4], c[kScanWords / 4];
+    load_seg_counts(bits, begin + (int64_t)threadIdx.x * kScanWords, end, aligned, c0);
+    uint32_t mine = packed_sum(c0);
+    for (int64_t sub = begin + kScanSub; sub < end; sub += kScanSub) {
+        load_seg_counts(bits, sub + (int64_t)threadIdx.x * kScanWords, end, aligned, c);
+        mine += packed_sum(c);
+    }
+    block_excl_scan_u32<kBigThreads>(mine, s_tmp, &s_total);
+    __syncthreads();
+    const uint32_t agg = s_total;
+    uint32_t carry = ordered_exclusive(status, chunk, agg, &s_prefix);
+    if (threadIdx.x == 0 && end >= total_words) *total_nodes = carry + agg;
+    // pass 2: prefixes (later sub-chunks re-read their bits from L2)
+    for (int64_t sub = begin; sub < end; sub += kScanSub) {
+        const int64_t w0 = sub + (int64_t)threadIdx.x * kScanWords;
+        if (sub == begin) {
+#pragma unroll
+            for (int v = 0; v < kScanWords / 4; v++) c[v] = c0[v];
+        } else {
+            load_seg_counts(bits, w0, end, aligned, c);
+        }
+        __syncthreads();
+        uint32_t run = carry + block_excl_scan_u32<kBigThreads>(packed_sum(c), s_tmp, &s_total);
+        uint32_t o[kScanWords];
+#pragma unroll
+        for (int i = 0; i < kScanWords; i++) {
+            o[i] = run;
+            run += (c[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        }
+        if (w0 + kScanWords <= end) {
+#pragma unroll
+            for (int v = 0; v < kScanWords / 4; v++)
+                reinterpret_cast<uint4*>(nbase + w0)[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kScanWords; i++)
+                if (w0 + i < end) nbase[w0 + i] = o[i];
+        }
+        __syncthreads();
+        carry += s_total;
+    }
+}
+
+// ---- 2. tile-local union-find ------------------------------------------------------------------------
+constexpr int kTileR = 32;     // rows per tile
+constexpr int kTileC = 32;     // words per tile row (1024 px)
+constexpr int kTileWords = kTileR * kTileC;
+constexpr int kTileCap = 2048; // nodes a tile can hold in shared memory (2 per word; denser tiles use global parents)
+constexpr int kTilePer = kTileWords / kThreads;  // consecutive words per thread (same tile row)
+static_assert(kTileC % kTilePer == 0, "a thread's words must share a tile row");
+
+struct TileSmem {
+    uint32_t bits[kTileWords];
+    uint32_t lbase[kTileWords];   // tile-local id of the word's first segment
+    uint32_t gbase[kTileWords];   // global id of the word's first segment
+    int lp[kTileCap];             // local parents
+    uint32_t info[kTileCap];      // local node -> (word index in tile << 5) | start bit
+};
+
+__global__ void __launch_bounds__(kThreads) ccl_tile_kernel(const uint32_t* __restrict__ bits,
+                                                            const uint32_t* __restrict__ nbase, CclGeom g,
+                                                            int tiles_x, int tiles_y, int* __restrict__ P) {
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(tile_smem_raw);
     __shared__ uint32_t s_tmp[kThreads / 32];
-    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gw < g.total_words ? bits[gw] : 0u;
-    uint32_t starts = seg_starts(b);
-    const uint32_t base = block_offsets[blockIdx.x] + block_excl_scan_u32(__popc(starts), s_tmp);
-    if (gw < g.total_words) {
-        nbase[gw] = base;
-        uint32_t k = 0;
+    __shared__ uint32_t s_total;
+    const int tx = blockIdx.x % tiles_x;
+    const int ty = (blockIdx.x / tiles_x) % tiles_y;
+    const int frame = blockIdx.x / (tiles_x * tiles_y);
+    const int j0 = tx * kTileC, y0 = ty * kTileR;
+    const int64_t fbase = (int64_t)frame * g.words_per_frame;
+    for (int i = threadIdx.x; i < kTileWords; i += kThreads) {
+        const int r = i / kTileC, c = i - r * kTileC;
+        uint32_t b = 0, nb = 0;
+        if (y0 + r < g.h && j0 + c < g.wpr) {
+            const int64_t gw = fbase + (int64_t)(y0 + r) * g.wpr + j0 + c;
+            b = __ldg(bits + gw);
+            nb = __ldg(nbase + gw);
+        }
+        S.bits[i] = b;
+        S.gbase[i] = nb;
+    }
+    __syncthreads();
+    const int i0 = threadIdx.x * kTilePer;
+    uint32_t wb[kTilePer];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < kTilePer; q++) {
+        wb[q] = S.bits[i0 + q];
+        mine += seg_count(wb[q]);
+    }
+    uint32_t lb = block_excl_scan_u32(mine, s_tmp, &s_total);
+#pragma unroll
+    for (int q = 0; q < kTilePer; q++) {
+        S.lbase[i0 + q] = lb;
+        lb += seg_count(wb[q]);
+    }
+    __syncthreads();
+    const int nl = (int)s_total;
+    if (nl == 0) return;
+    if (nl > kTileCap) {
+        // dense tile: the same links, word-parallel, on the global parent array
+#pragma unroll
+        for (int q = 0; q < kTilePer; q++) {
+            const int n = seg_count(wb[q]);
+            const uint32_t gb = S.gbase[i0 + q];
+            for (int k = 0; k < n; k++) P[gb + k] = (int)(gb + k);
+        }
+        __syncthreads();
+        const int r = i0 / kTileC;
+#pragma unroll
+        for (int q = 0; q < kTilePer; q++) {
+            const uint32_t b = wb[q];
+            if (!b) continue;
+            const int i = i0 + q, c = i - r * kTileC;
+            const uint32_t left = c > 0 ? S.bits[i - 1] : 0u;
+            uint32_t up = 0, u = 0, un = 0;
+            if (r > 0) {
+                up = c > 0 ? S.bits[i - kTileC - 1] : 0u;
+                u = S.bits[i - kTileC];
+                un = c + 1 < kTileC ? S.bits[i - kTileC + 1] : 0u;
+            }
+            const int self = (int)S.gbase[i];
+            word_links(b, left, up, u, un, [&](int kind, int ks, int ko) {
+                int other;
+                if (kind == 0) other = (int)S.gbase[i - 1] + seg_count(left) - 1;
+                else if (kind == 1) other = (int)S.gbase[i - kTileC - 1] + seg_count(up) - 1;
+                else if (kind == 2) other = (int)S.gbase[i - kTileC] + ko;
+                else other = (int)S.gbase[i - kTileC + 1];
+                unite(P, self + ks, other);
+            });
+        }
+        return;
+    }
+    // parents = identity, node -> (word, start bit)
+#pragma unroll
+    for (int q = 0; q < kTilePer; q++) {
+        uint32_t starts = seg_starts(wb[q]);
+        uint32_t l = S.lbase[i0 + q];
         while (starts) {
             const int sbit = __ffs(starts) - 1;
             starts &= starts - 1;
-            P[base + k] = (int)(base + k);
-            node_info[base + k] = ((uint32_t)gw << 5) | (uint32_t)sbit;
-            k++;
+            S.lp[l] = (int)l;
+            S.info[l] = ((uint32_t)(i0 + q) << 5) | (uint32_t)sbit;
+            l++;
         }
     }
-}
-
-// ---- 3. union: one thread per segment ----------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_union_kernel(const uint32_t* __restrict__ bits,
-                                                             const uint32_t* __restrict__ nbase,
-                                                             const uint32_t* __restrict__ node_info, CclGeom g,
-                                                             const uint32_t* __restrict__ total_nodes,
-                                                             int* __restrict__ P) {
-    const int total = (int)*total_nodes;
-    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < total; node += gridDim.x * blockDim.x) {
-        const uint32_t info = node_info[node];
-        const int64_t gw = info >> 5;
-        const int s = (int)(info & 31u);
-        const uint32_t b = bits[gw];
-        const int64_t row_id = gw / g.wpr;
-        const int j = (int)(gw - row_id * g.wpr);
-        const int y = (int)(row_id % g.h);
-        // horizontal: a segment at bit 0 continues the segment that ends at bit 31 of the previous word
-        if (s == 0 && j > 0) {
-            const uint32_t pv = bits[gw - 1];
-            if (pv >> 31) unite(P, node, (int)nbase[gw - 1] + seg_index(pv, 31));
+    __syncthreads();
+    // links between words of this tile: one thread per NODE (all lanes busy)
+    for (int l = threadIdx.x; l < nl; l += kThreads) {
+        const uint32_t info = S.info[l];
+        const int i = (int)(info >> 5), sbit = (int)(info & 31u);
+        const int r = i / kTileC, c = i - r * kTileC;
+        const uint32_t b = S.bits[i];
+        const uint32_t left = (sbit == 0 && c > 0) ? S.bits[i - 1] : 0u;
+        uint32_t up = 0, u = 0, un = 0;
+        if (r > 0) {
+            up = c > 0 ? S.bits[i - kTileC - 1] : 0u;
+            u = S.bits[i - kTileC];
+            un = c + 1 < kTileC ? S.bits[i - kTileC + 1] : 0u;
         }
-        if (y == 0) continue;
-        // vertical: 34-column window of the row above; bit k of `above` <-> column 32*j + k - 1
-        const uint32_t u = bits[gw - g.wpr];
-        const uint32_t up = j > 0 ? bits[gw - g.wpr - 1] : 0u;
-        const uint32_t un = j + 1 < g.wpr ? bits[gw - g.wpr + 1] : 0u;
-        const unsigned long long above =
-            (unsigned long long)(up >> 31) | ((unsigned long long)u << 1) | ((unsigned long long)(un & 1u) << 33);
-        const uint32_t from_s = b >> s;
-        const int len = (~from_s) ? __ffs(~from_s) - 1 : 32 - s;
-        const int e = s + len - 1;
-        const unsigned long long wmask = ((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull);  // bits s .. e+2
-        unsigned long long m = above & wmask;
-        if (!m) continue;
-        const int base_u = u ? (int)nbase[gw - g.wpr] : 0;
-        while (m) {
-            const int k0 = __ffsll((long long)m) - 1;
-            m &= m + (1ull << k0);  // clear the lowest run of ones
+        seg_links(b, sbit, left, above_window(up, u, un), u, [&](int kind, int ko) {
             int other;
-            if (k0 == 0) {
-                other = (int)nbase[gw - g.wpr - 1] + seg_index(up, 31);
-            } else if (k0 == 33) {
-                other = (int)nbase[gw - g.wpr + 1];  // bit 0 of the next word starts its first segment
-            } else {
-                other = base_u + seg_index(u, k0 - 1);
-            }
-            unite(P, node, other);
+            if (kind == 0) other = (int)S.lbase[i - 1] + seg_count(left) - 1;
+            else if (kind == 1) other = (int)S.lbase[i - kTileC - 1] + seg_count(up) - 1;
+            else if (kind == 2) other = (int)S.lbase[i - kTileC] + ko;
+            else other = (int)S.lbase[i - kTileC + 1];
+            s_unite(S.lp, l, other);
+        });
+    }
+    __syncthreads();
+    // flattened local forest -> global parents
+    for (int l = threadIdx.x; l < nl; l += kThreads) {
+        int x = l, p = S.lp[x];
+        while (p != x) {
+            x = p;
+            p = S.lp[x];
         }
+        const int wi = (int)(S.info[l] >> 5), wr = (int)(S.info[x] >> 5);
+        const uint32_t gid = S.gbase[wi] + ((uint32_t)l - S.lbase[wi]);
+        const uint32_t gr = S.gbase[wr] + ((uint32_t)x - S.lbase[wr]);
+        P[gid] = (int)gr;
     }
 }
 
-// ---- 4. flatten (one thread per node) + root counts per 256-node chunk; last block scans them ---------
-__global__ void __launch_bounds__(kThreads) ccl_flatten_kernel(const uint32_t* __restrict__ total_nodes,
-                                                               int* __restrict__ P,
-                                                               uint32_t* __restrict__ chunk_roots,
-                                                               uint32_t* __restrict__ total_roots,
-                                                               unsigned int* __restrict__ counter) {
-    __shared__ uint32_t s_tmp[kThreads / 32];
-    __shared__ uint32_t s_carry;
-    __shared__ int s_flag;
-    const int total = (int)*total_nodes;
-    const int chunks = (total + kThreads - 1) / kThreads;
-    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
-        const int node = c * kThreads + threadIdx.x;
-        uint32_t is_root = 0;
+// ---- 3. links that cross a tile edge --------------------------------------------------------------------
+// thread space: [0, na) top rows of the tile bands (all links to the row above + the left link at
+// tile column 0); [na, na + nb) the two edge word-columns of every tile in the other rows.
+__global__ void __launch_bounds__(kThreads) ccl_border_kernel(const uint32_t* __restrict__ bits,
+                                                              const uint32_t* __restrict__ nbase, CclGeom g,
+                                                              int tiles_x, int tiles_y, int64_t na, int64_t nb,
+                                                              int* __restrict__ P) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= na + nb) return;
+    int y, j, frame;
+    bool top, left_edge;
+    if (t < na) {
+        const int64_t band = t / g.wpr;  // frame * tiles_y + ty
+        j = (int)(t - band * g.wpr);
+        frame = (int)(band / tiles_y);
+        y = (int)(band - (int64_t)frame * tiles_y) * kTileR;
+        top = true;
+        left_edge = (j % kTileC) == 0;
+    } else {
+        const int64_t u = t - na;
+        const int side = (int)(u & 1);
+        const int64_t v = u >> 1;
+        const int txi = (int)(v % tiles_x);
+        const int64_t row_id = v / tiles_x;  // frame * h + y
+        frame = (int)(row_id / g.h);
+        y = (int)(row_id - (int64_t)frame * g.h);
+        if ((y % kTileR) == 0) return;  // top rows are handled above
+        j = txi * kTileC + (side ? kTileC - 1 : 0);
+        if (j >= g.wpr) return;
+        top = false;
+        left_edge = side == 0;
+    }
+    const int64_t gw = (int64_t)frame * g.words_per_frame + (int64_t)y * g.wpr + j;
+    const uint32_t b = __ldg(bits + gw);
+    if (!b) return;
+    const bool right_edge = (j % kTileC) == kTileC - 1;
+    uint32_t left = 0, up = 0, u = 0, un = 0;
+    if (left_edge && j > 0) left = __ldg(bits + gw - 1);
+    if (y > 0) {
+        if ((top || left_edge) && j > 0) up = __ldg(bits + gw - g.wpr - 1);
+        if (top) u = __ldg(bits + gw - g.wpr);
+        if ((top || right_edge) && j + 1 < g.wpr) un = __ldg(bits + gw - g.wpr + 1);
+    }
+    if (!((b & 1u) && (left >> 31)) && !(up >> 31) && !u && !(un & 1u)) return;
+    const int self = (int)__ldg(nbase + gw);
+    word_links(b, left, up, u, un, [&](int kind, int ks, int ko) {
+        int other;
+        if (kind == 0) other = (int)__ldg(nbase + gw - 1) + seg_count(left) - 1;
+        else if (kind == 1) other = (int)__ldg(nbase + gw - g.wpr - 1) + seg_count(up) - 1;
+        else if (kind == 2) other = (int)__ldg(nbase + gw - g.wpr) + ko;
+        else other = (int)__ldg(nbase + gw - g.wpr + 1);
+        unite(P, self + ks, other);
+    });
+}
+
+// ---- 4. flatten + rank: P[node] = root, P[root] = -(rank + 1) ---------------------------------------------
+constexpr int kRankPer = 8;
+constexpr int kRankSub = kBigThreads * kRankPer;   // nodes per sub-chunk
+
+// walk kRankPer consecutive nodes to their roots (read-only), store the roots; returns the root bitmask
+__device__ __forceinline__ uint32_t flatten_nodes(int* __restrict__ P, int n0, int total) {
+    int par[kRankPer];
+    if (n0 + kRankPer <= total) {
+#pragma unroll
+        for (int v = 0; v < kRankPer / 4; v++) {
+            const int4 q = __ldcg(reinterpret_cast<const int4*>(P + n0) + v);
+            par[4 * v] = q.x; par[4 * v + 1] = q.y; par[4 * v + 2] = q.z; par[4 * v + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRankPer; i++) par[i] = n0 + i < total ? __ldcg(P + n0 + i) : -1;
+    }
+    // first hop of all nodes at once (after the tile pass most nodes point at a root already);
+    // a negative parent marks a root that already holds its rank
+    int gp[kRankPer];
+#pragma unroll
+    for (int i = 0; i < kRankPer; i++) {
+        const int node = n0 + i;
+        gp[i] = (node < total && par[i] != node) ? __ldcg(P + par[i]) : -1;
+    }
+    uint32_t roots = 0;
+#pragma unroll
+    for (int i = 0; i < kRankPer; i++) {
+        const int node = n0 + i;
         if (node < total) {
-            const int r = find_root_ro(P, node);
-            if (r == node) is_root = 1;
-            else P[node] = r;
+            if (par[i] == node) {
+                roots |= 1u << i;
+            } else {
+                int x = par[i], p = gp[i];
+                while (p >= 0 && p != x) {
+                    x = p;
+                    p = __ldcg(P + x);
+                }
+                if (par[i] != x) P[node] = x;
+            }
         }
-        const uint32_t t = block_sum_u32(is_root, s_tmp);
-        if (threadIdx.x == 0) chunk_roots[c] = t;
-        __syncthreads();
     }
-    if (last_block_done(counter, gridDim.x, &s_flag))
-        block_scan_array(chunk_roots, chunks, total_roots, s_tmp, &s_carry);
+    return roots;
 }
 
-// ---- 5. root labels: P[root] = -(rank + 1) ---------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) ccl_rootlabel_kernel(const uint32_t* __restrict__ total_nodes,
-                                                                 const uint32_t* __restrict__ chunk_offsets,
-                                                                 int* __restrict__ P) {
-    __shared__ uint32_t s_tmp[kThreads / 32];
+// grid <= num_sms; chunks = min(grid, ceil(total / kRankSub)), each a whole number of sub-chunks
+__global__ void __launch_bounds__(kBigThreads) ccl_rank_kernel(const uint32_t* __restrict__ total_nodes,
+                                                               int* __restrict__ P,
+                                                               unsigned long long* __restrict__ status,
+                                                               unsigned int* __restrict__ ticket,
+                                                               uint32_t* __restrict__ sub_excl,
+                                                               uint32_t* __restrict__ total_roots,
+                                                               int32_t* __restrict__ counts_single) {
+    __shared__ uint32_t s_tmp[kBigThreads / 32];
+    __shared__ uint32_t s_prefix, s_total;
+    __shared__ int s_chunk;
     const int total = (int)*total_nodes;
-    const int chunks = (total + kThreads - 1) / kThreads;
-    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
-        const int node = c * kThreads + threadIdx.x;
-        const uint32_t is_root = (node < total && __ldcg(P + node) == node) ? 1u : 0u;
-        const uint32_t rank = chunk_offsets[c] + block_excl_scan_u32(is_root, s_tmp);
-        if (is_root) P[node] = -(int)(rank + 1);
+    const int subs = (total + kRankSub - 1) / kRankSub;
+    if (subs == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *total_roots = 0;
+            if (counts_single) *counts_single = 0;
+        }
+        return;
+    }
+    const int chunks = subs < (int)gridDim.x ? subs : (int)gridDim.x;
+    const int subs_per = (subs + chunks - 1) / chunks;
+    if (threadIdx.x == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int chunk = s_chunk;
+    const int sub_begin = chunk * subs_per;
+    if (chunk >= chunks || sub_begin >= subs) {
+        // nothing to rank here, but later chunks still sum over this ticket's status word
+        if (chunk < (int)gridDim.x && threadIdx.x == 0) st_status(status + chunk, kFlagValid);
+        return;
+    }
+    const int sub_end = sub_begin + subs_per < subs ? sub_begin + subs_per : subs;
+    // pass 1: flatten, count roots (the first sub-chunk's root mask stays in a register for pass 2)
+    const uint32_t roots0 = flatten_nodes(P, sub_begin * kRankSub + threadIdx.x * kRankPer, total);
+    uint32_t mine = __popc(roots0);
+    for (int sub = sub_begin + 1; sub < sub_end; sub++)
+        mine += __popc(flatten_nodes(P, sub * kRankSub + threadIdx.x * kRankPer, total));
+    block_excl_scan_u32<kBigThreads>(mine, s_tmp, &s_total);
+    __syncthreads();
+    const uint32_t agg = s_total;
+    uint32_t carry = ordered_exclusive(status, chunk, agg, &s_prefix);
+    if (threadIdx.x == 0 && sub_end >= subs) {
+        *total_roots = carry + agg;
+        if (counts_single) *counts_single = (int32_t)(carry + agg);
+    }
+    // pass 2: rank the roots (a root's slot still holds its own index)
+    for (int sub = sub_begin; sub < sub_end; sub++) {
+        const int n0 = sub * kRankSub + threadIdx.x * kRankPer;
+        uint32_t roots = roots0;
+        if (sub != sub_begin) {
+            roots = 0;
+#pragma unroll
+            for (int i = 0; i < kRankPer; i++)
+                if (n0 + i < total && __ldcg(P + n0 + i) == n0 + i) roots |= 1u << i;
+        }
         __syncthreads();
+        uint32_t rank = carry + block_excl_scan_u32<kBigThreads>(__popc(roots), s_tmp, &s_total);
+        if (threadIdx.x == 0) sub_excl[sub] = carry;
+#pragma unroll
+        for (int i = 0; i < kRankPer; i++) {
+            if ((roots >> i) & 1u) {
+                P[n0 + i] = -(int)(rank + 1);
+                rank++;
+            }
+        }
+        __syncthreads();
+        carry += s_total;
     }
 }
 
-// ---- 6. per-frame root offsets and component counts (one thread per frame) ---------------------------------
-__global__ void ccl_frame_offsets_kernel(const uint32_t* __restrict__ nbase, CclGeom g,
-                                         const uint32_t* __restrict__ total_nodes,
-                                         const uint32_t* __restrict__ total_roots,
-                                         const uint32_t* __restrict__ chunk_offsets, const int* __restrict__ P,
-                                         uint32_t* __restrict__ frame_off, int32_t* __restrict__ counts) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- 5. per-frame root offsets and component counts (one warp per frame; stacks only) ---------------------
+__global__ void __launch_bounds__(kThreads) ccl_frame_offsets_kernel(const uint32_t* __restrict__ nbase, CclGeom g,
+                                                                     const uint32_t* __restrict__ total_nodes,
+                                                                     const uint32_t* __restrict__ total_roots,
+                                                                     const uint32_t* __restrict__ chunk_excl,  // per rank sub-chunk
+                                                                     const int* __restrict__ P,
+                                                                     uint32_t* __restrict__ frame_off,
+                                                                     int32_t* __restrict__ counts) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (f >= g.frames) return;
     auto roots_before_frame = [&](int frame) -> uint32_t {
         if (frame >= g.frames) return *total_roots;
         const uint32_t n0 = nbase[(int64_t)frame * g.words_per_frame];
         if (n0 >= *total_nodes) return *total_roots;
-        uint32_t r = chunk_offsets[n0 / kThreads];
-        for (uint32_t i = (n0 / kThreads) * kThreads; i < n0; i++) r += (P[i] < 0) ? 1u : 0u;
-        return r;
+        const uint32_t c0 = n0 / kRankSub;
+        uint32_t r = 0;
+        for (uint32_t i = c0 * kRankSub + lane; i < n0; i += 32) r += (P[i] < 0) ? 1u : 0u;
+        return chunk_excl[c0] + yam_warp_sum(r);
     };
     const uint32_t here = roots_before_frame(f), next = roots_before_frame(f + 1);
-    frame_off[f] = here;
-    if (counts) counts[f] = (int32_t)(next - here);
+    if (lane == 0) {
+        frame_off[f] = here;
+        if (counts) counts[f] = (int32_t)(next - here);
+    }
 }
 
-// ---- 7. final labels ----------------------------------------------------------------------------
-// block = kFinalThreads words; labels are staged in shared memory (swizzled at int4 granularity:
-// both the per-thread row writes and the coalesced read-out are conflict free)
-constexpr int kFinalThreads = 128;
+// ---- 6. final labels ----------------------------------------------------------------------------
+// Generic widths: one thread per NIBBLE (4 pixels = one 16-byte store where the row pitch allows).
+// A set nibble holds at most two run segments, each resolved with at most two dependent loads
+// (node -> root -> -(label)).
+constexpr int kFinalIter = 4;  // nibbles per thread
 
-__global__ void __launch_bounds__(kFinalThreads) ccl_final_kernel(const uint32_t* __restrict__ bits,
+// Whole-word rows (w % 32 == 0): lane = word.  Each lane resolves the labels of its word's first two
+// segments, then the warp writes the 32 words cooperatively: 8 rounds x (lane = nibble of one of 4
+// words), the owner's bits and labels arrive by shuffle.  Words with more than two segments (noise)
+// are written by their owner lane afterwards.
+__global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t* __restrict__ bits,
                                                                   const uint32_t* __restrict__ nbase,
                                                                   const uint32_t* __restrict__ frame_off, CclGeom g,
                                                                   const int* __restrict__ P,
                                                                   int32_t* __restrict__ labels) {
-    __shared__ int4 s_out[kFinalThreads * 8];
-    const int64_t gw0 = (int64_t)blockIdx.x * kFinalThreads;
-    const int64_t gw = gw0 + threadIdx.x;
-    const int t = threadIdx.x;
-    uint32_t b = 0;
-    int off = 0, base = 0;
-    if (gw < g.total_words) {
-        b = bits[gw];
-        if (b) {
-            base = (int)nbase[gw];
-            if (g.frames > 1) off = (int)frame_off[gw / g.words_per_frame];
-        }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_base = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+    if (warp_base >= g.total_words) return;
+    const int64_t gw = warp_base + lane;
+    const uint32_t b = gw < g.total_words ? __ldg(bits + gw) : 0u;
+    int4* dst = reinterpret_cast<int4*>(labels + warp_base * 32);
+    const int valid_words = g.total_words - warp_base < 32 ? (int)(g.total_words - warp_base) : 32;
+    if (!__any_sync(0xffffffffu, b != 0u)) {
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+            if (4 * it + (lane >> 3) < valid_words) __stcs(dst + it * 32 + lane, make_int4(0, 0, 0, 0));
+        return;
     }
-    int32_t out[32];
+    int l0 = 0, l1 = 0, base = 0, off = 0;
+    const uint32_t starts = seg_starts(b);
+    const int nseg = __popc(starts);
     if (b) {
-        // first-level loads for up to 4 segments are issued together; more segments are rare
-        uint32_t starts = seg_starts(b);
-        const int nseg = __popc(starts);
-        int lab[4];
+        base = (int)__ldg(nbase + gw);
+        if (g.frames > 1) off = (int)__ldg(frame_off + gw / g.words_per_frame);
+        int v0 = __ldg(P + base);
+        int v1 = nseg > 1 ? __ldg(P + base + 1) : -1;
+        if (v0 >= 0) v0 = __ldg(P + v0);  // non-root: its root holds -(label)
+        if (v1 >= 0) v1 = __ldg(P + v1);
+        l0 = -v0 - off;
+        l1 = -v1 - off;
+    }
+    // bits that belong to the second (or a later) segment
+    const uint32_t later = starts & (starts - 1u);
+    const uint32_t hi = later ? ~((later & (0u - later)) - 1u) : 0u;
+    const bool many = nseg > 2;
+    const bool any_many = __any_sync(0xffffffffu, many);
 #pragma unroll
-        for (int k = 0; k < 4; k++) lab[k] = k < nseg ? __ldg(P + base + k) : -1;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (lab[k] >= 0) lab[k] = __ldg(P + lab[k]);  // non-root: its root holds -(label)
+    for (int it = 0; it < 8; it++) {
+        const int src = 4 * it + (lane >> 3), q = lane & 7;
+        const uint32_t bb = __shfl_sync(0xffffffffu, b, src);
+        const uint32_t hh = __shfl_sync(0xffffffffu, hi, src);
+        const int a0 = __shfl_sync(0xffffffffu, l0, src);
+        const int a1 = __shfl_sync(0xffffffffu, l1, src);
+        const uint32_t nib = (bb >> (4 * q)) & 0xfu;
+        const uint32_t sec = (hh >> (4 * q)) & 0xfu;
+        int4 out;
+        out.x = (nib & 1u) ? ((sec & 1u) ? a1 : a0) : 0;
+        out.y = (nib & 2u) ? ((sec & 2u) ? a1 : a0) : 0;
+        out.z = (nib & 4u) ? ((sec & 4u) ? a1 : a0) : 0;
+        out.w = (nib & 8u) ? ((sec & 8u) ? a1 : a0) : 0;
+        bool skip = src >= valid_words;
+        if (any_many) skip = skip || __shfl_sync(0xffffffffu, many ? 1 : 0, src);
+        if (!skip) __stcs(dst + it * 32 + lane, out);
+    }
+    if (many) {
+        int32_t* d = labels + gw * 32;
+        uint32_t st = starts;
         int cur = 0, k = 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 32; i++) {
-            const bool set = (b >> i) & 1u;
-            const bool start = set && (i == 0 || !((b >> (i - 1)) & 1u));
-            if (start) {
-                int v;
-                if (k < 4) {
-                    v = k == 0 ? lab[0] : k == 1 ? lab[1] : k == 2 ? lab[2] : lab[3];
-                } else {
-                    v = __ldg(P + base + k);
-                    if (v >= 0) v = __ldg(P + v);
-                }
+            if ((st >> i) & 1u) {
+                int v = __ldg(P + base + k);
+                if (v >= 0) v = __ldg(P + v);
                 cur = -v - off;
                 k++;
             }
-            out[i] = set ? cur : 0;
+            d[i] = ((b >> i) & 1u) ? cur : 0;
         }
-    } else {
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __restrict__ bits,
+                                                             const uint32_t* __restrict__ nbase,
+                                                             const uint32_t* __restrict__ frame_off, CclGeom g,
+                                                             const int* __restrict__ P, int32_t* __restrict__ labels,
+                                                             bool vec_ok) {
+    const int64_t t_base = (int64_t)blockIdx.x * (kThreads * kFinalIter) + threadIdx.x;
+    const int64_t total_nibbles = g.total_words * 8;
+    uint32_t bw[kFinalIter];
 #pragma unroll
-        for (int i = 0; i < 32; i++) out[i] = 0;
+    for (int it = 0; it < kFinalIter; it++) {
+        const int64_t t = t_base + (int64_t)it * kThreads;
+        bw[it] = t < total_nibbles ? __ldg(bits + (t >> 3)) : 0u;
     }
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-        s_out[t * 8 + ((q + t) & 7)] = make_int4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-    __syncthreads();
-    if ((g.w & 31) == 0 && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0)) {
-        // rows are whole words: the block's words are consecutive labels
-        int4* dst = reinterpret_cast<int4*>(labels + gw0 * 32);
-        const int64_t valid_words = g.total_words - gw0 < kFinalThreads ? g.total_words - gw0 : kFinalThreads;
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int idx = it * kFinalThreads + t;  // int4 index inside the block tile
-            const int wd = idx >> 3, q = idx & 7;
-            if (wd < valid_words) __stcs(dst + idx, s_out[wd * 8 + ((q + wd) & 7)]);
+    for (int it = 0; it < kFinalIter; it++) {
+        const int64_t t = t_base + (int64_t)it * kThreads;
+        if (t >= total_nibbles) continue;
+        const int64_t gw = t >> 3;
+        const int q = (int)(t & 7);
+        const uint32_t b = bw[it];
+        const uint32_t nib = (b >> (4 * q)) & 0xfu;
+        int4 out = make_int4(0, 0, 0, 0);
+        if (nib) {
+            const int base = (int)__ldg(nbase + gw);
+            const int off = g.frames > 1 ? (int)__ldg(frame_off + gw / g.words_per_frame) : 0;
+            const int first = __ffs(nib) - 1;
+            const uint32_t second = nib & (nib + (1u << first)) & 0xfu;  // bits of a second run, if any
+            const int k0 = seg_index(b, 4 * q + first);
+            int v0 = __ldg(P + base + k0);
+            int v1 = second ? __ldg(P + base + k0 + 1) : -1;
+            if (v0 >= 0) v0 = __ldg(P + v0);   // non-root: its root holds -(label)
+            if (v1 >= 0) v1 = __ldg(P + v1);
+            const int l0 = -v0 - off, l1 = -v1 - off;
+            out.x = (nib & 1u) ? ((second & 1u) ? l1 : l0) : 0;
+            out.y = (nib & 2u) ? ((second & 2u) ? l1 : l0) : 0;
+            out.z = (nib & 4u) ? ((second & 4u) ? l1 : l0) : 0;
+            out.w = (nib & 8u) ? ((second & 8u) ? l1 : l0) : 0;
         }
-    } else if (gw < g.total_words) {
-        const int64_t row_id = gw / g.wpr;
-        const int j = (int)(gw - row_id * g.wpr);
-        int32_t* drow = labels + row_id * (int64_t)g.w + (int64_t)j * 32;
-        const int valid = min(32, g.w - j * 32);
-        for (int i = 0; i < valid; i++) {
-            const int4 v = s_out[t * 8 + (((i >> 2) + t) & 7)];
-            drow[i] = (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+        {
+            const int64_t row_id = gw / g.wpr;
+            const int x = (int)(gw - row_id * g.wpr) * 32 + 4 * q;
+            if (x >= g.w) continue;
+            int32_t* d = labels + row_id * (int64_t)g.w + x;
+            if (vec_ok && x + 4 <= g.w) {
+                __stcs(reinterpret_cast<int4*>(d), out);
+            } else {
+                d[0] = out.x;
+                if (x + 1 < g.w) d[1] = out.y;
+                if (x + 2 < g.w) d[2] = out.z;
+                if (x + 3 < g.w) d[3] = out.w;
+            }
         }
     }
 }
@@ -618,52 +991,68 @@ static int ccl_label_impl(yam_ctx* ctx, const void* mask, const uint32_t* bits_i
                 (long long)h, (long long)w);
     YAM_REQUIRE(g.total_words * 16 < (1ll << 31) && g.total_words < (1ll << 27),
                 "ccl: stack too large for one call (%lld words); split the stack", (long long)g.total_words);
-    const int64_t nblocks = (g.total_words + kThreads - 1) / kThreads;
     const int64_t max_nodes = g.total_words * 16;  // at most 16 run segments per 32-pixel word
-    const int64_t max_chunks = (max_nodes + kThreads - 1) / kThreads;
-    // scratch: bits | nbase | blockA | chunkB | frame_off | misc(totals[2], counter) | counts | node_info | P
+    const int64_t scan_subs = (g.total_words + kScanSub - 1) / kScanSub;
+    const int64_t scan_chunks = scan_subs < ctx->num_sms ? scan_subs : ctx->num_sms;
+    const int64_t scan_per = (scan_subs + scan_chunks - 1) / scan_chunks * kScanSub;  // words per chunk
+    const int64_t rank_chunks = ctx->num_sms;                                        // status words
+    const int64_t rank_subs = (max_nodes + kRankSub - 1) / kRankSub;
+    // scratch: bits | nbase | [tickets | statusA | statusB] | chunk_excl | frame_off | totals | counts | P
     const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
-    const size_t blk_bytes = yam_align_up((size_t)nblocks * 4, 256);
-    const size_t chunk_bytes = yam_align_up((size_t)max_chunks * 4, 256);
+    const size_t sync_bytes = yam_align_up(256 + (size_t)(scan_chunks + rank_chunks) * 8, 256);
+    const size_t chunk_bytes = yam_align_up((size_t)rank_subs * 4, 256);
     const size_t frame_bytes = yam_align_up((size_t)n * 4, 256);
     const size_t node_bytes = yam_align_up((size_t)max_nodes * 4, 256);
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, 2 * words_bytes + blk_bytes + chunk_bytes + 2 * frame_bytes + 256 + 2 * node_bytes, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, 2 * words_bytes + sync_bytes + chunk_bytes + 2 * frame_bytes + 256 + node_bytes, &scratch)) return rc;
     char* sp = (char*)scratch;
     uint32_t* bits_scratch = (uint32_t*)sp; sp += words_bytes;
     const uint32_t* bits = bits_in ? bits_in : bits_scratch;
     uint32_t* nbase = (uint32_t*)sp; sp += words_bytes;
-    uint32_t* blockA = (uint32_t*)sp; sp += blk_bytes;
-    uint32_t* chunkB = (uint32_t*)sp; sp += chunk_bytes;
+    unsigned int* tickets = (unsigned int*)sp;                       // [0] scan, [1] rank
+    unsigned long long* statusA = (unsigned long long*)(sp + 256);
+    unsigned long long* statusB = statusA + scan_chunks;
+    char* sync_base = sp; sp += sync_bytes;
+    uint32_t* chunk_excl = (uint32_t*)sp; sp += chunk_bytes;
     uint32_t* frame_off = (uint32_t*)sp; sp += frame_bytes;
-    uint32_t* totals = (uint32_t*)sp;            // [0] nodes, [1] roots
-    unsigned int* counter = (unsigned int*)(sp + 16); sp += 256;
+    uint32_t* totals = (uint32_t*)sp; sp += 256;                     // [0] nodes, [1] roots
     int32_t* counts = counts_dev ? counts_dev : (int32_t*)sp; sp += frame_bytes;
-    uint32_t* node_info = (uint32_t*)sp; sp += node_bytes;
     int* P = (int*)sp;
 
-    // the election counter is self-resetting, but scratch is shared with other operators
-    YAM_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), ctx->stream));
-    const unsigned gblocks = (unsigned)nblocks;
-    const unsigned pgrid = (unsigned)(ctx->num_sms * 8);  // persistent grids for the node-parallel kernels
-    if (bits_in)
-        ccl_count_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, totals, counter);
-    else
-        ccl_pack_kernel<<<gblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits_scratch, blockA, totals, counter);
+    YAM_CUDA(cudaMemsetAsync(sync_base, 0, sync_bytes, ctx->stream));
+    if (n == 1) YAM_CUDA(cudaMemsetAsync(frame_off, 0, sizeof(uint32_t), ctx->stream));
+    const unsigned wblocks = (unsigned)((g.total_words + kThreads - 1) / kThreads);
+    if (!bits_in) {
+        ccl_pack_kernel<<<wblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits_scratch);
+        YAM_LAUNCHED(ctx);
+    }
+    ccl_scan_kernel<<<(unsigned)scan_chunks, kBigThreads, 0, ctx->stream>>>(bits, g.total_words, scan_per, nbase, statusA, tickets, totals);
     YAM_LAUNCHED(ctx);
-    ccl_nodebase_kernel<<<gblocks, kThreads, 0, ctx->stream>>>(bits, g, blockA, nbase, P, node_info);
+    const int tiles_x = (g.wpr + kTileC - 1) / kTileC, tiles_y = (g.h + kTileR - 1) / kTileR;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
+    YAM_REQUIRE(tiles < (1ll << 31), "ccl: too many tiles");
+    ccl_tile_kernel<<<(unsigned)tiles, kThreads, sizeof(TileSmem), ctx->stream>>>(bits, nbase, g, tiles_x, tiles_y, P);
     YAM_LAUNCHED(ctx);
-    ccl_union_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(bits, nbase, node_info, g, totals, P);
+    const int64_t na = (int64_t)tiles_y * n * g.wpr, nb = (int64_t)h * n * tiles_x * 2;
+    ccl_border_kernel<<<(unsigned)((na + nb + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(bits, nbase, g, tiles_x,
+                                                                                                  tiles_y, na, nb, P);
     YAM_LAUNCHED(ctx);
-    ccl_flatten_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(totals, P, chunkB, totals + 1, counter);
+    ccl_rank_kernel<<<(unsigned)rank_chunks, kBigThreads, 0, ctx->stream>>>(totals, P, statusB, tickets + 1, chunk_excl, totals + 1,
+                                                         n == 1 ? counts : nullptr);
     YAM_LAUNCHED(ctx);
-    ccl_rootlabel_kernel<<<pgrid, kThreads, 0, ctx->stream>>>(totals, chunkB, P);
-    YAM_LAUNCHED(ctx);
-    ccl_frame_offsets_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(nbase, g, totals, totals + 1, chunkB, P,
-                                                                                 frame_off, counts);
-    YAM_LAUNCHED(ctx);
-    const unsigned fblocks = (unsigned)((g.total_words + kFinalThreads - 1) / kFinalThreads);
-    ccl_final_kernel<<<fblocks, kFinalThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels);
+    if (n > 1) {
+        ccl_frame_offsets_kernel<<<(unsigned)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(
+            nbase, g, totals, totals + 1, chunk_excl, P, frame_off, counts);
+        YAM_LAUNCHED(ctx);
+    }
+    const bool lab_aligned = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
+    const unsigned fblocks = (unsigned)((g.total_words * 8 + kThreads * kFinalIter - 1) / (kThreads * kFinalIter));
+    if ((g.w & 31) == 0 && lab_aligned) {
+        const unsigned wblocks32 = (unsigned)((g.total_words + kThreads - 1) / kThreads);  // 8 warps x 32 words
+        ccl_final_warp_kernel<<<wblocks32, kThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels);
+    } else
+        ccl_final_kernel<<<fblocks, kThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels,
+                                                                       lab_aligned && (g.w & 3) == 0);
     YAM_LAUNCHED(ctx);
     if (counts_host) {
         YAM_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -6,6 +6,8 @@
 // (halo re-reads hit L2).  Arithmetic follows oracle/np_oracle.py bit for bit.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "yam_common.cuh"
 #include "yam_host.h"
 #include "yam_median_net.h"
@@ -569,6 +571,46 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
         }
     } else {
         store_tile<Tout>(s_out, dst, h, w, x0, y0);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// The same filter on the packed fp32 pipe (FFMA2 / FADD2 / FMUL2, sm_100): every lane of a packed
+// instruction is an IEEE fp32 operation, so results are bit-identical to the kernel above while the
+// FMA chains take half the issue slots.
+//   s_in2  float2 [ROWS/2][SWP]: .x = row 2p, .y = row 2p+1 of the converted input tile -> the
+//          horizontal pass pairs the SAME column of two consecutive rows (same taps, two chains)
+//   s_t    float  [ROWS][TWP] row-major                          -> the vertical pass pairs two
+//          adjacent columns of a row (one float2 load = one operand pair)
+template <int KS>
+__device__ __forceinline__ float2 row_dot2(const float2* __restrict__ x, const TapsF& taps) {
+    // x points at the left-most tap; same operation order as row_dot
+    if (KS == 3) {
+        const float2 k1 = make_float2(taps.v[1], taps.v[1]), k2 = make_float2(taps.v[2], taps.v[2]);
+        return __ffma2_rn(__fadd2_rn(x[0], x[2]), k2, __fmul2_rn(x[1], k1));
+    }
+    if (KS == 5) {
+        const float2 k2 = make_float2(taps.v[2], taps.v[2]), k3 = make_float2(taps.v[3], taps.v[3]),
+                     k4 = make_float2(taps.v[4], taps.v[4]);
+        float2 s = __fmul2_rn(__fadd2_rn(x[1], x[3]), k3);
+        s = __ffma2_rn(x[2], k2, s);
+        return __ffma2_rn(__fadd2_rn(x[0], x[4]), k4, s);
+    }
+    float2 s = __fmul2_rn(make_float2(taps.v[0], taps.v[0]), x[0]);
+#pragma unroll
+    for (int i = 1; i < KS; i++) s = __ffma2_rn(x[i], make_float2(taps.v[i], taps.v[i]), s);
+    return s;
+}
+
+template <typename Tin>
+__device__ __forceinline__ void load_row_vec(const Tin* __restrict__ row, int gx, int w, int border, bool fast, float* f) {
+    constexpr int VEC = 16 / sizeof(Tin);
+    if (fast && gx >= 0 && gx + VEC <= w) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + gx);
+        vec_to_f32<Tin>(q, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) f[i] = (float)row[yam_border(gx + i, w, border)];
     }
 }
 
