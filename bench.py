@@ -241,8 +241,8 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             bits2 = be.bits_morph(bits, wd, 4, 5, 1)
             return [
                 ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(inp, 11, 2)),
-                ("bits_morph open+close 5x5 (bit_morph_chain_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
-                ("ccl_label_bits (count, nodebase, union, flatten, rootlabel, frame_offsets, final)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
+                ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
+                ("ccl_label_bits (scan, tile, border, rank, final_warp)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
             ]
 
         def ops_unfused(inp):
@@ -251,7 +251,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             return [
                 ("adaptive_threshold_u16_b11 (sep_f32_tiled)", 3.0, lambda: be.adaptive_threshold(inp, 11, 2)),
                 ("morph_open_close_5x5_u8 (morph_fast_kernel)", 4.0, lambda: be.morph_open_close(m, 5, 1)),
-                ("ccl_label (pack, nodebase, union, flatten, rootlabel, frame_offsets, final)", 5.0, lambda: be.ccl_label(m2)),
+                ("ccl_label (pack, scan, tile, border, rank, final_warp)", 5.0, lambda: be.ccl_label(m2)),
             ]
         ops.unfused = ops_unfused
         return x, run, ops
@@ -294,7 +294,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             ("otsu_threshold_u16 (hist + scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ("adaptive_threshold_u16_b11 (sep_f32_kernel)", 3.0, lambda: be.adaptive_threshold(c, 11, 2)),
             ("morph_open_close_5x5_u8 (morph_rect_chain_kernel)", 4.0, lambda: be.morph_open_close(m, 5, 1)),
-            ("ccl_label (pack, union, flatten, scan, prefix, final)", 5.0, lambda: be.ccl_label(m2)),
+            ("ccl_label (pack, scan, tile, border, rank, frame_offsets, final_warp)", 5.0, lambda: be.ccl_label(m2)),
         ]
     return x, run, ops
 

@@ -408,7 +408,7 @@ def test_region_props(backend, rng):
 def test_adaptive_bits_and_unpack(backend, rng, dt):
     for shape in ((64, 64), (40, 72), (130, 257), (33, 71), (200, 1100)):
         a = blobs(rng, shape, dt) if shape[0] > 40 else rnd(rng, shape, dt)
-        for block, C in ((11, 2), (5, 2), (15, -1)):
+        for block, C in ((11, 2), (5, 2), (15, -1), (3, 1), (7, 3)):
             bits = backend.adaptive_threshold_bits(dev(backend, a), block, C)
             got = host(backend, backend.bits_unpack(bits, shape[1]))
             want = host(backend, backend.adaptive_threshold(dev(backend, a), block, C))

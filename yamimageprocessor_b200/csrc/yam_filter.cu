@@ -6,8 +6,6 @@
 // (halo re-reads hit L2).  Arithmetic follows oracle/np_oracle.py bit for bit.
 #include <math.h>
 
-#include <stdlib.h>
-
 #include "yam_common.cuh"
 #include "yam_host.h"
 #include "yam_median_net.h"
@@ -512,40 +510,38 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
     }
     __syncthreads();
 
-    // ---- vertical pass: lane -> column pair, warp -> RB rows
+    // ---- vertical pass: lane -> column pair, warp -> RB rows.  The two columns of a lane form one
+    // packed fp32 operand (FFMA2 / FADD2 / FMUL2: each half is an IEEE fp32 operation, so results
+    // are bit-identical to scalar code at half the issue slots).
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int cx = 2 * lane;
         const int r0 = warp * RB;
-        float c0[RB + KS - 1], c1[RB + KS - 1];
+        float2 c[RB + KS - 1];
 #pragma unroll
-        for (int i = 0; i < RB + KS - 1; i++) {
-            const float2 v = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TWP + cx);
-            c0[i] = v.x;
-            c1[i] = v.y;
-        }
+        for (int i = 0; i < RB + KS - 1; i++) c[i] = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TWP + cx);
+        const float2 kc = make_float2(taps.v[R], taps.v[R]);
 #pragma unroll
         for (int j = 0; j < RB; j++) {
-            float a = __fmul_rn(taps.v[R], c0[j + R]);
-            float b = __fmul_rn(taps.v[R], c1[j + R]);
+            float2 a = __fmul2_rn(kc, c[j + R]);
 #pragma unroll
-            for (int q = 1; q <= R; q++) {
-                a = __fmaf_rn(__fadd_rn(c0[j + R + q], c0[j + R - q]), taps.v[R + q], a);
-                b = __fmaf_rn(__fadd_rn(c1[j + R + q], c1[j + R - q]), taps.v[R + q], b);
-            }
+            for (int q = 1; q <= R; q++)
+                a = __ffma2_rn(__fadd2_rn(c[j + R + q], c[j + R - q]), make_float2(taps.v[R + q], taps.v[R + q]), a);
             if (FEPI == FEPI_ADAPTIVE || FEPI == FEPI_ADAPTIVE_BITS) {
                 // mean = rint(blur) (round-half-even via the 1.5*2^23 add; blur is a convex
                 // combination of pixel values so saturation can never trigger);
                 // dst = (src - mean > -idelta) ? 255 : 0, all values exact integers in float
                 const float2 sp = *reinterpret_cast<const float2*>(s_in + (r0 + j + R) * SWP + RA + cx);
-                const float m0 = __fadd_rn(__fadd_rn(a, 12582912.0f), -12582912.0f);
-                const float m1 = __fadd_rn(__fadd_rn(b, 12582912.0f), -12582912.0f);
+                const float2 big = make_float2(12582912.0f, 12582912.0f), nbig = make_float2(-12582912.0f, -12582912.0f);
+                const float2 m = __fadd2_rn(__fadd2_rn(a, big), nbig);
+                // sp - m, exact: one rounding of an exactly representable difference of integers
+                const float2 d = __ffma2_rn(m, make_float2(-1.0f, -1.0f), sp);
                 const float nd = -(float)idelta;
-                const uint32_t o0 = (__fadd_rn(sp.x, -m0) > nd) ? 255u : 0u;
-                const uint32_t o1 = (__fadd_rn(sp.y, -m1) > nd) ? 255u : 0u;
+                const uint32_t o0 = (d.x > nd) ? 255u : 0u;
+                const uint32_t o1 = (d.y > nd) ? 255u : 0u;
                 *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(s_out) + (r0 + j) * TW + cx) = (uint16_t)(o0 | (o1 << 8));
             } else {
-                *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_out) + (r0 + j) * TW + cx) = make_float2(a, b);
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_out) + (r0 + j) * TW + cx) = a;
             }
         }
     }
@@ -571,46 +567,6 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
         }
     } else {
         store_tile<Tout>(s_out, dst, h, w, x0, y0);
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// The same filter on the packed fp32 pipe (FFMA2 / FADD2 / FMUL2, sm_100): every lane of a packed
-// instruction is an IEEE fp32 operation, so results are bit-identical to the kernel above while the
-// FMA chains take half the issue slots.
-//   s_in2  float2 [ROWS/2][SWP]: .x = row 2p, .y = row 2p+1 of the converted input tile -> the
-//          horizontal pass pairs the SAME column of two consecutive rows (same taps, two chains)
-//   s_t    float  [ROWS][TWP] row-major                          -> the vertical pass pairs two
-//          adjacent columns of a row (one float2 load = one operand pair)
-template <int KS>
-__device__ __forceinline__ float2 row_dot2(const float2* __restrict__ x, const TapsF& taps) {
-    // x points at the left-most tap; same operation order as row_dot
-    if (KS == 3) {
-        const float2 k1 = make_float2(taps.v[1], taps.v[1]), k2 = make_float2(taps.v[2], taps.v[2]);
-        return __ffma2_rn(__fadd2_rn(x[0], x[2]), k2, __fmul2_rn(x[1], k1));
-    }
-    if (KS == 5) {
-        const float2 k2 = make_float2(taps.v[2], taps.v[2]), k3 = make_float2(taps.v[3], taps.v[3]),
-                     k4 = make_float2(taps.v[4], taps.v[4]);
-        float2 s = __fmul2_rn(__fadd2_rn(x[1], x[3]), k3);
-        s = __ffma2_rn(x[2], k2, s);
-        return __ffma2_rn(__fadd2_rn(x[0], x[4]), k4, s);
-    }
-    float2 s = __fmul2_rn(make_float2(taps.v[0], taps.v[0]), x[0]);
-#pragma unroll
-    for (int i = 1; i < KS; i++) s = __ffma2_rn(x[i], make_float2(taps.v[i], taps.v[i]), s);
-    return s;
-}
-
-template <typename Tin>
-__device__ __forceinline__ void load_row_vec(const Tin* __restrict__ row, int gx, int w, int border, bool fast, float* f) {
-    constexpr int VEC = 16 / sizeof(Tin);
-    if (fast && gx >= 0 && gx + VEC <= w) {
-        const uint4 q = *reinterpret_cast<const uint4*>(row + gx);
-        vec_to_f32<Tin>(q, f);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; i++) f[i] = (float)row[yam_border(gx + i, w, border)];
     }
 }
 
