@@ -224,7 +224,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             return [
                 ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
                 ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-                ("otsu_threshold_u16 (hist + scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+                ("otsu_threshold_u16 (hist + host scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ]
         return x, run, ops
 
@@ -274,27 +274,25 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
         t, otsu_mask = be.otsu_threshold(c, 255)
-        m = be.adaptive_threshold(c, 11, 2)
-        m = be.morph_open_close(m, 5, 1)
-        labels, counts = be.ccl_label(m)
-        cnt = be.to_host(counts)
-        tables = []
-        for i in range(labels.shape[0]):
-            tables.append(be.region_props(labels[i], c[i], int(cnt[i])))
+        labels, counts = be.segment_fused(c, 11, 2, 5, 1)
+        tables, offsets = be.region_props_stack(labels, c, counts)
         return otsu_mask, labels, tables
 
     def ops(inp):
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
-        m = be.adaptive_threshold(c, 11, 2)
-        m2 = be.morph_open_close(m, 5, 1)
+        wd = int(inp.shape[-1])
+        bits = be.adaptive_threshold_bits(c, 11, 2)
+        bits2 = be.bits_morph(bits, wd, 4, 5, 1)
+        labels, counts = be.ccl_label_bits(bits2, wd)
         return [
             ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
             ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-            ("otsu_threshold_u16 (hist + scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
-            ("adaptive_threshold_u16_b11 (sep_f32_kernel)", 3.0, lambda: be.adaptive_threshold(c, 11, 2)),
-            ("morph_open_close_5x5_u8 (morph_rect_chain_kernel)", 4.0, lambda: be.morph_open_close(m, 5, 1)),
-            ("ccl_label (pack, scan, tile, border, rank, frame_offsets, final_warp)", 5.0, lambda: be.ccl_label(m2)),
+            ("otsu_threshold_u16 (hist + host scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+            ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(c, 11, 2)),
+            ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
+            ("ccl_label_bits (scan, tile, border, rank, frame_offsets, final_warp)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
+            ("region_props_stack (props_init + props_kernel)", 6.0, lambda: be.region_props_stack(labels, c, counts)),
         ]
     return x, run, ops
 

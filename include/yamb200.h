@@ -198,6 +198,14 @@ int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* rem
 int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype,
                      int64_t h, int64_t w, int64_t n_labels, int64_t* props_dev);
 
+/* The same for a stack of n labelled frames (time-lapse batches, processing/pipeline_manager.py
+ * _apply_slice_wise:475-492 treats planes independently): frame f holds labels 1..count_f and its
+ * rows start at props_dev[offsets_dev[f]]; offsets_dev = exclusive prefix of the per-frame counts
+ * (n + 1 entries, device memory), total = offsets[n]. */
+int yam_region_props_stack(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype,
+                           int64_t n, int64_t h, int64_t w, const int64_t* offsets_dev, int64_t total,
+                           int64_t* props_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,6 +403,25 @@ def test_region_props(backend, rng):
         assert_same(props[:, 4:8], want["bbox"], "bbox")
 
 
+def test_region_props_stack(backend, rng):
+    m = np.stack([_ccl_case(rng, (70, 96), d) for d in (0.2, 0.5, 0.0, 0.35)])
+    inten = np.stack([rnd(rng, (70, 96), U16) for _ in range(4)])
+    labels, counts = backend.ccl_label(dev(backend, m))
+    props, offsets = backend.region_props_stack(labels, dev(backend, inten), counts)
+    props = host(backend, props)
+    lab = host(backend, labels)
+    cnt = host(backend, counts)
+    assert offsets[-1] == int(cnt.sum()) == props.shape[0]
+    for i in range(4):
+        want = O.region_props(lab[i], inten[i], int(cnt[i]))
+        got = props[offsets[i]:offsets[i + 1]]
+        assert_same(got[:, 0], want["area"], f"area frame {i}")
+        assert_same(got[:, 1], want["sum_y"], "sum_y")
+        assert_same(got[:, 2], want["sum_x"], "sum_x")
+        assert_same(got[:, 3], want["sum_intensity"], "sum_intensity")
+        assert_same(got[:, 4:8], want["bbox"], "bbox")
+
+
 # --------------------------------------------------------------------------- fused binary path
 @pytest.mark.parametrize("dt", [U8, U16])
 def test_adaptive_bits_and_unpack(backend, rng, dt):

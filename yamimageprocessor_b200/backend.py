@@ -481,6 +481,34 @@ class Backend:
         return props
 
 
+    def region_props_stack(self, labels, intensity=None, counts=None):
+        """Region tables of a labelled stack (n, h, w) in one launch.  Returns (props int64[total, 8] on
+        device, offsets int64[n + 1] on host): frame f owns rows offsets[f]:offsets[f + 1]."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(3,), dtypes=(torch.int32,), name="labels")
+        n, h, w = self._nhw(labels)
+        if counts is None:
+            counts = labels.reshape(n, -1).amax(dim=1)
+        cnt = counts.detach().cpu().numpy().astype(np.int64) if hasattr(counts, "detach") else np.asarray(counts, np.int64)
+        offsets = np.zeros(n + 1, np.int64)
+        np.cumsum(cnt, out=offsets[1:])
+        total = int(offsets[-1])
+        idt = 0
+        iptr = None
+        if intensity is not None:
+            intensity = self._check(intensity, ndim=(3,), dtypes=(torch.uint8, torch.uint16), name="intensity")
+            if tuple(intensity.shape) != (n, h, w):
+                raise ValueError("intensity stack must match the label stack shape")
+            idt = _dtype_code(intensity)
+            iptr = self._p(intensity)
+        props = torch.empty((total, PROPS_STRIDE), dtype=torch.int64, device=self.device)
+        if total > 0:
+            offs_dev = torch.from_numpy(offsets).to(self.device)
+            self._call("yam_region_props_stack", self._p(labels), iptr, idt, n, h, w, self._p(offs_dev), total,
+                       self._p(props))
+        return props, offsets
+
+
 _default: Dict[int, Backend] = {}
 _default_lock = threading.Lock()
 

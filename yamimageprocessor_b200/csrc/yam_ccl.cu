@@ -842,7 +842,17 @@ constexpr int kRowsPerIter = 4;
 template <typename TI>
 __global__ void __launch_bounds__(kThreads) props_kernel(const int32_t* __restrict__ labels,
                                                          const TI* __restrict__ intensity, int h, int w,
-                                                         int64_t n_labels, long long* __restrict__ props) {
+                                                         int64_t n_labels, long long* __restrict__ props,
+                                                         const int64_t* __restrict__ frame_offsets) {
+    if (frame_offsets) {
+        // stack: blockIdx.z = frame; its rows of the table start at frame_offsets[frame]
+        const int64_t f = blockIdx.z, o0 = frame_offsets[f];
+        n_labels = frame_offsets[f + 1] - o0;
+        if (n_labels <= 0) return;
+        labels += f * (int64_t)h * w;
+        if (intensity) intensity += f * (int64_t)h * w;
+        props += o0 * YAM_PROPS_STRIDE;
+    }
     const int chunks = (w + 7) / 8;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= chunks) return;
@@ -1073,10 +1083,10 @@ int yam_ccl_label_bits(yam_ctx* ctx, const uint32_t* bits, int32_t* labels, int6
     return ccl_label_impl(ctx, nullptr, bits, labels, n, h, w, counts_dev, counts_host);
 }
 
-int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t h,
-                     int64_t w, int64_t n_labels, int64_t* props_dev) {
+static int region_props_impl(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t n,
+                             int64_t h, int64_t w, const int64_t* offsets_dev, int64_t n_labels, int64_t* props_dev) {
     if (int rc = yam_enter(ctx)) return rc;
-    YAM_REQUIRE(labels && h > 0 && w > 0 && n_labels >= 0, "region_props: bad arguments");
+    YAM_REQUIRE(labels && n > 0 && n <= 65535 && h > 0 && w > 0 && n_labels >= 0, "region_props: bad arguments");
     YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "region_props: image side too large");
     if (n_labels == 0) return YAM_OK;
     YAM_REQUIRE(props_dev, "region_props: props_dev is NULL");
@@ -1090,13 +1100,26 @@ int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity,
     unsigned gx = (unsigned)((chunks + kThreads - 1) / kThreads);
     const int64_t bands = (h + kBand - 1) / kBand;
     unsigned gy = (unsigned)(bands < 65535 ? bands : 65535);
-    dim3 grid(gx, gy, 1);
+    dim3 grid(gx, gy, (unsigned)n);
     if (!intensity || intensity_dtype == YAM_U16)
-        props_kernel<uint16_t><<<grid, kThreads, 0, ctx->stream>>>(labels, (const uint16_t*)intensity, (int)h, (int)w, n_labels, props);
+        props_kernel<uint16_t><<<grid, kThreads, 0, ctx->stream>>>(labels, (const uint16_t*)intensity, (int)h, (int)w, n_labels,
+                                                                   props, offsets_dev);
     else
-        props_kernel<uint8_t><<<grid, kThreads, 0, ctx->stream>>>(labels, (const uint8_t*)intensity, (int)h, (int)w, n_labels, props);
+        props_kernel<uint8_t><<<grid, kThreads, 0, ctx->stream>>>(labels, (const uint8_t*)intensity, (int)h, (int)w, n_labels,
+                                                                  props, offsets_dev);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
+}
+
+int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t h,
+                     int64_t w, int64_t n_labels, int64_t* props_dev) {
+    return region_props_impl(ctx, labels, intensity, intensity_dtype, 1, h, w, nullptr, n_labels, props_dev);
+}
+
+int yam_region_props_stack(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t n,
+                           int64_t h, int64_t w, const int64_t* offsets_dev, int64_t total, int64_t* props_dev) {
+    YAM_REQUIRE(offsets_dev != nullptr, "region_props_stack: offsets_dev is NULL");
+    return region_props_impl(ctx, labels, intensity, intensity_dtype, n, h, w, offsets_dev, total, props_dev);
 }
 
 }  // extern "C"

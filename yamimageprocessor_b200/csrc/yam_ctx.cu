@@ -268,7 +268,8 @@ void yam_host_structuring_element(int shape, int k, uint8_t* out) {
     memset(out, 1, (size_t)k * k);
 }
 
-int yam_host_otsu(const uint64_t* h, int bins) {
+template <typename CountT>
+static int host_otsu_impl(const CountT* h, int bins) {
     // cv2 getThreshVal_Otsu_{8u,16u}: fp64 recurrence, strict '>' keeps the first maximum.
     // This TU is compiled without FMA contraction (-ffp-contract=off).
     double total = 0, mu = 0;
@@ -307,6 +308,9 @@ int yam_host_otsu(const uint64_t* h, int bins) {
     }
     return max_val;
 }
+
+int yam_host_otsu(const uint64_t* h, int bins) { return host_otsu_impl<uint64_t>(h, bins); }
+int yam_host_otsu32(const uint32_t* h, int bins) { return host_otsu_impl<uint32_t>(h, bins); }
 
 extern "C" {
 

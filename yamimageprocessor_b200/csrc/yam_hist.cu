@@ -12,7 +12,10 @@
 // 8-bit histograms use per-warp privatised 256-bin shared histograms.
 #include <math.h>
 
-#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -556,31 +559,77 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const T* __restrict__ 
     }
 }
 
-// Otsu recurrence for several frames on host threads (the fp64 recurrence is sequential per frame).
-void otsu_scan_frames_host(const uint64_t* hists, int bins, int64_t n, int32_t* out) {
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
-    const int64_t nt = n < (int64_t)hw ? n : (int64_t)(hw < 32 ? hw : 32);
-    if (nt <= 1) {
-        for (int64_t f = 0; f < n; f++) out[f] = yam_host_otsu(hists + f * bins, bins);
-        return;
+// Otsu recurrence on host threads (the fp64 recurrence is sequential per frame).  One process-wide
+// pool of workers, created on first use and never torn down (its threads sleep on a condition
+// variable); callers hand in frames as their histograms arrive and wait for the batch at the end.
+class ScanPool {
+public:
+    static ScanPool& instance() {
+        static ScanPool* pool = new ScanPool();  // leaked on purpose: no static-destruction order issues
+        return *pool;
     }
-    std::atomic<int64_t> next{0};
-    auto work = [&]() {
-        for (;;) {
-            const int64_t f = next.fetch_add(1);
-            if (f >= n) break;
-            out[f] = yam_host_otsu(hists + f * bins, bins);
+    void submit(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            queue_.push_back(std::move(fn));
+            pending_++;
         }
-    };
-    std::vector<std::thread> pool;
-    try {
-        for (int64_t t = 1; t < nt; t++) pool.emplace_back(work);
-    } catch (...) {
-        // could not start (all) helpers: the calling thread finishes whatever is left
+        cv_.notify_one();
     }
-    work();
-    for (auto& th : pool) th.join();
+    // the calling thread helps until every submitted task has finished
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            if (!queue_.empty()) {
+                auto fn = std::move(queue_.front());
+                queue_.pop_front();
+                lk.unlock();
+                fn();
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+                continue;
+            }
+            if (pending_ == 0) return;
+            done_.wait(lk);
+        }
+    }
+
+private:
+    ScanPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw == 0) hw = 4;
+        const unsigned nt = (hw < 32 ? hw : 32) - 1;  // the caller is the last worker
+        for (unsigned i = 0; i < nt; i++) {
+            try {
+                std::thread([this] { run(); }).detach();
+            } catch (...) {
+                break;  // fewer helpers: wait_all() still drains the queue on the calling thread
+            }
+        }
+    }
+    void run() {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_.wait(lk, [this] { return !queue_.empty(); });
+            auto fn = std::move(queue_.front());
+            queue_.pop_front();
+            lk.unlock();
+            fn();
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<std::function<void()>> queue_;
+    int64_t pending_ = 0;
+};
+
+// 64-bit device histograms -> 32-bit counts for the host scan (halves the read-back)
+__global__ void __launch_bounds__(256) hist_narrow_kernel(const unsigned long long* __restrict__ in,
+                                                          uint32_t* __restrict__ out, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (uint32_t)in[i];
 }
 
 // Interleaved LUTs for the apply pass on large 16-bit frames: quad[cell][v] holds the four LUT
@@ -788,7 +837,8 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
     const size_t hist_bytes = sizeof(unsigned long long) * bins * n;
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, hist_bytes + sizeof(int32_t) * n + 256, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256) +
+                                      sizeof(uint32_t) * bins * n, &scratch)) return rc;
     unsigned long long* hist = (unsigned long long*)scratch;
     int32_t* t_dev = thresh_dev ? thresh_dev : (int32_t*)((char*)scratch + yam_align_up(hist_bytes, 256));
     if (int rc = hist_into(ctx, src, n, h, w, dtype, hist)) return rc;
@@ -797,21 +847,69 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     // (chunks of <= 64 frames through a pinned buffer); 256-bin histograms stay on the device.
     const bool host_scan = (dtype == YAM_U16);
     if (host_scan) {
-        const int64_t chunk = 64;
-        void* pinned = nullptr;
+        // Read-back in chunks of <= 64 frames through a pinned buffer, 8 frames per copy; each copy is
+        // followed by an event, and the frames of a copy are handed to the worker pool as soon as
+        // its event fires, so the scans overlap the remaining copies.
+        const int64_t chunk = 64, sub = 8;
+        const bool narrow = (h * w) < (1ll << 32);
+        const size_t count_bytes = narrow ? sizeof(uint32_t) : sizeof(unsigned long long);
         const int64_t first = n < chunk ? n : chunk;
-        if (int rc = yam_pinned(ctx, (size_t)first * (sizeof(unsigned long long) * bins + sizeof(int32_t)), &pinned)) return rc;
-        int32_t* t_stage = (int32_t*)((char*)pinned + (size_t)first * sizeof(unsigned long long) * bins);
+        void* pinned = nullptr;
+        if (int rc = yam_pinned(ctx, (size_t)first * (count_bytes * bins + sizeof(int32_t)), &pinned)) return rc;
+        int32_t* t_stage = (int32_t*)((char*)pinned + (size_t)first * count_bytes * bins);
+        uint32_t* narrow_dev = nullptr;
+        if (narrow) {
+            // the 32-bit copy lives behind the thresholds in the scratch block requested above
+            narrow_dev = (uint32_t*)((char*)scratch + yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256));
+            const int64_t cells = (int64_t)bins * n;
+            hist_narrow_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(hist, narrow_dev, cells);
+            YAM_LAUNCHED(ctx);
+        }
+        cudaEvent_t ev[8];
+        int nev = 0;
         for (int64_t f0 = 0; f0 < n; f0 += chunk) {
             const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
-            YAM_CUDA(cudaMemcpyAsync(pinned, hist + f0 * bins, sizeof(unsigned long long) * bins * nf,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-            YAM_CUDA(cudaStreamSynchronize(ctx->stream));
-            otsu_scan_frames_host((const uint64_t*)pinned, bins, nf, t_stage);
+            const int subs = (int)((nf + sub - 1) / sub);
+            for (int k = 0; k < subs; k++) {
+                const int64_t s0 = k * sub, sn = (nf - s0) < sub ? (nf - s0) : sub;
+                const char* srcp = narrow ? (const char*)(narrow_dev + (f0 + s0) * bins) : (const char*)(hist + (f0 + s0) * bins);
+                YAM_CUDA(cudaMemcpyAsync((char*)pinned + (size_t)s0 * count_bytes * bins, srcp, (size_t)sn * count_bytes * bins,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+                if (k >= nev) {
+                    YAM_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+                    nev = k + 1;
+                }
+                YAM_CUDA(cudaEventRecord(ev[k], ctx->stream));
+            }
+            ScanPool& pool = ScanPool::instance();
+            cudaError_t ev_err = cudaSuccess;
+            for (int k = 0; k < subs; k++) {
+                const int64_t s0 = k * sub, sn = (nf - s0) < sub ? (nf - s0) : sub;
+                if (ev_err == cudaSuccess) ev_err = cudaEventSynchronize(ev[k]);
+                if (ev_err != cudaSuccess) break;
+                for (int64_t f = s0; f < s0 + sn; f++) {
+                    const char* hp = (const char*)pinned + (size_t)f * count_bytes * bins;
+                    int32_t* outp = t_stage + f;
+                    if (nf == 1) {
+                        *outp = narrow ? yam_host_otsu32((const uint32_t*)hp, bins) : yam_host_otsu((const uint64_t*)hp, bins);
+                    } else {
+                        pool.submit([hp, outp, bins, narrow] {
+                            *outp = narrow ? yam_host_otsu32((const uint32_t*)hp, bins) : yam_host_otsu((const uint64_t*)hp, bins);
+                        });
+                    }
+                }
+            }
+            pool.wait_all();
+            if (ev_err != cudaSuccess) {
+                for (int k = 0; k < nev; k++) cudaEventDestroy(ev[k]);
+                yam_set_error("otsu: histogram read-back failed: %s", cudaGetErrorString(ev_err));
+                return YAM_ECUDA;
+            }
             YAM_CUDA(cudaMemcpyAsync(t_dev + f0, t_stage, sizeof(int32_t) * nf, cudaMemcpyHostToDevice, ctx->stream));
             if (thresh_host) memcpy(thresh_host + f0, t_stage, sizeof(int32_t) * nf);
-            if (f0 + chunk < n) YAM_CUDA(cudaStreamSynchronize(ctx->stream));  // t_stage is reused
+            if (f0 + chunk < n) YAM_CUDA(cudaStreamSynchronize(ctx->stream));  // the pinned buffer is reused
         }
+        for (int k = 0; k < nev; k++) cudaEventDestroy(ev[k]);
     } else {
         otsu_scan_kernel<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(hist, bins, n, t_dev);
         YAM_LAUNCHED(ctx);

@@ -9,3 +9,4 @@ void yam_host_gaussian_taps(int k, double sigma, double* out);
 void yam_host_fixed_taps(const double* kf, int k, int bits, int64_t* out);
 void yam_host_structuring_element(int shape, int k, uint8_t* out);
 int yam_host_otsu(const uint64_t* h, int bins);
+int yam_host_otsu32(const uint32_t* h, int bins);  // same recurrence on 32-bit counts (frames < 2^32 px)

@@ -9,7 +9,7 @@ path has no halo, ``SURVEY.md`` §0 fact 5):
   g core rows           --tile histograms -> LUTs-->   all-gather LUTs (tiles x 128 KiB)
   g (+ halo)            --CLAHE apply with GLOBAL geometry-->  c
   c core rows           --histogram--> all-reduce (65536 x int64)  --Otsu scan-->  t, Otsu mask
-  c (+ halo)            --adaptive threshold -> open -> close-->  mask (cropped to the core)
+  c (+ halo)            --adaptive threshold -> open -> close-->  packed 1-bit mask (cropped to the core)
   mask core             --CCL-->  per-strip labels; boundary rows all-gathered, equivalences
                           united, labels renumbered in global raster-first order (relabel kernel)
   labels, c             --region props--> partial tables, all-reduced (sum / min / max)
@@ -256,9 +256,10 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     otsu_mask = be.threshold(c_core, float(t), 255)
 
     # segmentation on the extended rows, cropped to the core
-    m = be.morph_open_close(be.adaptive_threshold(c, p.block_size, p.C), p.morph_ksize, 1)
-    mask_core = m[c0 - a0: c1 - a0].contiguous()
-    labels, counts = be.ccl_label(mask_core)
+    # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
+    # cropping whole rows of the packed mask is a view, not a copy)
+    bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
+    labels, counts = be.ccl_label_bits(bits[c0 - a0: c1 - a0], W)
     n_local = int(be.to_host(counts)[0])
 
     # cross-strip merge from boundary rows
