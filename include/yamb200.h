@@ -189,6 +189,14 @@ int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, in
 int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev,
                 int64_t remap_size);
 
+/* Cross-strip label merge for row-strip sharded mosaics: strip r holds canonical
+ * labels 1..count_r; global id = offsets[r] + local label.  edges_dev is [world][2][w] int32: the
+ * first and last label row of every strip.  Unites the ids that touch across a strip boundary
+ * (8-connectivity) and writes, for every global id in [0, total], the smallest id of its merged
+ * set to root_dev[total + 1] (root_dev[0] = 0).  offsets_dev: world + 1 int64 on the device. */
+int yam_merge_strip_labels(yam_ctx* ctx, const int32_t* edges_dev, const int64_t* offsets_dev, int world,
+                           int64_t w, int64_t total, int32_t* root_dev);
+
 /* ---- K11 region properties -----------------------------------------------------------------
  * skimage.measure.regionprops restated (core/extraction.py:61,74): for a single labelled frame
  * with labels 1..n_labels writes, per label (row i = label i+1), 8 int64 accumulators to

@@ -969,9 +969,74 @@ __global__ void __launch_bounds__(kThreads) relabel_kernel(int32_t* __restrict__
     }
 }
 
+// ---- cross-strip merge: union-find over the global label ids that meet at strip boundaries --------
+__global__ void __launch_bounds__(kThreads) iota_kernel(int32_t* __restrict__ p, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = (int32_t)i;
+}
+
+// thread = (boundary r | r+1, column x): bottom row of strip r against the three neighbours in the
+// top row of strip r + 1
+__global__ void __launch_bounds__(kThreads) strip_union_kernel(const int32_t* __restrict__ edges,
+                                                               const int64_t* __restrict__ offs, int world, int64_t w,
+                                                               int* __restrict__ P) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)(world - 1) * w) return;
+    const int r = (int)(t / w);
+    const int64_t x = t - (int64_t)r * w;
+    const int32_t a = edges[((int64_t)r * 2 + 1) * w + x];
+    if (a <= 0) return;
+    const int ga = (int)(offs[r] + a);
+    const int32_t* top = edges + ((int64_t)(r + 1) * 2) * w;
+    const int64_t ob = offs[r + 1];
+    int last = 0;
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+        const int64_t xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const int32_t b = top[xx];
+        if (b > 0 && b != last) {
+            unite(P, ga, (int)(ob + b));
+            last = b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) flatten_all_kernel(int* __restrict__ P, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int x = (int)i, p = __ldcg(P + x);
+    if (p == x) return;
+    while (p != x) {
+        x = p;
+        p = __ldcg(P + x);
+    }
+    P[i] = x;  // owner-only store: readers see either an ancestor or the root
+}
+
 }  // namespace
 
 extern "C" {
+
+int yam_merge_strip_labels(yam_ctx* ctx, const int32_t* edges_dev, const int64_t* offsets_dev, int world, int64_t w,
+                           int64_t total, int32_t* root_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(edges_dev && offsets_dev && root_dev && world >= 1 && w > 0 && total >= 0 && total < (1ll << 31) - 1,
+                "merge_strip_labels: bad arguments");
+    const int64_t count = total + 1;
+    const unsigned nb = (unsigned)((count + kThreads - 1) / kThreads);
+    iota_kernel<<<nb, kThreads, 0, ctx->stream>>>(root_dev, count);
+    YAM_LAUNCHED(ctx);
+    if (world > 1) {
+        const int64_t pairs = (int64_t)(world - 1) * w;
+        strip_union_kernel<<<(unsigned)((pairs + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(
+            edges_dev, offsets_dev, world, w, root_dev);
+        YAM_LAUNCHED(ctx);
+        flatten_all_kernel<<<nb, kThreads, 0, ctx->stream>>>(root_dev, count);
+        YAM_LAUNCHED(ctx);
+    }
+    return YAM_OK;
+}
 
 int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev, int64_t remap_size) {
     if (int rc = yam_enter(ctx)) return rc;

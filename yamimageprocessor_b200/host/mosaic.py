@@ -38,6 +38,7 @@ class MosaicParams:
     block_size: int = 11
     C: float = 2.0
     morph_ksize: int = 5
+    trace: Any = None              # optional callable(phase_name, rank): profiling hook, called at phase ends
 
 
 @dataclass
@@ -226,6 +227,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         comm = TorchComm()
     if world == 1:
         comm = None
+    mark = (lambda name: p.trace(name, rank)) if p.trace is not None else (lambda name: None)
     H, W = int(source.shape[0]), int(source.shape[1])
     tiles_x, tiles_y = p.tile_grid
     if W % tiles_x:
@@ -239,12 +241,14 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
 
     x = device_source if device_source is not None else be.to_device(np.ascontiguousarray(source[r0:r1]))
     g = be.gaussian(x, p.gauss_ksize, 0.0)                     # exact on [a0, a1): artificial edges are hg rows away
+    mark("gaussian")
 
     # CLAHE: LUTs of the tile rows this rank owns, gathered from every rank
     luts_local = be.clahe_luts(g[c0 - r0: c1 - r0], p.clip_limit, (tiles_x, tiles_y // world))
     luts = torch.cat(comm.all_gather(luts_local), dim=0) if comm is not None else luts_local
     c = be.clahe_apply(g[a0 - r0: a1 - r0], luts, (tw, th), y_offset=a0)
     c_core = c[c0 - a0: c1 - a0]
+    mark("clahe")
 
     # Otsu on the global histogram
     hist = be.histogram(c_core)[0]
@@ -254,6 +258,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     else:
         t = be.otsu_from_histogram(be.to_host(hist))
     otsu_mask = be.threshold(c_core, float(t), 255)
+    mark("otsu")
 
     # segmentation on the extended rows, cropped to the core
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
@@ -261,6 +266,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
     labels, counts = be.ccl_label_bits(bits[c0 - a0: c1 - a0], W)
     n_local = int(be.to_host(counts)[0])
+    mark("segment")
 
     # cross-strip merge from boundary rows
     if comm is not None:
@@ -268,26 +274,25 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         edges = comm.all_gather(edge)
         cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
         def merge():
-            # host: only the labels on the strip boundaries; device: the O(all labels) prefix work
-            tops = [be.to_host(e[0]) for e in edges]
-            bottoms = [be.to_host(e[1]) for e in edges]
-            involved, roots, offs = sharding.boundary_roots(tops, bottoms, [int(v.item()) for v in cnts])
-            total_local = int(offs[-1])
-            root = torch.arange(total_local + 1, dtype=torch.int64, device=be.device)
-            if involved.size:
-                root[torch.from_numpy(involved).to(be.device)] = torch.from_numpy(roots).to(be.device)
-            is_root = root == torch.arange(total_local + 1, dtype=torch.int64, device=be.device)
+            # all on the device: union of the ids that touch across strip boundaries, then the
+            # raster-first renumbering (rank of every root among the roots)
+            offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device), torch.cat(cnts).cumsum(0)])
+            root = be.merge_strip_labels(torch.stack(edges), offs_dev).to(torch.int64)
+            ids = torch.arange(root.numel(), dtype=torch.int64, device=be.device)
+            is_root = root == ids
             is_root[0] = False
             rank = torch.cumsum(is_root.to(torch.int32), dim=0, dtype=torch.int32)
             glob = rank[root]
             glob[0] = 0
-            return glob, offs, int(rank[-1].item()) if total_local else 0
+            offs = [int(v) for v in offs_dev.tolist()]
+            return glob, offs, int(rank[-1].item()) if root.numel() > 1 else 0
 
         glob, offs, total = comm.once(merge)
         remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
         be.relabel(labels, remap)
     else:
         total = n_local
+    mark("merge")
 
     props = None
     if with_props:
