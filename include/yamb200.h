@@ -214,6 +214,38 @@ int yam_region_props_stack(yam_ctx* ctx, const int32_t* labels, const void* inte
                            int64_t n, int64_t h, int64_t w, const int64_t* offsets_dev, int64_t total,
                            int64_t* props_dev);
 
+/* ---- remaining per-pixel menu steps -----------------------------------------
+ * cv2.addWeighted (SharpenModule, modules/preprocessing.py:167-171): scalars as float32,
+ * dst = saturate(rint(fmaf(a, alpha, fmaf(b, beta, gamma)))); U8 | U16, dtype preserved. */
+int yam_add_weighted(yam_ctx* ctx, const void* a, const void* b, void* dst, int64_t count, int dtype,
+                     double alpha, double beta, double gamma);
+
+/* SelectChannelModule (modules/preprocessing.py:188-209) on interleaved BGR (px pixels):
+ * B / G / R pick (U8 | U16) or the truncated mean of two channels (U8 only). */
+#define YAM_CHANNEL_B 0
+#define YAM_CHANNEL_G 1
+#define YAM_CHANNEL_R 2
+#define YAM_CHANNEL_RG 3
+#define YAM_CHANNEL_GB 4
+#define YAM_CHANNEL_BR 5
+int yam_select_channel(yam_ctx* ctx, const void* bgr, void* dst, int64_t px, int dtype, int mode);
+/* cv2.cvtColor(GRAY2BGR): channel "All" on a single-channel image (modules/preprocessing.py:192-193) */
+int yam_gray2bgr(yam_ctx* ctx, const void* gray, void* bgr, int64_t px, int dtype);
+
+/* remove_border_regions (core/segmentation.py:316-325): elements closer than border_distance to an
+ * image edge become 0; like the reference's [d:-d] slice, d == 0 or 2d >= side clears everything. */
+int yam_border_clear(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int channels,
+                     int dtype, int border_distance);
+
+/* sobel_operator / prewitt_operator / laplacian_operator (core/segmentation.py:150-169): gray U8 |
+ * U16 in, uint8 magnitude out (clip to 255, truncate), BORDER_REFLECT_101; ksize 1, 3, 5 or 7
+ * (exact integer range; Prewitt is 3x3). */
+#define YAM_EDGE_SOBEL 0
+#define YAM_EDGE_PREWITT 1
+#define YAM_EDGE_LAPLACIAN 2
+int yam_edge_filter(yam_ctx* ctx, const void* src, void* dst_u8, int64_t n, int64_t h, int64_t w, int dtype,
+                    int kind, int ksize);
+
 #ifdef __cplusplus
 }
 #endif

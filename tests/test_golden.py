@@ -80,3 +80,46 @@ def test_connected_components(gold, meta):
         assert props["area"][i] == stats[l, 4]
         assert tuple(props["bbox"][i]) == (stats[l, 1], stats[l, 0], stats[l, 1] + stats[l, 3], stats[l, 0] + stats[l, 2])
         assert abs(props["centroid_col"][i] - cent[l, 0]) < 1e-9 and abs(props["centroid_row"][i] - cent[l, 1]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# fixtures from tests/golden/make_golden_n3.py (unmodified reference)
+@pytest.fixture(scope="module")
+def gold_n3():
+    return np.load(GOLD / "reference_outputs_n3.npz")
+
+
+@pytest.mark.parametrize("tag", ["u8", "u16"])
+def test_n3_steps(gold_n3, tag):
+    g = gold_n3
+    noise, ramp, bgr = g[f"in_noise_{tag}"], g[f"in_ramp_{tag}"], g[f"in_bgr_{tag}"]
+    for s in (1.0, 0.35, 2.3):
+        eq(O.sharpen(noise, s), g[f"sharpen_{s}_{tag}"], f"Sharpen {s}")
+        eq(O.sharpen(ramp, s), g[f"sharpen_ramp_{s}_{tag}"], f"Sharpen ramp {s}")
+    for ch in ("R", "G", "B", "All"):
+        eq(O.select_channel(bgr, ch), g[f"select_{ch}_{tag}"], f"SelectChannel {ch}")
+    eq(O.select_channel(noise, "All"), g[f"select_gray_All_{tag}"], "SelectChannel gray All")
+    eq(O.select_channel(noise, "G"), g[f"select_gray_G_{tag}"], "SelectChannel gray G")
+    for k in (1, 3, 5, 7):
+        for name, img in (("noise", noise), ("ramp", ramp)):
+            eq(O.sobel_magnitude(img, k), g[f"sobel{k}_{name}_{tag}"], f"Sobel {k} {name}")
+            eq(O.laplacian_abs(img, k), g[f"laplacian{k}_{name}_{tag}"], f"Laplacian {k} {name}")
+    eq(O.sobel_magnitude(O.bgr2gray(bgr), 3), g[f"sobel3_bgr_{tag}"], "Sobel colour")
+    for bd in (0, 1, 5, 22, 23, 40):
+        eq(O.remove_border_regions(noise, bd), g[f"border{bd}_{tag}"], f"Border Removal {bd}")
+    eq(O.remove_border_regions(bgr, 5), g[f"border5_bgr_{tag}"], "Border Removal colour")
+    # Prewitt: cv2.magnitude(float32) goes through an approximate square root in the wheel's IPP
+    # build (cv2.magnitude(123, 0) == 122.99999), so exact squares can truncate one lower.  The
+    # restatement uses the correctly rounded root; tolerance = north_star's 1 LSB on uint8 output.
+    for name, img in (("noise", noise), ("ramp", ramp)):
+        got, want = O.prewitt_magnitude(img), g[f"prewitt_{name}_{tag}"]
+        diff = got.astype(np.int16) - want.astype(np.int16)
+        assert diff.min() >= 0 and diff.max() <= 1, f"Prewitt {name}"
+        assert (diff != 0).mean() < 0.01
+
+
+def test_n3_channel_means(gold_n3):
+    for ch in ("RG", "GB", "BR"):
+        eq(O.select_channel(gold_n3["in_bgr_u8"], ch), gold_n3[f"select_{ch}_u8"], f"SelectChannel {ch}")
+    with pytest.raises(TypeError):
+        O.select_channel(gold_n3["in_bgr_u16"], "RG")

@@ -193,3 +193,77 @@ def test_full_size_preprocess_properties(backend):
     eq(backend.to_host(g)[1005:1295], O.gaussian_fixed(band, 11, 0.0)[5:295], "gaussian band")
     # CLAHE at full size against the oracle (tile 512^2, clip 8)
     eq(backend.to_host(c), O.clahe(backend.to_host(g), 2.0, (8, 8)), "clahe 4096")
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) N3 steps through the plugin's process(): reference outputs (make_golden_n3.py)
+@pytest.fixture(scope="module")
+def gold_n3():
+    return np.load(GOLD / "reference_outputs_n3.npz")
+
+
+@pytest.mark.parametrize("tag", ["u8", "u16"])
+def test_n3_plugin_steps_match_reference_outputs(backend, gold_n3, mods, tag):
+    g = gold_n3
+    noise, ramp, bgr = g[f"in_noise_{tag}"], g[f"in_ramp_{tag}"], g[f"in_bgr_{tag}"]
+    for s in (1.0, 0.35, 2.3):
+        eq(mods["Sharpen"].process(noise, strength=s), g[f"sharpen_{s}_{tag}"], f"Sharpen {s}")
+        eq(mods["Sharpen"].process(ramp, strength=s), g[f"sharpen_ramp_{s}_{tag}"], f"Sharpen ramp {s}")
+    for ch in ("R", "G", "B", "All"):
+        eq(mods["SelectChannel"].process(bgr, channel=ch), g[f"select_{ch}_{tag}"], f"SelectChannel {ch}")
+    eq(mods["SelectChannel"].process(noise, channel="All"), g[f"select_gray_All_{tag}"], "SelectChannel gray All")
+    eq(mods["SelectChannel"].process(noise, channel="G"), g[f"select_gray_G_{tag}"], "SelectChannel gray G")
+    for k in (1, 3, 5, 7):
+        for name, img in (("noise", noise), ("ramp", ramp)):
+            eq(mods["Sobel"].process(img, ksize=k), g[f"sobel{k}_{name}_{tag}"], f"Sobel {k} {name}")
+            eq(mods["Laplacian"].process(img, ksize=k), g[f"laplacian{k}_{name}_{tag}"], f"Laplacian {k} {name}")
+    eq(mods["Sobel"].process(bgr, ksize=3), g[f"sobel3_bgr_{tag}"], "Sobel colour")
+    for bd in (0, 1, 5, 22, 23, 40):
+        eq(mods["Border Removal"].process(noise, border_distance=bd), g[f"border{bd}_{tag}"], f"Border Removal {bd}")
+    eq(mods["Border Removal"].process(bgr, border_distance=5), g[f"border5_bgr_{tag}"], "Border Removal colour")
+    for name, img in (("noise", noise), ("ramp", ramp)):
+        # bit-exact against the oracle; <= 1 LSB against the reference (approximate float32 sqrt in
+        # the wheel's cv2.magnitude, see tests/test_golden.py)
+        got = mods["Prewitt"].process(img)
+        eq(got, O.prewitt_magnitude(img), f"Prewitt {name} vs oracle")
+        diff = got.astype(np.int16) - g[f"prewitt_{name}_{tag}"].astype(np.int16)
+        assert diff.min() >= 0 and diff.max() <= 1
+
+
+def test_n3_channel_means_and_limits(backend, gold_n3, mods):
+    from yamimageprocessor_b200.host.steps import UnsupportedOnDevice
+
+    for ch in ("RG", "GB", "BR"):
+        eq(mods["SelectChannel"].process(gold_n3["in_bgr_u8"], channel=ch), gold_n3[f"select_{ch}_u8"], f"SelectChannel {ch}")
+    with pytest.raises(TypeError):
+        mods["SelectChannel"].process(gold_n3["in_bgr_u16"], channel="RG")
+    with pytest.raises(UnsupportedOnDevice):
+        mods["Sobel"].process(gold_n3["in_noise_u8"], ksize=9)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16])
+def test_n3_ops_vs_oracle_shapes(backend, dt):
+    rng = np.random.default_rng(5)
+    hi = 255 if dt == np.uint8 else 65535
+    for shape in ((64, 64), (33, 71), (130, 257), (3, 5), (1, 40), (200, 33)):
+        a = rng.integers(0, hi + 1, shape, dtype=dt)
+        b = rng.integers(0, hi + 1, shape, dtype=dt)
+        x = backend.to_device(a)
+        for al, be_, ga in ((2.0, -1.0, 0.0), (3.3, -2.3, 0.0), (0.25, 0.6, 7.5)):
+            eq(backend.to_host(backend.add_weighted(x, al, backend.to_device(b), be_, ga)), O.add_weighted(a, al, b, be_, ga), "add_weighted")
+        eq(backend.to_host(backend.sharpen(x, 1.5)), O.sharpen(a, 1.5), f"sharpen {shape}")
+        for k in (1, 3, 5, 7):
+            eq(backend.to_host(backend.edge_filter(x, "sobel", k)), O.sobel_magnitude(a, k), f"sobel {k} {shape}")
+            eq(backend.to_host(backend.edge_filter(x, "laplacian", k)), O.laplacian_abs(a, k), f"laplacian {k} {shape}")
+        small = (a >> (4 if dt == np.uint8 else 12)).astype(dt)
+        eq(backend.to_host(backend.edge_filter(backend.to_device(small), "sobel", 3)), O.sobel_magnitude(small, 3), "sobel small")
+        eq(backend.to_host(backend.edge_filter(backend.to_device(small), "prewitt", 3)), O.prewitt_magnitude(small), "prewitt small")
+        for bd in (0, 1, 2, 16, 100):
+            eq(backend.to_host(backend.border_clear(x, bd)), O.remove_border_regions(a, bd), f"border {bd} {shape}")
+    stack = rng.integers(0, hi + 1, (3, 40, 56), dtype=dt)
+    got = backend.to_host(backend.edge_filter(backend.to_device(stack), "sobel", 3))
+    for i in range(3):
+        eq(got[i], O.sobel_magnitude(stack[i], 3), "sobel stack")
+    got = backend.to_host(backend.border_clear(backend.to_device(stack), 4))
+    for i in range(3):
+        eq(got[i], O.remove_border_regions(stack[i], 4), "border stack")

@@ -122,3 +122,35 @@ def test_ccl_and_region_props(rng):
             assert tuple(rp["bbox"][i]) == (stats[lab, 1], stats[lab, 0], stats[lab, 1] + stats[lab, 3], stats[lab, 0] + stats[lab, 2])
             assert abs(rp["centroid_col"][i] - cent[lab, 0]) < 1e-9 and abs(rp["centroid_row"][i] - cent[lab, 1]) < 1e-9
             assert abs(rp["mean_intensity"][i] - inten[l4 == lab].mean()) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) N3 steps
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_add_weighted_and_sharpen(rng, dt):
+    for shp in ((33, 71), (64, 64), (5, 9)):
+        a, b = rnd(rng, shp, dt), rnd(rng, shp, dt)
+        for al, be, ga in ((2.0, -1.0, 0.0), (3.3, -2.3, 0.0), (1.1, -0.1, 0.0), (0.25, 0.6, 7.5), (1.7, -0.7, -3.0)):
+            eq(O.add_weighted(a, al, b, be, ga), cv2.addWeighted(a, al, b, be, ga))
+        for s in (1.0, 0.35, 2.3, 5.0, 0.0):
+            want = cv2.addWeighted(a, 1 + s, cv2.GaussianBlur(a, (0, 0), sigmaX=3), -s, 0)
+            eq(O.sharpen(a, s), want)
+
+
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_edge_operators(rng, dt):
+    for shp in ((33, 71), (64, 64), (7, 5), (3, 3)):
+        g = rnd(rng, shp, dt)
+        for k in (1, 3, 5, 7):
+            gx, gy = cv2.Sobel(g, cv2.CV_64F, 1, 0, ksize=k), cv2.Sobel(g, cv2.CV_64F, 0, 1, ksize=k)
+            eq(O.sobel_magnitude(g, k), np.uint8(np.clip(cv2.magnitude(gx, gy), 0, 255)))
+            eq(O.laplacian_abs(g, k), np.uint8(np.clip(np.abs(cv2.Laplacian(g, cv2.CV_64F, ksize=k)), 0, 255)))
+        # low-amplitude input so that the clip at 255 does not hide the arithmetic
+        small = (g >> (4 if dt == U8 else 12)).astype(dt)
+        gx, gy = cv2.Sobel(small, cv2.CV_64F, 1, 0, ksize=3), cv2.Sobel(small, cv2.CV_64F, 0, 1, ksize=3)
+        eq(O.sobel_magnitude(small, 3), np.uint8(np.clip(cv2.magnitude(gx, gy), 0, 255)))
+        kx = np.array([[1, 0, -1], [1, 0, -1], [1, 0, -1]])
+        fx, fy = cv2.filter2D(small, -1, kx), cv2.filter2D(small, -1, kx.T)
+        want = np.uint8(np.clip(cv2.magnitude(fx.astype(np.float32), fy.astype(np.float32)), 0, 255))
+        diff = O.prewitt_magnitude(small).astype(np.int16) - want.astype(np.int16)
+        assert diff.min() >= 0 and diff.max() <= 1  # approximate float32 sqrt inside cv2.magnitude (see test_golden.py)

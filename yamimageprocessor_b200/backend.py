@@ -412,6 +412,71 @@ class Backend:
                                                                       C.cast(C.byref(t), C.c_void_p)))
         return int(t.value)
 
+    # ------------------------------------------------------------------ remaining menu steps
+    def add_weighted(self, a, alpha: float, b, beta: float, gamma: float = 0.0):
+        torch = _torch()
+        a = self._check(a, ndim=(2, 3), dtypes=(torch.uint8, torch.uint16), name="a")
+        b = self._check(b, ndim=(2, 3), dtypes=(a.dtype,), name="b")
+        if a.shape != b.shape:
+            raise ValueError("add_weighted: operands must have the same shape")
+        out = torch.empty_like(a)
+        self._call("yam_add_weighted", self._p(a), self._p(b), self._p(out), int(a.numel()), _dtype_code(a),
+                   float(alpha), float(beta), float(gamma))
+        return out
+
+    def sharpen(self, img, strength: float = 1.0):
+        """Unsharp mask: addWeighted(img, 1+s, GaussianBlur(img, (0,0), sigma=3), -s)."""
+        blurred = self.gaussian(img, 0, 3.0)
+        return self.add_weighted(img, 1.0 + float(strength), blurred, -float(strength), 0.0)
+
+    def select_channel(self, img, channel: str = "All"):
+        """SelectChannelModule: img is (h, w, 3) BGR or a (h, w) plane (replicated to BGR first)."""
+        torch = _torch()
+        modes = {"B": 0, "G": 1, "R": 2, "RG": 3, "GB": 4, "BR": 5}
+        img = self._check(img, ndim=(2, 3), dtypes=(torch.uint8, torch.uint16), name="image")
+        if img.dim() == 3 and img.shape[-1] != 3:
+            raise ValueError("select_channel expects an interleaved 3-channel image or a single plane")
+        if channel not in modes:
+            if img.dim() == 3:
+                return img
+            out = torch.empty(tuple(img.shape) + (3,), dtype=img.dtype, device=self.device)
+            self._call("yam_gray2bgr", self._p(img), self._p(out), int(img.numel()), _dtype_code(img))
+            return out
+        if img.dim() == 2:
+            if modes[channel] <= 2:
+                return img.clone()
+            if img.dtype != torch.uint8:
+                raise TypeError("two-channel means are defined for uint8 only")
+            return img.clone()  # (x + x) >> 1 == x
+        if modes[channel] > 2 and img.dtype != torch.uint8:
+            raise TypeError("two-channel means are defined for uint8 only")
+        out = torch.empty(tuple(img.shape[:2]), dtype=img.dtype, device=self.device)
+        self._call("yam_select_channel", self._p(img), self._p(out), int(out.numel()), _dtype_code(img), modes[channel])
+        return out
+
+    def border_clear(self, img, border_distance: int):
+        """remove_border_regions: (h, w), (n, h, w) planes or (h, w, 3) colour."""
+        torch = _torch()
+        img = self._check(img, ndim=(2, 3), dtypes=(torch.uint8, torch.uint16), name="image")
+        out = torch.empty_like(img)
+        if img.dim() == 3 and img.shape[-1] in (3, 4):
+            n, h, w, ch = 1, int(img.shape[0]), int(img.shape[1]), int(img.shape[2])
+        else:
+            n, h, w = self._nhw(img)
+            ch = 1
+        self._call("yam_border_clear", self._p(img), self._p(out), n, h, w, ch, _dtype_code(img), int(border_distance))
+        return out
+
+    def edge_filter(self, img, kind: str, ksize: int = 3):
+        """Sobel / Prewitt / Laplacian magnitude image (uint8), kind in {'sobel','prewitt','laplacian'}."""
+        torch = _torch()
+        kinds = {"sobel": 0, "prewitt": 1, "laplacian": 2}
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        self._call("yam_edge_filter", self._p(img), self._p(out), n, h, w, _dtype_code(img), kinds[kind], int(ksize))
+        return out
+
     # ------------------------------------------------------------------ fused binary segmentation
     def adaptive_threshold_bits(self, img, block_size: int = 11, C_: float = 2.0):
         """Adaptive threshold with a 1-bit-per-pixel result: int32 tensor (..., h, ceil(w/32))."""

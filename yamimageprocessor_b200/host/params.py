@@ -84,6 +84,8 @@ MODULE_PARAMS: Dict[str, Dict[str, ParamSpec]] = {
         "method": ParamSpec("Gaussian", "str", choices=("Gaussian", "Median", "Bilateral")),
         "ksize": ParamSpec(5, "int", 1, 15, coerce_fn=ensure_odd),
     },
+    "Sharpen": {"strength": ParamSpec(1.0, "float", 0.0, 5.0, decimals=2)},
+    "SelectChannel": {"channel": ParamSpec("All", "str", choices=("All", "R", "G", "B", "RG", "GB", "BR"))},
     # ---- north_star ops the reference lacks (same third-party library, cv2 semantics) ----
     "CLAHE": {
         "clip_limit": ParamSpec(2.0, "float", 0.0, 40.0, decimals=2),
@@ -99,6 +101,10 @@ MODULE_PARAMS: Dict[str, Dict[str, ParamSpec]] = {
         "block_size": ParamSpec(11, "int", 3, 101, coerce_fn=ensure_odd),
         "C": ParamSpec(2, "int", -10, 10),
     },
+    "Sobel": {"ksize": ParamSpec(3, "int", 1, 31, coerce_fn=ensure_odd)},
+    "Prewitt": {},
+    "Laplacian": {"ksize": ParamSpec(3, "int", 1, 31, coerce_fn=ensure_odd)},
+    "Border Removal": {"border_distance": ParamSpec(100, "int", 0, 999)},
     "Opening": _morph(),
     "Closing": _morph(),
     "Dilation": _morph(),

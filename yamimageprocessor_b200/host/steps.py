@@ -1,7 +1,7 @@
 """Step name -> device operator table.
 
 Keys are the step names the reference uses (they enter the ``pipeline_cache`` signatures):
-preprocessing module identifiers (``modules/preprocessing.py:46,66,89,113,134``), segmentation
+preprocessing module identifiers (``modules/preprocessing.py:46,66,89,113,134,161,182``), segmentation
 method names (``processing/segmentation_pipeline.py:84-184``) and the extraction name
 ``Region Properties`` (``processing/extraction_pipeline.py:77-127``), plus the north_star ops the
 reference lacks (``CLAHE``, ``BoxFilter``, ``HistogramEqualization``, ``ConnectedComponents``).
@@ -103,6 +103,30 @@ def adaptive(be: Backend, t, p):
     return be.adaptive_threshold(_gray(be, t), int(p.get("block_size", 11)), float(p.get("C", 2)))
 
 
+def sharpen(be: Backend, t, p):
+    return be.sharpen(_plane_only(t, "Sharpen"), float(p.get("strength", 1.0)))
+
+
+def select_channel(be: Backend, t, p):
+    if t.dim() == 3 and t.shape[-1] != 3:
+        raise UnsupportedOnDevice("SelectChannel: stacks / 4-channel images are outside the GPU hot path")
+    return be.select_channel(t, str(p.get("channel", "All")))
+
+
+def _edge(kind: str) -> Callable:
+    def run(be: Backend, t, p):
+        ksize = int(p.get("ksize", 3))
+        if ksize not in (1, 3, 5, 7):
+            raise UnsupportedOnDevice(f"{kind}: ksize {ksize} exceeds the exact integer range of the device kernel (1, 3, 5, 7)")
+        return be.edge_filter(_gray(be, t), kind, ksize)
+
+    return run
+
+
+def border_removal(be: Backend, t, p):
+    return be.border_clear(t, int(p.get("border_distance", 100)))
+
+
 def _morph(op: int) -> Callable:
     def run(be: Backend, t, p):
         return be.morph(
@@ -145,6 +169,12 @@ DEVICE_STEPS: Dict[str, Callable] = {
     "CLAHE": clahe,
     "BoxFilter": box_filter,
     "HistogramEqualization": histogram_equalization,
+    "Sharpen": sharpen,
+    "SelectChannel": select_channel,
+    "Sobel": _edge("sobel"),
+    "Prewitt": _edge("prewitt"),
+    "Laplacian": _edge("laplacian"),
+    "Border Removal": border_removal,
     "Global": global_threshold,
     "Otsu": otsu,
     "Adaptive": adaptive,

@@ -90,6 +90,10 @@ IntensityNormalizationModule = _module("IntensityNormalization", "Intensity Norm
                                        "cv2.normalize NORM_MINMAX (modules/preprocessing.py:119-123).")
 NoiseReductionModule = _module("NoiseReduction", "Noise Reduction", ModuleStage.PREPROCESSING,
                                "Gaussian / median denoising (modules/preprocessing.py:140-150).")
+SharpenModule = _module("Sharpen", "Sharpen", ModuleStage.PREPROCESSING,
+                        "Unsharp mask: addWeighted(img, 1+s, GaussianBlur(sigma 3), -s) (modules/preprocessing.py:167-171).")
+SelectChannelModule = _module("SelectChannel", "Select Color Channel", ModuleStage.PREPROCESSING,
+                              "Channel pick / two-channel mean (modules/preprocessing.py:188-209).")
 ClaheModule = _module("CLAHE", "CLAHE", ModuleStage.PREPROCESSING,
                       "cv2.createCLAHE(clip_limit,(tile_grid_x,tile_grid_y)).apply (north_star op).")
 BoxFilterModule = _module("BoxFilter", "Box Filter", ModuleStage.PREPROCESSING,
@@ -103,6 +107,14 @@ OtsuThresholdModule = _module("Otsu", "Otsu Threshold", ModuleStage.SEGMENTATION
                               "cv2.threshold BINARY+OTSU (core/segmentation.py:145-148).", _SEG)
 AdaptiveThresholdModule = _module("Adaptive", "Adaptive Threshold", ModuleStage.SEGMENTATION,
                                   "cv2.adaptiveThreshold GAUSSIAN_C (core/segmentation.py:91-94).", _SEG)
+SobelModule = _module("Sobel", "Sobel", ModuleStage.SEGMENTATION,
+                      "Sobel gradient magnitude (core/segmentation.py:150-155).", _SEG)
+PrewittModule = _module("Prewitt", "Prewitt", ModuleStage.SEGMENTATION,
+                        "Prewitt gradient magnitude (core/segmentation.py:157-164).", _SEG)
+LaplacianModule = _module("Laplacian", "Laplacian", ModuleStage.SEGMENTATION,
+                          "Absolute Laplacian (core/segmentation.py:166-169).", _SEG)
+BorderRemovalModule = _module("Border Removal", "Border Removal", ModuleStage.SEGMENTATION,
+                              "Clear a frame of border pixels (core/segmentation.py:316-325).", _SEG)
 OpeningModule = _module("Opening", "Opening", ModuleStage.SEGMENTATION,
                         "cv2.morphologyEx OPEN (core/segmentation.py:264-275).", _SEG)
 ClosingModule = _module("Closing", "Closing", ModuleStage.SEGMENTATION,
@@ -122,12 +134,18 @@ MODULE_CLASSES = (
     GammaCorrectionModule,
     IntensityNormalizationModule,
     NoiseReductionModule,
+    SharpenModule,
+    SelectChannelModule,
     ClaheModule,
     BoxFilterModule,
     HistogramEqualizationModule,
     GlobalThresholdModule,
     OtsuThresholdModule,
     AdaptiveThresholdModule,
+    SobelModule,
+    PrewittModule,
+    LaplacianModule,
+    BorderRemovalModule,
     OpeningModule,
     ClosingModule,
     DilationModule,
