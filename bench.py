@@ -59,6 +59,22 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _traffic(op_name: str, px: int):
+    """Measured DRAM bytes per launch of an operator (ncu --set full, profiles/r01_traffic_c2.json);
+    None when no capture exists for this operator at this frame size."""
+    p = ROOT / "profiles" / "r01_traffic_c2.json"
+    try:
+        d = json.loads(p.read_text())
+    except Exception:
+        return None
+    if int(d.get("pixels", 0)) != int(px):
+        return None
+    for key, row in d.get("ops", {}).items():
+        if op_name.startswith(key):
+            return int(row["dram_read_bytes"]) + int(row["dram_write_bytes"])
+    return None
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm
 def _cpu_pipeline(workload: str):
@@ -362,7 +378,7 @@ def run_gpu_mosaic(args):
     import torch.distributed as dist
 
     from yamimageprocessor_b200.backend import get_backend
-    from yamimageprocessor_b200.host import mosaic
+    from yamimageprocessor_b200.host import ingest, mosaic
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -425,8 +441,12 @@ def run_gpu_mosaic(args):
     barrier()
     t0 = time.perf_counter()
     res = mosaic.run_local_strips(be, shape, local, world > 1, p, with_props=False,
-                                  device_sources=[be.to_device(h) for h in host_strips])
-    outs = [(be.to_host(r.labels), be.to_host(r.otsu_mask)) for r in res]
+                                  device_sources=[ingest.upload_rows(be, h, 0, h.shape[0]) for h in host_strips])
+    outs = []
+    for r in res:  # results land in fresh pageable arrays, streamed through the pinned ring
+        lab = np.empty(tuple(r.labels.shape), np.int32)
+        msk = np.empty(tuple(r.otsu_mask.shape), np.uint16)
+        outs.append((ingest.download_into(be, r.labels, lab), ingest.download_into(be, r.otsu_mask, msk)))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = sum(h.nbytes for h in host_strips)
@@ -459,7 +479,8 @@ def run_gpu_mosaic(args):
                          "traffic": None, "peak_source": peak_src, "per_gpu": True},
             "cpu_baseline": cpu,
             "e2e": {"value": px / MP / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "api": "host.mosaic.run_local_strips(host strips) -> labels + Otsu mask"},
+                    "d2h_bytes_per_step": int(d2h),
+                    "api": "host.ingest.upload_rows(pageable strips) -> host.mosaic.run_local_strips -> host.ingest.download_into(fresh pageable arrays): labels + Otsu mask"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -604,7 +625,9 @@ def run_gpu(args):
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": None,
+                "traffic": _traffic(dom[0], px_per_rank),
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "algorithmic_bytes": int(px_per_rank * dom[1]),
                 "peak_source": peak_src,
                 "pipeline_achieved": pipe_achieved,
                 "pipeline_frac": pipe_achieved / peak,

@@ -267,3 +267,45 @@ def test_n3_ops_vs_oracle_shapes(backend, dt):
     got = backend.to_host(backend.border_clear(backend.to_device(stack), 4))
     for i in range(3):
         eq(got[i], O.remove_border_regions(stack[i], 4), "border stack")
+
+
+# ---------------------------------------------------------------------------------------------
+# streaming ingest / egress through the pinned ring
+def test_ingest_roundtrip_memmap(backend, tmp_path):
+    from yamimageprocessor_b200.host import ingest
+
+    rng = np.random.default_rng(9)
+    for dt, shape in ((np.uint16, (3000, 4100)), (np.uint8, (517, 1031)), (np.int32, (40, 70000))):
+        a = rng.integers(0, 200, shape).astype(dt)
+        path = tmp_path / f"src_{np.dtype(dt).name}.npy"
+        np.save(path, a)
+        mm = np.load(path, mmap_mode="r")          # what core/tiled_image.py:85-96 hands out
+        for r0, r1 in ((0, shape[0]), (7, shape[0] - 5), (shape[0] // 2, shape[0] // 2 + 1)):
+            t = ingest.upload_rows(backend, mm, r0, r1)
+            assert tuple(t.shape) == (r1 - r0, shape[1])
+            assert np.array_equal(backend.to_host(t), a[r0:r1])
+            out = np.empty((r1 - r0, shape[1]), dt)
+            got = ingest.download_into(backend, t, out)
+            assert got is out and np.array_equal(out, a[r0:r1])
+    with pytest.raises(ValueError):
+        ingest.upload_rows(backend, np.zeros((4, 4), np.uint8), 2, 9)
+    with pytest.raises(ValueError):
+        ingest.download_into(backend, backend.to_device(np.zeros((4, 4), np.uint8)), np.zeros((4, 5), np.uint8))
+
+
+def test_mosaic_from_memmap_source(backend, tmp_path):
+    """run_strip streams its rows from an .npy memmap and equals the dense run."""
+    from yamimageprocessor_b200.host import mosaic
+
+    p = mosaic.MosaicParams()
+    frame = synth.nuclei(512, 384, seed=21)
+    path = tmp_path / "mosaic.npy"
+    np.save(path, frame)
+    mm = np.load(path, mmap_mode="r")
+    res = mosaic.run_emulated(backend, mm, 2, p)
+    x = backend.to_device(frame)
+    c = backend.clahe(backend.gaussian(x, p.gauss_ksize, 0.0), p.clip_limit, p.tile_grid)
+    labels, counts = backend.segment_fused(c, p.block_size, p.C, p.morph_ksize, 1)
+    got = np.concatenate([backend.to_host(r.labels) for r in res])
+    assert np.array_equal(got, backend.to_host(labels))
+    assert res[0].n_components == int(backend.to_host(counts)[0])

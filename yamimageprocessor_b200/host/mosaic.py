@@ -27,7 +27,7 @@ from typing import Any, Optional, Sequence, Tuple
 import numpy as np
 
 from ..backend import Backend
-from . import sharding
+from . import ingest, sharding
 
 
 @dataclass
@@ -239,7 +239,8 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     a0, a1 = max(0, c0 - halo_seg), min(H, c1 + halo_seg)      # rows of CLAHE output needed
     r0, r1 = max(0, a0 - hg), min(H, a1 + hg)                  # rows of input needed
 
-    x = device_source if device_source is not None else be.to_device(np.ascontiguousarray(source[r0:r1]))
+    # rows are streamed from the (memmap) source through a pinned ring, gather overlapping the DMA
+    x = device_source if device_source is not None else ingest.upload_rows(be, source, r0, r1)
     g = be.gaussian(x, p.gauss_ksize, 0.0)                     # exact on [a0, a1): artificial edges are hg rows away
     mark("gaussian")
 
