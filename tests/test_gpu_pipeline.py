@@ -309,3 +309,62 @@ def test_mosaic_from_memmap_source(backend, tmp_path):
     got = np.concatenate([backend.to_host(r.labels) for r in res])
     assert np.array_equal(got, backend.to_host(labels))
     assert res[0].n_components == int(backend.to_host(counts)[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident PipelineCache tier
+def test_device_pipeline_cache(backend, mods):
+    import threading
+
+    from yamimageprocessor_b200.host import cache_keys
+    from yamimageprocessor_b200.host.device_cache import DevicePipelineCache, OperationCancelled
+    from yamimageprocessor_b200.host.executor import B200Executor
+
+    def step(name, **params):
+        s = mods[name].create_pipeline_step()
+        s.enabled = True
+        s.params.update(params)
+        return s
+
+    frame = synth.nuclei(256, 320, seed=31)
+    ex = B200Executor(backend)
+    cache = DevicePipelineCache(ex)
+    sid = cache.register_source(frame)
+    assert sid == cache_keys.source_id(frame)
+    steps = [step("NoiseReduction", method="Gaussian", ksize=11), step("CLAHE"), step("Otsu")]
+    r1 = cache.compute(sid, frame, steps)
+    assert r1.computed == (0, 1, 2)
+    want = O.otsu_threshold(O.clahe(O.gaussian_fixed(frame, 11, 0.0), 2.0, (8, 8)), 255)[1]
+    eq(r1.image, want, "cached pipeline result")
+    assert r1.final_signature == cache_keys.predict(sid, steps)[0]
+    assert [s["signature"] for s in r1.metadata["steps"]] == [r.signature for r in r1.steps]
+    # identical request: no kernel runs, only the final download
+    backend.launch_count(reset=True)
+    r2 = cache.compute(sid, None, steps)
+    assert r2.computed == () and backend.launch_count() == 0
+    eq(r2.image, want, "cache hit")
+    # changing the last step re-runs only that step
+    steps2 = steps[:2] + [step("Global", threshold=20000)]
+    r3 = cache.compute(sid, None, steps2)
+    assert r3.computed == (2,)
+    eq(r3.image, O.threshold_binary(O.clahe(O.gaussian_fixed(frame, 11, 0.0), 2.0, (8, 8)), 20000, 255), "partial re-run")
+    # a disabled step keeps its slot in the signature chain but does not run
+    steps3 = [steps[0], step("CLAHE"), steps[2]]
+    steps3[1].enabled = False
+    r4 = cache.compute(sid, None, steps3)
+    assert r4.computed == (2,) and r4.final_signature != r1.final_signature
+    eq(r4.image, O.otsu_threshold(O.gaussian_fixed(frame, 11, 0.0), 255)[1], "disabled step")
+    # cancellation is checked between steps; eviction keeps the cache under its budget
+    ev = threading.Event()
+    ev.set()
+    with pytest.raises(OperationCancelled):
+        cache.compute(sid, None, [step("BoxFilter", ksize=5)], cancel_event=ev)
+    small = DevicePipelineCache(ex, max_bytes=frame.nbytes * 2)
+    sid2 = small.register_source(frame)
+    small.compute(sid2, frame, steps)
+    assert small.resident_bytes <= frame.nbytes * 2
+    small.discard_cache(sid2)
+    assert small.resident_bytes == 0
+    eq(small.compute(sid2, frame, steps).image, want, "recompute after discard")
+    with pytest.raises(KeyError):
+        cache.compute(sid, None, [step("Otsu"), type("S", (), {"name": "K-Means", "enabled": True, "params": {}})()])

@@ -49,6 +49,12 @@ class StepRecord:
     signature: str
     index: int
 
+    def to_dict(self) -> Dict[str, Any]:
+        """Same record the reference persists (processing/pipeline_cache.py:70-77)."""
+        return {"name": self.name, "enabled": self.enabled,
+                "params": {k: normalise_value(v) for k, v in self.params.items()},
+                "signature": self.signature, "index": self.index}
+
 
 def predict(source: str, steps: Sequence[Any]) -> Tuple[str, List[StepRecord]]:
     """Final signature and per-step records for ``steps`` applied to ``source``."""
