@@ -240,7 +240,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             return [
                 ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
                 ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-                ("otsu_threshold_u16 (hist + host scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+                ("otsu_threshold_u16 (hist + exact fp64 scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ]
         return x, run, ops
 
@@ -304,7 +304,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         return [
             ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
             ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-            ("otsu_threshold_u16 (hist + host scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+            ("otsu_threshold_u16 (hist + exact fp64 scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(c, 11, 2)),
             ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
             ("ccl_label_bits (scan, tile, border, rank, frame_offsets, final_warp)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),

@@ -72,6 +72,12 @@ int yam_ctx_set_stream(yam_ctx* ctx, void* stream);
 int yam_ctx_synchronize(yam_ctx* ctx);
 /* counts kernel launches issued through this context since the last reset (bench "gpu_launches") */
 int64_t yam_ctx_launch_count(yam_ctx* ctx, int reset);
+
+/* Host worker threads this process may use for the sequential fp64 Otsu scans (default: all
+ * hardware threads, at most 32).  One process per GPU: pass cores / local_world_size so that 8
+ * ranks on one box do not oversubscribe; the staged device scan takes over when the host share
+ * would be slower (see yam_otsu_threshold).  Returns the value now in effect. */
+int yam_set_host_threads(int threads);
 /* raw device memory + copies for hosts that do not bring their own allocator */
 int yam_malloc(yam_ctx* ctx, int64_t bytes, void** out);
 int yam_free(yam_ctx* ctx, void* ptr);

@@ -253,6 +253,45 @@ def test_otsu_stack_device_scan(backend, rng):
     assert_same(host(backend, out), np.stack([O.threshold_binary(p, tt, 255) for p, tt in zip(a, want_t)]), "otsu stack")
 
 
+def test_otsu_stack_staged_scan_distributions(backend, rng):
+    """>= 8 frames: the staged device scan (q1 chain, reciprocals, corrected-quotient mu1 chain,
+    parallel sigma with bit-for-bit verification) must return the reference thresholds for every
+    kind of histogram: dense, sparse plateaus (12-bit data), constant, two-level, near-empty tails."""
+    frames = []
+    shape = (96, 128)
+    frames += [blobs(rng, shape, U16), rnd(rng, shape, U16)]
+    frames.append((rnd(rng, shape, U16) >> 4).astype(U16) << 4)                 # plateaus: every 16th bin
+    frames.append((rng.integers(0, 4096, shape)).astype(U16))                    # 12-bit camera data
+    frames.append(np.full(shape, 777, U16))                                      # constant: no valid split
+    two = np.full(shape, 1000, U16); two[::2] = 50000; frames.append(two)        # two levels
+    tail = np.full(shape, 30000, U16); tail[0, :3] = 65535; tail[1, :2] = 0; frames.append(tail)  # q1 ~ eps tails
+    frames.append(np.clip(rng.normal(20000, 300, shape), 0, 65535).astype(U16))  # narrow dense peak
+    frames.append(np.zeros(shape, U16))
+    frames += [blobs(rng, shape, U16) for _ in range(70 - len(frames))]          # crosses the 64-frame chunk
+    a = np.stack(frames)
+    want_t = [O.otsu_value(p) for p in a]
+    backend.lib.yam_set_host_threads(1)  # one host thread: the cost model picks the staged device scan
+    try:
+        t, out = backend.otsu_threshold(dev(backend, a), 255)
+        assert host(backend, t).tolist() == want_t
+        got = host(backend, out)
+    finally:
+        backend.lib.yam_set_host_threads(backend.host_threads)
+    for i in (0, 2, 4, 6, 8, 69):
+        assert_same(got[i], O.threshold_binary(a[i], want_t[i], 255), f"otsu staged frame {i}")
+    # plenty of host threads: the same stack through the pooled host scans
+    backend.lib.yam_set_host_threads(32)
+    try:
+        t, _ = backend.otsu_threshold(dev(backend, a), 255)
+        assert host(backend, t).tolist() == want_t
+    finally:
+        backend.lib.yam_set_host_threads(backend.host_threads)
+    # the same frames one by one go through the host scan: both paths agree
+    for i in (2, 3, 6):
+        t1, _ = backend.otsu_threshold(dev(backend, a[i]), 255)
+        assert int(host(backend, t1)[0]) == want_t[i]
+
+
 def test_equalize_hist(backend, rng):
     for img in (rnd(rng, (64, 80), U8), blobs(rng, (130, 257), U8), np.full((9, 9), 7, U8)):
         got = host(backend, backend.equalize_hist(dev(backend, img)))

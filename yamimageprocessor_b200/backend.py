@@ -74,6 +74,11 @@ class Backend:
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
         handle = C.c_void_p()
+        # one process per GPU: this process's share of the host cores (torchrun exports LOCAL_WORLD_SIZE)
+        import os
+
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        self.host_threads = int(self.lib.yam_set_host_threads(max(1, (os.cpu_count() or 4) // local_world)))
         _lib.check("yam_ctx_create", self.lib.yam_ctx_create(self.device_index, C.byref(handle)))
         self._ctx = handle
         self._pinned: Dict[Tuple[str, int], object] = {}

@@ -12,6 +12,7 @@
 // 8-bit histograms use per-warp privatised 256-bin shared histograms.
 #include <math.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -177,6 +178,283 @@ __global__ void otsu_scan_kernel(const unsigned long long* __restrict__ hist, in
         }
     }
     out[f] = best_i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged Otsu scan for stacks of 16-bit histograms.  The recurrence
+//     mu1 <- (mu1 * q1_prev + i * p_i) / q1_i,   q1_i = q1_prev + p_i
+// has two sequential chains.  q1 does not depend on mu1, so it runs one tile ahead (one DADD per
+// bin), the reciprocals 1/q1_i of a finished tile are computed by all lanes in parallel, and the mu1
+// chain replaces the division by a multiplication with two FMA corrections (q = n*r;
+// q += fma(-q, q1, n) * r): five dependent fp64 operations per bin instead of a ~100-cycle division.  The last stage evaluates sigma in
+// parallel AND re-derives every mu1_i from its stored predecessor with a true IEEE division; a
+// single differing bit makes the block redo its frame with the plain sequential loop, so the
+// result is the reference's by construction, whatever the corrected quotient did.
+struct OtsuMeta {
+    double scale, mu;
+    int first, last;  // occupied bin range; first < 0: empty frame
+};
+constexpr double kOtsuEps = 1.1920928955078125e-07;  // FLT_EPSILON
+
+__global__ void __launch_bounds__(1024) otsu_prep_kernel(const unsigned long long* __restrict__ hist, int bins,
+                                                         OtsuMeta* __restrict__ meta) {
+    __shared__ unsigned long long s_tot[32], s_mom[32];
+    __shared__ int s_first[32], s_last[32];
+    const unsigned long long* h = hist + (int64_t)blockIdx.x * bins;
+    unsigned long long tot = 0, mom = 0;
+    int first = 0x7fffffff, last = -1;
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+        const unsigned long long c = h[i];
+        if (c) {
+            tot += c;
+            mom += c * (unsigned long long)i;  // integer-valued: exact in any order (as in the double sum)
+            first = min(first, i);
+            last = max(last, i);
+        }
+    }
+    tot = yam_warp_sum(tot);
+    mom = yam_warp_sum(mom);
+    first = yam_warp_min(first);
+    last = yam_warp_max(last);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_tot[warp] = tot; s_mom[warp] = mom; s_first[warp] = first; s_last[warp] = last;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        tot = lane < nw ? s_tot[lane] : 0ull;
+        mom = lane < nw ? s_mom[lane] : 0ull;
+        first = lane < nw ? s_first[lane] : 0x7fffffff;
+        last = lane < nw ? s_last[lane] : -1;
+        tot = yam_warp_sum(tot);
+        mom = yam_warp_sum(mom);
+        first = yam_warp_min(first);
+        last = yam_warp_max(last);
+        if (lane == 0) {
+            OtsuMeta m;
+            m.first = last < 0 ? -1 : first;
+            m.last = last;
+            m.scale = last < 0 ? 0.0 : __ddiv_rn(1.0, (double)tot);
+            m.mu = __dmul_rn((double)mom, m.scale);
+            meta[blockIdx.x] = m;
+        }
+    }
+}
+
+// Both chains in one warp per frame.  Per tile of kOtsuTile bins: all lanes stage p_i = h_i * scale
+// of the NEXT tile, the reciprocals 1/q1_i and i * p_i of the CURRENT tile in shared memory (coalesced
+// loads: nothing on a chain waits for DRAM); lane 0 then advances the q1 chain over the next tile
+// and the mu1 chain over the current tile in ONE loop, so the single DADD of the q1 chain issues in
+// the shadow of the five dependent operations of the mu1 chain; all lanes write the tiles back.
+constexpr int kOtsuTile = 512;
+
+__global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long* __restrict__ hist, int bins,
+                                                        const OtsuMeta* __restrict__ meta,
+                                                        double* __restrict__ q1arr, double* __restrict__ mu1arr) {
+    __shared__ double s_pn[kOtsuTile], s_qn[kOtsuTile];                     // next tile: p in, q1 out
+    __shared__ double s_q[kOtsuTile], s_r[kOtsuTile], s_ip[kOtsuTile], s_m[kOtsuTile];  // current tile
+    const OtsuMeta m = meta[blockIdx.x];
+    if (m.first < 0) return;
+    const int64_t base = (int64_t)blockIdx.x * bins;
+    const unsigned long long* h = hist + base;
+    const int lane = threadIdx.x;
+    const int span = m.last + 1 - m.first;
+    const int tiles = (span + kOtsuTile - 1) / kOtsuTile;
+    double q1 = 0.0, mu1 = 0.0, qprev = 0.0;
+    // prologue: q1 chain over tile 0
+    {
+        const int cnt = min(kOtsuTile, span);
+        for (int k = lane; k < cnt; k += 32) s_pn[k] = __dmul_rn((double)h[m.first + k], m.scale);
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < cnt; k++) {
+                q1 = __dadd_rn(q1, s_pn[k]);
+                s_qn[k] = q1;
+            }
+        __syncwarp();
+    }
+    for (int b = 0; b < tiles; b++) {
+        const int t0 = m.first + b * kOtsuTile;
+        const int cnt = min(kOtsuTile, m.last + 1 - t0);
+        const int cnt_next = b + 1 < tiles ? min(kOtsuTile, m.last + 1 - (t0 + kOtsuTile)) : 0;
+        for (int k = lane; k < cnt; k += 32) {
+            const int i = t0 + k;
+            const double q = s_qn[k];
+            const double q2 = __dsub_rn(1.0, q);
+            const bool skip = fmin(q, q2) < kOtsuEps || fmax(q, q2) > 1.0 - kOtsuEps;
+            s_q[k] = q;
+            s_r[k] = skip ? 0.0 : __drcp_rn(q);   // 0 marks a bin the reference skips
+            s_ip[k] = __dmul_rn((double)i, __dmul_rn((double)h[i], m.scale));
+            q1arr[base + i] = q;
+        }
+        __syncwarp();  // s_qn has been consumed: the next tile may overwrite s_pn / s_qn
+        for (int k = lane; k < cnt_next; k += 32) s_pn[k] = __dmul_rn((double)h[t0 + kOtsuTile + k], m.scale);
+        __syncwarp();
+        if (lane == 0) {
+            // blocks of 4 bins with the operands preloaded: shared-memory latency stays off the chains
+            auto mu_step = [&](int k, double q, double r, double ip) {
+                // mu1 = (mu1 * q1_prev + i p_i) / q1_i with the corrected quotient
+                const double t = __dmul_rn(mu1, qprev);
+                const double nsum = __dadd_rn(t, ip);
+                const double qq = __dmul_rn(nsum, r);
+                const double e = __fma_rn(-qq, q, nsum);
+                const double quo = __fma_rn(e, r, qq);
+                mu1 = r == 0.0 ? t : quo;  // skipped bin: the reference multiplied by q1 before `continue`
+                s_m[k] = mu1;
+                qprev = q;
+            };
+            const int both = (cnt < cnt_next ? cnt : cnt_next) & ~3;
+            int k = 0;
+            for (; k < both; k += 4) {
+                double q[4], r[4], ip[4], pn[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    q[j] = s_q[k + j];
+                    r[j] = s_r[k + j];
+                    ip[j] = s_ip[k + j];
+                    pn[j] = s_pn[k + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    q1 = __dadd_rn(q1, pn[j]);   // q1 chain, one tile ahead
+                    s_qn[k + j] = q1;
+                    mu_step(k + j, q[j], r[j], ip[j]);
+                }
+            }
+            for (int kk = k; kk < cnt_next; kk++) {
+                q1 = __dadd_rn(q1, s_pn[kk]);
+                s_qn[kk] = q1;
+            }
+            for (; k + 4 <= cnt; k += 4) {
+                double q[4], r[4], ip[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    q[j] = s_q[k + j];
+                    r[j] = s_r[k + j];
+                    ip[j] = s_ip[k + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) mu_step(k + j, q[j], r[j], ip[j]);
+            }
+            for (; k < cnt; k++) mu_step(k, s_q[k], s_r[k], s_ip[k]);
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) mu1arr[base + t0 + k] = s_m[k];
+        __syncwarp();
+    }
+}
+
+__device__ int otsu_scan_exact(const unsigned long long* __restrict__ h, int bins) {
+    double total = 0.0, mu = 0.0;
+    for (int i = 0; i < bins; i++) {
+        const double c = (double)h[i];
+        total = __dadd_rn(total, c);
+        mu = __dadd_rn(mu, __dmul_rn((double)i, c));
+    }
+    if (!(total > 0.0)) return 0;
+    const double scale = __ddiv_rn(1.0, total);
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0.0, q1 = 0.0, best = 0.0;
+    int best_i = 0;
+    for (int i = 0; i < bins; i++) {
+        const double p = __dmul_rn((double)h[i], scale);
+        mu1 = __dmul_rn(mu1, q1);
+        q1 = __dadd_rn(q1, p);
+        const double q2 = __dsub_rn(1.0, q1);
+        if (fmin(q1, q2) < kOtsuEps || fmax(q1, q2) > 1.0 - kOtsuEps) continue;
+        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p)), q1);
+        const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > best) {
+            best = sigma;
+            best_i = i;
+        }
+    }
+    return best_i;
+}
+
+// parallel: verify the chain bit for bit, evaluate sigma, first maximum
+__global__ void __launch_bounds__(1024) otsu_sigma_kernel(const unsigned long long* __restrict__ hist, int bins,
+                                                          const OtsuMeta* __restrict__ meta,
+                                                          const double* __restrict__ q1arr,
+                                                          const double* __restrict__ mu1arr, int32_t* __restrict__ out,
+                                                          int* __restrict__ redo_count) {
+    __shared__ double s_best[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_fail;
+    const OtsuMeta m = meta[blockIdx.x];
+    if (m.first < 0) {
+        if (threadIdx.x == 0) out[blockIdx.x] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * bins;
+    const unsigned long long* h = hist + base;
+    double best = 0.0;
+    int best_i = 0;
+    bool fail = false;
+    for (int i = m.first + threadIdx.x; i <= m.last; i += blockDim.x) {
+        const double q1 = q1arr[base + i], mu1 = mu1arr[base + i];
+        const double qprev = i > m.first ? q1arr[base + i - 1] : 0.0;
+        const double mprev = i > m.first ? mu1arr[base + i - 1] : 0.0;
+        const double q2 = __dsub_rn(1.0, q1);
+        const bool skip = fmin(q1, q2) < kOtsuEps || fmax(q1, q2) > 1.0 - kOtsuEps;
+        const double t = __dmul_rn(mprev, qprev);
+        const double p = __dmul_rn((double)h[i], m.scale);
+        const double expect = skip ? t : __ddiv_rn(__dadd_rn(t, __dmul_rn((double)i, p)), q1);
+        if (__double_as_longlong(expect) != __double_as_longlong(mu1)) fail = true;
+        if (skip) continue;
+        const double mu2 = __ddiv_rn(__dsub_rn(m.mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > best) {  // ascending i per thread: strict '>' keeps the first maximum
+            best = sigma;
+            best_i = i;
+        }
+    }
+    if (fail) s_fail = 1;
+    // (sigma, index) max-reduce; equal sigma -> smaller index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) {
+            best = ob;
+            best_i = oi;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_best[warp] = best;
+        s_idx[warp] = best_i;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? s_best[lane] : 0.0;
+        best_i = lane < nw ? s_idx[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ob > best || (ob == best && oi < best_i)) {
+                best = ob;
+                best_i = oi;
+            }
+        }
+        if (lane == 0) {
+            if (s_fail) {
+                atomicAdd(redo_count, 1);
+                best_i = otsu_scan_exact(h, bins);
+            } else if (!(best > 0.0)) {
+                best_i = 0;
+            }
+            out[blockIdx.x] = best_i;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -562,6 +840,17 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const T* __restrict__ 
 // Otsu recurrence on host threads (the fp64 recurrence is sequential per frame).  One process-wide
 // pool of workers, created on first use and never torn down (its threads sleep on a condition
 // variable); callers hand in frames as their histograms arrive and wait for the batch at the end.
+static std::atomic<int> g_host_threads{0};  // 0 = not configured: hardware_concurrency()
+
+static int host_threads() {
+    int t = g_host_threads.load();
+    if (t <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        t = hw == 0 ? 4 : (int)hw;
+    }
+    return t < 32 ? t : 32;
+}
+
 class ScanPool {
 public:
     static ScanPool& instance() {
@@ -596,10 +885,8 @@ public:
 
 private:
     ScanPool() {
-        unsigned hw = std::thread::hardware_concurrency();
-        if (hw == 0) hw = 4;
-        const unsigned nt = (hw < 32 ? hw : 32) - 1;  // the caller is the last worker
-        for (unsigned i = 0; i < nt; i++) {
+        const int nt = host_threads() - 1;  // the caller is the last worker
+        for (int i = 0; i < nt; i++) {
             try {
                 std::thread([this] { run(); }).detach();
             } catch (...) {
@@ -820,6 +1107,11 @@ int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, in
 
 extern "C" {
 
+int yam_set_host_threads(int threads) {
+    if (threads > 0) g_host_threads.store(threads);
+    return host_threads();
+}
+
 int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype, uint64_t* hist_dev) {
     if (int rc = yam_enter(ctx)) return rc;
     YAM_REQUIRE(src && hist_dev && n > 0 && h > 0 && w > 0 && n <= 65535, "histogram: bad arguments");
@@ -836,17 +1128,49 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "otsu: image side too large");
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
     const size_t hist_bytes = sizeof(unsigned long long) * bins * n;
+    // 16-bit stacks: staged scan on the device (~2.75 ms for any number of frames up to kStageChunk, no
+    // read-back, nothing for the host cores to fight over when 8 ranks share a box) when that beats
+    // this process's share of the host cores.
+    // Fewer frames: the fp64 recurrence is sequential per frame, 65536 dependent divisions take
+    // ~0.4 ms on a CPU core, so the histograms are read back and scanned on host threads.
+    // 256-bin histograms are scanned by one device thread per frame.
+    // Cost model (measured on B200 boxes): 0.45 ms per frame and host thread + 12 us read-back per
+    // frame on the host, 2.75 ms per launch group of <= kStageChunk frames on the device.
+    constexpr int64_t kDeviceScanFrames = 8, kStageChunk = 256;
+    const int64_t ht = host_threads();
+    const double host_ms = (double)((n + ht - 1) / ht) * 0.45 + (double)n * 0.012;
+    const double dev_ms = (double)((n + kStageChunk - 1) / kStageChunk) * 2.75;
+    const bool staged_scan = (dtype == YAM_U16) && n >= kDeviceScanFrames && dev_ms < host_ms;
+    const bool host_scan = (dtype == YAM_U16) && !staged_scan;
+    const int64_t nf_max = n < kStageChunk ? n : kStageChunk;
+    const size_t arr_bytes = yam_align_up(sizeof(double) * bins * nf_max, 256);
+    const size_t hist_block = yam_align_up(yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256) +
+                                               sizeof(uint32_t) * bins * n, 256);
+    const size_t stage_block = staged_scan ? 2 * arr_bytes + yam_align_up(sizeof(OtsuMeta) * nf_max, 256) + 256 : 0;
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256) +
-                                      sizeof(uint32_t) * bins * n, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, hist_block + stage_block, &scratch)) return rc;
     unsigned long long* hist = (unsigned long long*)scratch;
     int32_t* t_dev = thresh_dev ? thresh_dev : (int32_t*)((char*)scratch + yam_align_up(hist_bytes, 256));
     if (int rc = hist_into(ctx, src, n, h, w, dtype, hist)) return rc;
-    // scan: the fp64 recurrence is sequential per frame.  65536 dependent divisions take ~0.3 ms on
-    // a CPU core and ~6 ms on one GPU thread, so 16-bit histograms are scanned on host threads
-    // (chunks of <= 64 frames through a pinned buffer); 256-bin histograms stay on the device.
-    const bool host_scan = (dtype == YAM_U16);
-    if (host_scan) {
+    if (staged_scan) {
+        const int64_t chunk = kStageChunk;
+        char* sp = (char*)scratch + hist_block;
+        double* q1arr = (double*)sp; sp += arr_bytes;
+        double* mu1arr = (double*)sp; sp += arr_bytes;
+        OtsuMeta* meta = (OtsuMeta*)sp; sp += yam_align_up(sizeof(OtsuMeta) * nf_max, 256);
+        int* redo = (int*)sp;
+        YAM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
+        for (int64_t f0 = 0; f0 < n; f0 += chunk) {
+            const unsigned nf = (unsigned)((n - f0) < chunk ? (n - f0) : chunk);
+            const unsigned long long* hc = hist + f0 * bins;
+            otsu_prep_kernel<<<nf, 1024, 0, ctx->stream>>>(hc, bins, meta);
+            YAM_LAUNCHED(ctx);
+            otsu_chain_kernel<<<nf, 32, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr);
+            YAM_LAUNCHED(ctx);
+            otsu_sigma_kernel<<<nf, 1024, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr, t_dev + f0, redo);
+            YAM_LAUNCHED(ctx);
+        }
+    } else if (host_scan) {
         // Read-back in chunks of <= 64 frames through a pinned buffer, 8 frames per copy; each copy is
         // followed by an event, and the frames of a copy are handed to the worker pool as soon as
         // its event fires, so the scans overlap the remaining copies.
@@ -917,7 +1241,7 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     if (dst) {
         if (int rc = yam_threshold_dev(ctx, src, dst, n, h * w, dtype, t_dev, maxval)) return rc;
     }
-    if (thresh_host && !host_scan) {
+    if (thresh_host && !host_scan) {  // staged and 8-bit scans leave the thresholds on the device
         YAM_CUDA(cudaMemcpyAsync(thresh_host, t_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
         YAM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
