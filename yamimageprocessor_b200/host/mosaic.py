@@ -251,21 +251,30 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     c_core = c[c0 - a0: c1 - a0]
     mark("clahe")
 
-    # Otsu on the global histogram
+    # Otsu on the global histogram.  The fp64 scan runs on the host (sequential recurrence); it is
+    # overlapped with the segmentation kernels, which do not depend on it: the (all-reduced)
+    # histogram is read back asynchronously, the segmentation is enqueued, THEN the host scans.
     hist = be.histogram(c_core)[0]
     if comm is not None:
         comm.all_reduce(hist, "sum")
-        t = comm.once(lambda: be.otsu_from_histogram(be.to_host(hist)))
-    else:
-        t = be.otsu_from_histogram(be.to_host(hist))
-    otsu_mask = be.threshold(c_core, float(t), 255)
-    mark("otsu")
+    hist_host = torch.empty(hist.shape, dtype=hist.dtype, pin_memory=True)
+    hist_host.copy_(hist, non_blocking=True)
+    hist_ready = torch.cuda.Event()
+    hist_ready.record()
 
     # segmentation on the extended rows, cropped to the core
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
     # cropping whole rows of the packed mask is a view, not a copy)
     bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
     labels, counts = be.ccl_label_bits(bits[c0 - a0: c1 - a0], W)
+
+    def scan():
+        hist_ready.synchronize()
+        return be.otsu_from_histogram(hist_host.numpy())
+
+    t = comm.once(scan) if comm is not None else scan()
+    otsu_mask = be.threshold(c_core, float(t), 255)
+    mark("otsu")
     n_local = int(be.to_host(counts)[0])
     mark("segment")
 
