@@ -397,6 +397,13 @@ def run_gpu_mosaic(args):
     tiles = [synth.nuclei(tile, tile, seed=100 + i) for i in range(4)]
     shape = _Shape(size, size)
     p = mosaic.MosaicParams()
+    trace_marks = []
+    if os.environ.get("YAM_MOSAIC_TRACE") and rank == 0:
+        # diagnostics: phase end times of rank 0's strips (adds a device sync per phase; not for reported numbers)
+        def _trace(name, strip):
+            torch.cuda.synchronize()
+            trace_marks.append((time.perf_counter(), strip, name))
+        p.trace = _trace
     host_strips, dev_strips = [], []
     for li in range(local):
         s = rank * local + li
@@ -428,10 +435,18 @@ def run_gpu_mosaic(args):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        t_step = time.perf_counter()
+        trace_marks.clear()
         res = step(dev_strips)
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
+        if p.trace is not None:
+            last = t_step
+            for tm, strip, name in sorted(trace_marks):
+                sys.stderr.write(f"[trace] +{1e3 * (tm - last):7.2f} ms strip {strip} {name}\n")
+                last = tm
+            sys.stderr.write(f"[trace] step total {1e3 * (time.perf_counter() - t_step):.2f} ms\n")
         del res
     barrier()
     launches = be.launch_count()

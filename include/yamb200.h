@@ -191,6 +191,22 @@ int yam_clahe_apply(yam_ctx* ctx, const void* src, void* dst, int64_t rows, int6
 int yam_ccl_label(yam_ctx* ctx, const void* mask, int32_t* labels, int64_t n, int64_t h, int64_t w,
                   int32_t* counts_dev, int32_t* counts_host);
 
+/* The same labelling in two steps, for callers that renumber before the labels are written (the
+ * row-strip mosaic: strip-local labels become global labels after the cross-strip merge, SURVEY.md
+ * 8e) -- the label image is then written ONCE instead of written, re-read and rewritten:
+ *   resolve   everything up to the per-segment roots and their labels, kept in a caller-owned
+ *             workspace of yam_ccl_workspace_bytes() bytes (256-byte aligned device memory);
+ *             counts_dev[n] receives the component counts;
+ *   emit_rows writes the labels of rows [row_begin, row_end) (rows of the n*h stacked rows) to
+ *             `labels` (pointing at the first pixel of row_begin); remap_dev (optional, single
+ *             frame): label = remap_dev[local label], remap_dev[0] = 0. */
+int64_t yam_ccl_workspace_bytes(yam_ctx* ctx, int64_t n, int64_t h, int64_t w);
+int yam_ccl_resolve_bits(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, void* workspace,
+                         int32_t* counts_dev);
+int yam_ccl_emit_rows(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w,
+                      const void* workspace, const int32_t* remap_dev, int64_t row_begin, int64_t row_end,
+                      int32_t* labels);
+
 /* labels[i] = remap_dev[labels[i]] for labels in (0, remap_size); used by the cross-strip label merge */
 int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev,
                 int64_t remap_size);

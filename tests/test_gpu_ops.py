@@ -417,6 +417,27 @@ def test_ccl_stack_multi_tile(backend, rng):
         assert_same(got[i], want, f"ccl stack frame {i}")
 
 
+def test_ccl_resolve_emit_split(backend, rng):
+    """resolve + emit == one-shot labelling; row ranges and remap tables are applied while writing."""
+    for shape in ((70, 96), (45, 1100), (130, 257)):
+        m = _ccl_case(rng, shape, 0.35)
+        n_want, want = O.ccl_label(m)
+        wpr = (shape[1] + 31) // 32
+        padded = np.zeros((shape[0], wpr * 32), np.uint8)
+        padded[:, : shape[1]] = m > 0
+        bits_np = np.packbits(padded.reshape(shape[0], wpr, 32), axis=2, bitorder="little").view(np.uint32).reshape(shape[0], wpr)
+        bits = dev(backend, bits_np.view(np.int32))
+        ws, counts = backend.ccl_resolve_bits(bits, shape[1])
+        assert int(host(backend, counts)[0]) == n_want
+        assert_same(host(backend, backend.ccl_emit(bits, shape[1], ws)), want, f"emit all {shape}")
+        assert_same(host(backend, backend.ccl_emit(bits, shape[1], ws, rows=(0, 1))), want[0:1], "first row")
+        assert_same(host(backend, backend.ccl_emit(bits, shape[1], ws, rows=(shape[0] - 1, shape[0]))), want[-1:], "last row")
+        assert_same(host(backend, backend.ccl_emit(bits, shape[1], ws, rows=(7, 30))), want[7:30], "row range")
+        remap = np.concatenate([[0], rng.permutation(n_want) + 1000]).astype(np.int32)
+        got = host(backend, backend.ccl_emit(bits, shape[1], ws, remap=dev(backend, remap)))
+        assert_same(got, remap[want], f"emit with remap {shape}")
+
+
 def test_ccl_stack(backend, rng):
     m = np.stack([_ccl_case(rng, (70, 96), d) for d in (0.2, 0.5, 0.0, 0.8)])
     labels, counts = backend.ccl_label(dev(backend, m))

@@ -526,6 +526,43 @@ class Backend:
         self._call("yam_ccl_label_bits", self._p(bits), self._p(labels), n, h, int(width), self._p(counts), None)
         return labels, counts
 
+    def ccl_resolve_bits(self, bits, width: int):
+        """First half of ``ccl_label_bits``: returns ``(workspace, counts)``; ``ccl_emit`` writes labels
+        from the workspace, optionally renumbered through a remap table (cross-strip merge)."""
+        torch = _torch()
+        bits = self._check(bits, dtypes=(torch.int32,), name="bits")
+        n, h, wpr = self._nhw(bits)
+        if wpr != (int(width) + 31) // 32:
+            raise ValueError("bits tensor does not match the image width")
+        nbytes = int(self.lib.yam_ccl_workspace_bytes(self._ctx, n, h, int(width)))
+        if nbytes < 0:
+            _lib.check("yam_ccl_workspace_bytes", -1)
+        workspace = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._call("yam_ccl_resolve_bits", self._p(bits), n, h, int(width), self._p(workspace), self._p(counts))
+        return workspace, counts
+
+    def ccl_emit(self, bits, width: int, workspace, remap=None, rows: Optional[Tuple[int, int]] = None):
+        """Labels of rows ``[rows[0], rows[1])`` (default: all) of a resolved mask; ``remap`` (int32,
+        entry 0 = 0) maps strip-local to global labels while they are written."""
+        torch = _torch()
+        bits = self._check(bits, dtypes=(torch.int32,), name="bits")
+        n, h, wpr = self._nhw(bits)
+        r0, r1 = (0, n * h) if rows is None else (int(rows[0]), int(rows[1]))
+        if rows is None:
+            shape = (h, int(width)) if bits.dim() == 2 else (n, h, int(width))
+        else:
+            shape = (r1 - r0, int(width))
+        labels = torch.empty(shape, dtype=torch.int32, device=self.device)
+        rptr = None
+        if remap is not None:
+            remap = self._check(remap, ndim=(1,), dtypes=(torch.int32,), name="remap")
+            rptr = self._p(remap)
+        if r1 > r0:
+            self._call("yam_ccl_emit_rows", self._p(bits), n, h, int(width), self._p(workspace), rptr, r0, r1,
+                       self._p(labels))
+        return labels
+
     def segment_fused(self, img, block_size: int = 11, C_: float = 2.0, morph_ksize: int = 5, iterations: int = 1):
         """adaptive threshold -> open -> close (rectangular) -> connected components, the mask never
         leaving its 1-bit-per-pixel form.  Same labels as the unfused chain."""

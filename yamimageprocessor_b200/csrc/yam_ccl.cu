@@ -681,14 +681,17 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
                                                                   const uint32_t* __restrict__ nbase,
                                                                   const uint32_t* __restrict__ frame_off, CclGeom g,
                                                                   const int* __restrict__ P,
-                                                                  int32_t* __restrict__ labels) {
+                                                                  int32_t* __restrict__ labels,
+                                                                  const int32_t* __restrict__ remap,
+                                                                  int64_t word_begin, int64_t word_end) {
+    // words [word_begin, word_end) are written; labels points at the pixel of word_begin
     const int lane = threadIdx.x & 31;
-    const int64_t warp_base = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
-    if (warp_base >= g.total_words) return;
+    const int64_t warp_base = word_begin + ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+    if (warp_base >= word_end) return;
     const int64_t gw = warp_base + lane;
-    const uint32_t b = gw < g.total_words ? __ldg(bits + gw) : 0u;
-    int4* dst = reinterpret_cast<int4*>(labels + warp_base * 32);
-    const int valid_words = g.total_words - warp_base < 32 ? (int)(g.total_words - warp_base) : 32;
+    const uint32_t b = gw < word_end ? __ldg(bits + gw) : 0u;
+    int4* dst = reinterpret_cast<int4*>(labels + (warp_base - word_begin) * 32);
+    const int valid_words = word_end - warp_base < 32 ? (int)(word_end - warp_base) : 32;
     if (!__any_sync(0xffffffffu, b != 0u)) {
 #pragma unroll
         for (int it = 0; it < 8; it++)
@@ -707,6 +710,10 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
         if (v1 >= 0) v1 = __ldg(P + v1);
         l0 = -v0 - off;
         l1 = -v1 - off;
+        if (remap) {  // strip-local label -> global label (cross-strip merge)
+            l0 = __ldg(remap + l0);
+            if (nseg > 1) l1 = __ldg(remap + l1);
+        }
     }
     // bits that belong to the second (or a later) segment
     const uint32_t later = starts & (starts - 1u);
@@ -732,7 +739,7 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
         if (!skip) __stcs(dst + it * 32 + lane, out);
     }
     if (many) {
-        int32_t* d = labels + gw * 32;
+        int32_t* d = labels + (gw - word_begin) * 32;
         uint32_t st = starts;
         int cur = 0, k = 0;
 #pragma unroll 1
@@ -741,6 +748,7 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
                 int v = __ldg(P + base + k);
                 if (v >= 0) v = __ldg(P + v);
                 cur = -v - off;
+                if (remap) cur = __ldg(remap + cur);
                 k++;
             }
             d[i] = ((b >> i) & 1u) ? cur : 0;
@@ -752,9 +760,11 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
                                                              const uint32_t* __restrict__ nbase,
                                                              const uint32_t* __restrict__ frame_off, CclGeom g,
                                                              const int* __restrict__ P, int32_t* __restrict__ labels,
-                                                             bool vec_ok) {
-    const int64_t t_base = (int64_t)blockIdx.x * (kThreads * kFinalIter) + threadIdx.x;
-    const int64_t total_nibbles = g.total_words * 8;
+                                                             bool vec_ok, const int32_t* __restrict__ remap,
+                                                             int64_t word_begin, int64_t word_end) {
+    // words [word_begin, word_end) (whole rows) are written; labels points at the first pixel of that range
+    const int64_t t_base = word_begin * 8 + (int64_t)blockIdx.x * (kThreads * kFinalIter) + threadIdx.x;
+    const int64_t total_nibbles = word_end * 8;
     uint32_t bw[kFinalIter];
 #pragma unroll
     for (int it = 0; it < kFinalIter; it++) {
@@ -780,7 +790,11 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
             int v1 = second ? __ldg(P + base + k0 + 1) : -1;
             if (v0 >= 0) v0 = __ldg(P + v0);   // non-root: its root holds -(label)
             if (v1 >= 0) v1 = __ldg(P + v1);
-            const int l0 = -v0 - off, l1 = -v1 - off;
+            int l0 = -v0 - off, l1 = -v1 - off;
+            if (remap) {
+                l0 = __ldg(remap + l0);
+                if (second) l1 = __ldg(remap + l1);
+            }
             out.x = (nib & 1u) ? ((second & 1u) ? l1 : l0) : 0;
             out.y = (nib & 2u) ? ((second & 2u) ? l1 : l0) : 0;
             out.z = (nib & 4u) ? ((second & 4u) ? l1 : l0) : 0;
@@ -790,7 +804,7 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
             const int64_t row_id = gw / g.wpr;
             const int x = (int)(gw - row_id * g.wpr) * 32 + 4 * q;
             if (x >= g.w) continue;
-            int32_t* d = labels + row_id * (int64_t)g.w + x;
+            int32_t* d = labels + (row_id - word_begin / g.wpr) * (int64_t)g.w + x;
             if (vec_ok && x + 4 <= g.w) {
                 __stcs(reinterpret_cast<int4*>(d), out);
             } else {
@@ -1050,85 +1064,139 @@ int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* rem
     return YAM_OK;
 }
 
-static int ccl_label_impl(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, int32_t* labels, int64_t n,
-                          int64_t h, int64_t w, int32_t* counts_dev, int32_t* counts_host) {
-    if (int rc = yam_enter(ctx)) return rc;
-    YAM_REQUIRE((mask || bits_in) && labels && n > 0 && h > 0 && w > 0, "ccl: bad arguments");
+// Workspace of one labelling job (caller-owned device memory, or the context scratch for the
+// one-shot entry points): everything `emit` needs survives between `resolve` and `emit`.
+struct CclWorkspace {
+    uint32_t* bits_scratch;  // packed mask when the input was a byte mask
+    uint32_t* nbase;
+    char* sync_base;
+    size_t sync_bytes;
+    unsigned int* tickets;
+    unsigned long long *statusA, *statusB;
+    uint32_t* chunk_excl;
+    uint32_t* frame_off;
+    uint32_t* totals;
+    int32_t* counts;
+    int* P;
+    size_t bytes;
+};
+
+static int ccl_geometry(int64_t n, int64_t h, int64_t w, CclGeom* g) {
+    YAM_REQUIRE(n > 0 && h > 0 && w > 0, "ccl: bad arguments");
     YAM_REQUIRE(n <= 65535, "ccl: at most 65535 frames per call");
-    CclGeom g;
-    g.h = (int)h;
-    g.w = (int)w;
-    g.wpr = (int)((w + 31) / 32);
-    g.words_per_frame = (int64_t)h * g.wpr;
-    g.total_words = g.words_per_frame * n;
-    g.frames = (int)n;
-    YAM_REQUIRE(g.words_per_frame * 32 < (1ll << 31), "ccl: frame too large for int32 labels (%lld x %lld)",
+    g->h = (int)h;
+    g->w = (int)w;
+    g->wpr = (int)((w + 31) / 32);
+    g->words_per_frame = (int64_t)h * g->wpr;
+    g->total_words = g->words_per_frame * n;
+    g->frames = (int)n;
+    YAM_REQUIRE(g->words_per_frame * 32 < (1ll << 31), "ccl: frame too large for int32 labels (%lld x %lld)",
                 (long long)h, (long long)w);
-    YAM_REQUIRE(g.total_words * 16 < (1ll << 31) && g.total_words < (1ll << 27),
-                "ccl: stack too large for one call (%lld words); split the stack", (long long)g.total_words);
+    YAM_REQUIRE(g->total_words * 16 < (1ll << 31) && g->total_words < (1ll << 27),
+                "ccl: stack too large for one call (%lld words); split the stack", (long long)g->total_words);
+    return YAM_OK;
+}
+
+// layout: bits | nbase | [tickets | statusA | statusB] | chunk_excl | frame_off | totals | counts | P
+static void ccl_layout(const CclGeom& g, int num_sms, char* base, CclWorkspace* ws) {
     const int64_t max_nodes = g.total_words * 16;  // at most 16 run segments per 32-pixel word
+    const int64_t scan_subs = (g.total_words + kScanSub - 1) / kScanSub;
+    const int64_t scan_chunks = scan_subs < num_sms ? scan_subs : num_sms;
+    const int64_t rank_subs = (max_nodes + kRankSub - 1) / kRankSub;
+    const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
+    const size_t sync_bytes = yam_align_up(256 + (size_t)(scan_chunks + num_sms) * 8, 256);
+    const size_t chunk_bytes = yam_align_up((size_t)rank_subs * 4, 256);
+    const size_t frame_bytes = yam_align_up((size_t)g.frames * 4, 256);
+    const size_t node_bytes = yam_align_up((size_t)max_nodes * 4, 256);
+    char* sp = base;
+    ws->bits_scratch = (uint32_t*)sp; sp += words_bytes;
+    ws->nbase = (uint32_t*)sp; sp += words_bytes;
+    ws->sync_base = sp;
+    ws->sync_bytes = sync_bytes;
+    ws->tickets = (unsigned int*)sp;                       // [0] scan, [1] rank
+    ws->statusA = (unsigned long long*)(sp + 256);
+    ws->statusB = ws->statusA + scan_chunks;
+    sp += sync_bytes;
+    ws->chunk_excl = (uint32_t*)sp; sp += chunk_bytes;
+    ws->frame_off = (uint32_t*)sp; sp += frame_bytes;
+    ws->totals = (uint32_t*)sp; sp += 256;                 // [0] nodes, [1] roots
+    ws->counts = (int32_t*)sp; sp += frame_bytes;
+    ws->P = (int*)sp; sp += node_bytes;
+    ws->bytes = (size_t)(sp - base);
+}
+
+// scan .. rank: after this the workspace holds, for every run segment, its root and the root's label
+static int ccl_resolve(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, const CclGeom& g, const CclWorkspace& ws,
+                       int32_t* counts) {
+    const int64_t n = g.frames;
     const int64_t scan_subs = (g.total_words + kScanSub - 1) / kScanSub;
     const int64_t scan_chunks = scan_subs < ctx->num_sms ? scan_subs : ctx->num_sms;
     const int64_t scan_per = (scan_subs + scan_chunks - 1) / scan_chunks * kScanSub;  // words per chunk
-    const int64_t rank_chunks = ctx->num_sms;                                        // status words
-    const int64_t rank_subs = (max_nodes + kRankSub - 1) / kRankSub;
-    // scratch: bits | nbase | [tickets | statusA | statusB] | chunk_excl | frame_off | totals | counts | P
-    const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
-    const size_t sync_bytes = yam_align_up(256 + (size_t)(scan_chunks + rank_chunks) * 8, 256);
-    const size_t chunk_bytes = yam_align_up((size_t)rank_subs * 4, 256);
-    const size_t frame_bytes = yam_align_up((size_t)n * 4, 256);
-    const size_t node_bytes = yam_align_up((size_t)max_nodes * 4, 256);
-    void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, 2 * words_bytes + sync_bytes + chunk_bytes + 2 * frame_bytes + 256 + node_bytes, &scratch)) return rc;
-    char* sp = (char*)scratch;
-    uint32_t* bits_scratch = (uint32_t*)sp; sp += words_bytes;
-    const uint32_t* bits = bits_in ? bits_in : bits_scratch;
-    uint32_t* nbase = (uint32_t*)sp; sp += words_bytes;
-    unsigned int* tickets = (unsigned int*)sp;                       // [0] scan, [1] rank
-    unsigned long long* statusA = (unsigned long long*)(sp + 256);
-    unsigned long long* statusB = statusA + scan_chunks;
-    char* sync_base = sp; sp += sync_bytes;
-    uint32_t* chunk_excl = (uint32_t*)sp; sp += chunk_bytes;
-    uint32_t* frame_off = (uint32_t*)sp; sp += frame_bytes;
-    uint32_t* totals = (uint32_t*)sp; sp += 256;                     // [0] nodes, [1] roots
-    int32_t* counts = counts_dev ? counts_dev : (int32_t*)sp; sp += frame_bytes;
-    int* P = (int*)sp;
-
-    YAM_CUDA(cudaMemsetAsync(sync_base, 0, sync_bytes, ctx->stream));
-    if (n == 1) YAM_CUDA(cudaMemsetAsync(frame_off, 0, sizeof(uint32_t), ctx->stream));
+    const uint32_t* bits = bits_in ? bits_in : ws.bits_scratch;
+    YAM_CUDA(cudaMemsetAsync(ws.sync_base, 0, ws.sync_bytes, ctx->stream));
+    if (n == 1) YAM_CUDA(cudaMemsetAsync(ws.frame_off, 0, sizeof(uint32_t), ctx->stream));
     const unsigned wblocks = (unsigned)((g.total_words + kThreads - 1) / kThreads);
     if (!bits_in) {
-        ccl_pack_kernel<<<wblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, bits_scratch);
+        ccl_pack_kernel<<<wblocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, g, ws.bits_scratch);
         YAM_LAUNCHED(ctx);
     }
-    ccl_scan_kernel<<<(unsigned)scan_chunks, kBigThreads, 0, ctx->stream>>>(bits, g.total_words, scan_per, nbase, statusA, tickets, totals);
+    ccl_scan_kernel<<<(unsigned)scan_chunks, kBigThreads, 0, ctx->stream>>>(bits, g.total_words, scan_per, ws.nbase, ws.statusA,
+                                                                          ws.tickets, ws.totals);
     YAM_LAUNCHED(ctx);
     const int tiles_x = (g.wpr + kTileC - 1) / kTileC, tiles_y = (g.h + kTileR - 1) / kTileR;
     const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
     YAM_REQUIRE(tiles < (1ll << 31), "ccl: too many tiles");
-    ccl_tile_kernel<<<(unsigned)tiles, kThreads, sizeof(TileSmem), ctx->stream>>>(bits, nbase, g, tiles_x, tiles_y, P);
+    ccl_tile_kernel<<<(unsigned)tiles, kThreads, sizeof(TileSmem), ctx->stream>>>(bits, ws.nbase, g, tiles_x, tiles_y, ws.P);
     YAM_LAUNCHED(ctx);
-    const int64_t na = (int64_t)tiles_y * n * g.wpr, nb = (int64_t)h * n * tiles_x * 2;
-    ccl_border_kernel<<<(unsigned)((na + nb + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(bits, nbase, g, tiles_x,
-                                                                                                  tiles_y, na, nb, P);
+    const int64_t na = (int64_t)tiles_y * n * g.wpr, nb = (int64_t)g.h * n * tiles_x * 2;
+    ccl_border_kernel<<<(unsigned)((na + nb + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(bits, ws.nbase, g, tiles_x,
+                                                                                                  tiles_y, na, nb, ws.P);
     YAM_LAUNCHED(ctx);
-    ccl_rank_kernel<<<(unsigned)rank_chunks, kBigThreads, 0, ctx->stream>>>(totals, P, statusB, tickets + 1, chunk_excl, totals + 1,
-                                                         n == 1 ? counts : nullptr);
+    ccl_rank_kernel<<<(unsigned)ctx->num_sms, kBigThreads, 0, ctx->stream>>>(ws.totals, ws.P, ws.statusB, ws.tickets + 1,
+                                                                            ws.chunk_excl, ws.totals + 1,
+                                                                            n == 1 ? counts : nullptr);
     YAM_LAUNCHED(ctx);
     if (n > 1) {
         ccl_frame_offsets_kernel<<<(unsigned)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(
-            nbase, g, totals, totals + 1, chunk_excl, P, frame_off, counts);
+            ws.nbase, g, ws.totals, ws.totals + 1, ws.chunk_excl, ws.P, ws.frame_off, counts);
         YAM_LAUNCHED(ctx);
     }
+    return YAM_OK;
+}
+
+// labels of the words [word_begin, word_end) (whole rows), optionally mapped through remap
+static int ccl_emit(yam_ctx* ctx, const uint32_t* bits, const CclGeom& g, const CclWorkspace& ws, int32_t* labels,
+                    const int32_t* remap, int64_t word_begin, int64_t word_end) {
+    const int64_t words = word_end - word_begin;
+    if (words <= 0) return YAM_OK;
     const bool lab_aligned = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
-    const unsigned fblocks = (unsigned)((g.total_words * 8 + kThreads * kFinalIter - 1) / (kThreads * kFinalIter));
     if ((g.w & 31) == 0 && lab_aligned) {
-        const unsigned wblocks32 = (unsigned)((g.total_words + kThreads - 1) / kThreads);  // 8 warps x 32 words
-        ccl_final_warp_kernel<<<wblocks32, kThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels);
-    } else
-        ccl_final_kernel<<<fblocks, kThreads, 0, ctx->stream>>>(bits, nbase, frame_off, g, P, labels,
-                                                                       lab_aligned && (g.w & 3) == 0);
+        const unsigned wblocks32 = (unsigned)((words + kThreads - 1) / kThreads);  // 8 warps x 32 words
+        ccl_final_warp_kernel<<<wblocks32, kThreads, 0, ctx->stream>>>(bits, ws.nbase, ws.frame_off, g, ws.P, labels, remap,
+                                                                      word_begin, word_end);
+    } else {
+        const unsigned fblocks = (unsigned)((words * 8 + kThreads * kFinalIter - 1) / (kThreads * kFinalIter));
+        ccl_final_kernel<<<fblocks, kThreads, 0, ctx->stream>>>(bits, ws.nbase, ws.frame_off, g, ws.P, labels,
+                                                                lab_aligned && (g.w & 3) == 0, remap, word_begin, word_end);
+    }
     YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+static int ccl_label_impl(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, int32_t* labels, int64_t n,
+                          int64_t h, int64_t w, int32_t* counts_dev, int32_t* counts_host) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE((mask || bits_in) && labels, "ccl: bad arguments");
+    CclGeom g;
+    if (int rc = ccl_geometry(n, h, w, &g)) return rc;
+    CclWorkspace ws;
+    ccl_layout(g, ctx->num_sms, nullptr, &ws);
+    void* scratch = nullptr;
+    if (int rc = yam_scratch(ctx, ws.bytes, &scratch)) return rc;
+    ccl_layout(g, ctx->num_sms, (char*)scratch, &ws);
+    int32_t* counts = counts_dev ? counts_dev : ws.counts;
+    if (int rc = ccl_resolve(ctx, mask, bits_in, g, ws, counts)) return rc;
+    if (int rc = ccl_emit(ctx, bits_in ? bits_in : ws.bits_scratch, g, ws, labels, nullptr, 0, g.total_words)) return rc;
     if (counts_host) {
         YAM_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
         YAM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1174,6 +1242,42 @@ static int region_props_impl(yam_ctx* ctx, const int32_t* labels, const void* in
                                                                   props, offsets_dev);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
+}
+
+int64_t yam_ccl_workspace_bytes(yam_ctx* ctx, int64_t n, int64_t h, int64_t w) {
+    if (!ctx) return -1;
+    CclGeom g;
+    if (ccl_geometry(n, h, w, &g)) return -1;
+    CclWorkspace ws;
+    ccl_layout(g, ctx->num_sms, nullptr, &ws);
+    return (int64_t)ws.bytes;
+}
+
+int yam_ccl_resolve_bits(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, void* workspace,
+                         int32_t* counts_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(bits && workspace && counts_dev, "ccl_resolve_bits: NULL argument");
+    YAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "ccl_resolve_bits: workspace must be 256-byte aligned");
+    CclGeom g;
+    if (int rc = ccl_geometry(n, h, w, &g)) return rc;
+    CclWorkspace ws;
+    ccl_layout(g, ctx->num_sms, (char*)workspace, &ws);
+    return ccl_resolve(ctx, nullptr, bits, g, ws, counts_dev);
+}
+
+int yam_ccl_emit_rows(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, const void* workspace,
+                      const int32_t* remap_dev, int64_t row_begin, int64_t row_end, int32_t* labels) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(bits && workspace && labels, "ccl_emit_rows: NULL argument");
+    CclGeom g;
+    if (int rc = ccl_geometry(n, h, w, &g)) return rc;
+    const int64_t total_rows = n * h;
+    YAM_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= total_rows, "ccl_emit_rows: bad row range [%lld, %lld)",
+                (long long)row_begin, (long long)row_end);
+    YAM_REQUIRE(!remap_dev || n == 1, "ccl_emit_rows: a remap table applies to a single frame");
+    CclWorkspace ws;
+    ccl_layout(g, ctx->num_sms, (char*)const_cast<void*>(workspace), &ws);
+    return ccl_emit(ctx, bits, g, ws, labels, remap_dev, row_begin * g.wpr, row_end * g.wpr);
 }
 
 int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t h,

@@ -10,8 +10,9 @@ path has no halo, ``SURVEY.md`` §0 fact 5):
   g (+ halo)            --CLAHE apply with GLOBAL geometry-->  c
   c core rows           --histogram--> all-reduce (65536 x int64)  --Otsu scan-->  t, Otsu mask
   c (+ halo)            --adaptive threshold -> open -> close-->  packed 1-bit mask (cropped to the core)
-  mask core             --CCL-->  per-strip labels; boundary rows all-gathered, equivalences
-                          united, labels renumbered in global raster-first order (relabel kernel)
+  mask core             --CCL resolve-->  per-strip roots; boundary label rows all-gathered,
+                          equivalences united on the device, then the label image is written ONCE in
+                          global raster-first numbering (CCL emit through the remap table)
   labels, c             --region props--> partial tables, all-reduced (sum / min / max)
 
 Halo rows are over-fetched from the shared source once (Gaussian r + adaptive r + 4 morphology r
@@ -266,7 +267,9 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
     # cropping whole rows of the packed mask is a view, not a copy)
     bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
-    labels, counts = be.ccl_label_bits(bits[c0 - a0: c1 - a0], W)
+    bits_core = bits[c0 - a0: c1 - a0]
+    # labelling in two steps: resolve now, write the label image once the global numbering is known
+    ccl_ws, counts = be.ccl_resolve_bits(bits_core, W)
 
     def scan():
         hist_ready.synchronize()
@@ -280,7 +283,9 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
 
     # cross-strip merge from boundary rows
     if comm is not None:
-        edge = torch.stack([labels[0], labels[-1]]).contiguous()
+        rows_core = c1 - c0
+        edge = torch.cat([be.ccl_emit(bits_core, W, ccl_ws, rows=(0, 1)),
+                          be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core))]).contiguous()
         edges = comm.all_gather(edge)
         cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
         def merge():
@@ -299,9 +304,10 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
 
         glob, offs, total = comm.once(merge)
         remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
-        be.relabel(labels, remap)
+        labels = be.ccl_emit(bits_core, W, ccl_ws, remap=remap)   # global labels, written once
     else:
         total = n_local
+        labels = be.ccl_emit(bits_core, W, ccl_ws)
     mark("merge")
 
     props = None
