@@ -268,6 +268,11 @@ int yam_border_clear(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_
 int yam_edge_filter(yam_ctx* ctx, const void* src, void* dst_u8, int64_t n, int64_t h, int64_t w, int dtype,
                     int kind, int ksize);
 
+/* Raw material of cv2.moments(mask) (hu_moments_data, core/extraction.py:100-105): for every row y
+ * of a mask (non-zero = set) out_dev[y][4] = (count, sum x, sum x^2, sum x^3) over the set pixels,
+ * exact int64.  m_pq = 255 * sum_y y^q * out[y][p] is formed on the host in exact arithmetic. */
+int yam_mask_row_moments(yam_ctx* ctx, const void* mask, int64_t h, int64_t w, int dtype, int64_t* out_dev);
+
 #ifdef __cplusplus
 }
 #endif

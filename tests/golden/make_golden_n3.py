@@ -57,6 +57,22 @@ def main() -> None:
         g[f"border5_bgr_{tag}"] = cs.remove_border_regions(bgr, 5)
     for ch in ("RG", "GB", "BR"):
         g[f"select_{ch}_u8"] = mp.SelectChannelModule().process(g["in_bgr_u8"], channel=ch)
+    # extraction tables (core/extraction.py:100-105, 280-290); blob image so that Otsu splits it
+    from core import extraction as ce
+
+    yy, xx = np.mgrid[0:96, 0:128]
+    blob = np.zeros((96, 128))
+    for _ in range(7):
+        cy, cx, r = rng.integers(10, 86), rng.integers(10, 118), rng.integers(4, 12)
+        blob += np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2.0 * r * r))
+    blob_u8 = np.clip(blob * 200 + rng.normal(8, 3, blob.shape), 0, 255).astype(np.uint8)
+    g["in_blob_u8"] = blob_u8
+    for name, img in (("blob", blob_u8), ("noise", g["in_noise_u8"]), ("bgr", g["in_bgr_u8"])):
+        g[f"hu_{name}_u8"] = ce.hu_moments_data(img).to_numpy(dtype=np.float64).ravel()
+        g[f"histstats_{name}_u8"] = ce.histogram_data(img).to_numpy(dtype=np.float64).ravel()
+    blob_u16 = (blob_u8.astype(np.uint16) << 8) | 17
+    g["in_blob_u16"] = blob_u16
+    g["hu_blob_u16"] = ce.hu_moments_data(blob_u16).to_numpy(dtype=np.float64).ravel()
     np.savez_compressed(OUT / "reference_outputs_n3.npz", **g)
     print(f"wrote {len(g)} arrays, {(OUT / 'reference_outputs_n3.npz').stat().st_size} bytes")
 

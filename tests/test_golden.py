@@ -123,3 +123,30 @@ def test_n3_channel_means(gold_n3):
         eq(O.select_channel(gold_n3["in_bgr_u8"], ch), gold_n3[f"select_{ch}_u8"], f"SelectChannel {ch}")
     with pytest.raises(TypeError):
         O.select_channel(gold_n3["in_bgr_u16"], "RG")
+
+
+def _row_power_sums(mask):
+    rows = np.zeros((mask.shape[0], 4), np.int64)
+    ys, xs = np.nonzero(mask)
+    xs = xs.astype(np.int64)
+    for p in range(4):
+        np.add.at(rows[:, p], ys, xs ** p)
+    return rows
+
+
+def test_n3_extraction_tables(gold_n3):
+    """hu_moments_data / histogram_data of the reference vs the host algebra on exact integer inputs.
+    Tolerance 1e-9 relative: cv2's build contracts some central-moment expressions into FMAs and
+    scipy sums the repeated data pairwise, so the last bits differ (see host/moments.py)."""
+    from yamimageprocessor_b200.host import moments as M
+
+    for name in ("blob_u8", "noise_u8", "bgr_u8", "blob_u16"):
+        img = gold_n3[f"in_{name}"]
+        gray = O.bgr2gray(img) if img.ndim == 3 else img
+        mask = O.otsu_threshold(gray, 255)[1]
+        hu = M.hu_moments(M.complete_moments(M.raw_moments_from_rows(_row_power_sums(mask))))
+        np.testing.assert_allclose(hu, gold_n3[f"hu_{name}"], rtol=1e-9, atol=0)
+        if name.endswith("u8"):
+            st = M.histogram_statistics(np.bincount(gray.ravel(), minlength=256))
+            got = np.array([st["mean"], st["variance"], st["skewness"], st["kurtosis"]])
+            np.testing.assert_allclose(got, gold_n3[f"histstats_{name}"], rtol=1e-9, atol=0)

@@ -167,6 +167,10 @@ def test_full_size_segmentation_properties(backend):
     assert int(props[:, 3].sum()) == int(frame[mh > 0].astype(np.int64).sum())
     cy, cx = props[:, 1] / props[:, 0], props[:, 2] / props[:, 0]
     assert np.all((cy >= props[:, 4]) & (cy < props[:, 6]) & (cx >= props[:, 5]) & (cx < props[:, 7]))
+    # the fused 1-bit path (the schedule bench.py times) produces the very same label image
+    labels_f, counts_f = backend.segment_fused(x, 11, 2, 5, 1)
+    assert int(backend.to_host(counts_f)[0]) == n
+    assert bool((labels_f == labels).all())
     # a 1024^2 crop away from the borders labels identically up to numbering (oracle-checked)
     crop = mh[1024:2048, 2048:3072]
     n_c, lab_c = O.ccl_label(crop)
@@ -368,3 +372,28 @@ def test_device_pipeline_cache(backend, mods):
     eq(small.compute(sid2, frame, steps).image, want, "recompute after discard")
     with pytest.raises(KeyError):
         cache.compute(sid, None, [step("Otsu"), type("S", (), {"name": "K-Means", "enabled": True, "params": {}})()])
+
+
+def test_n3_extraction_tables_on_device(backend, gold_n3):
+    from yamimageprocessor_b200.modules import b200_backend as plugin
+
+    for name in ("blob_u8", "noise_u8", "bgr_u8", "blob_u16"):
+        img = gold_n3[f"in_{name}"]
+        hu = plugin.hu_moments_data(img)
+        np.testing.assert_allclose([hu[f"hu_{i}"] for i in range(1, 8)], gold_n3[f"hu_{name}"], rtol=1e-9, atol=0)
+        if name.endswith("u8"):
+            st = plugin.histogram_data(img)
+            got = [st["mean"], st["variance"], st["skewness"], st["kurtosis"]]
+            np.testing.assert_allclose(got, gold_n3[f"histstats_{name}"], rtol=1e-9, atol=0)
+    # the device row sums are exact integers
+    rng = np.random.default_rng(4)
+    for shape, dt in (((37, 71), np.uint8), ((130, 1031), np.uint16)):
+        m = ((rng.random(shape) < 0.4) * 255).astype(dt)
+        rows = backend.to_host(backend.mask_row_moments(backend.to_device(m)))
+        want = np.zeros((shape[0], 4), np.int64)
+        ys, xs = np.nonzero(m)
+        for p in range(4):
+            np.add.at(want[:, p], ys, xs.astype(np.int64) ** p)
+        assert np.array_equal(rows, want)
+    with pytest.raises(TypeError):
+        plugin.histogram_data(gold_n3["in_noise_u16"])

@@ -482,6 +482,15 @@ class Backend:
         self._call("yam_edge_filter", self._p(img), self._p(out), n, h, w, _dtype_code(img), kinds[kind], int(ksize))
         return out
 
+    def mask_row_moments(self, mask):
+        """int64 [h, 4] on device: per row (count, sum x, sum x^2, sum x^3) over the set pixels."""
+        torch = _torch()
+        mask = self._check(mask, ndim=(2,), dtypes=(torch.uint8, torch.uint16), name="mask")
+        h, w = int(mask.shape[0]), int(mask.shape[1])
+        out = torch.empty((h, 4), dtype=torch.int64, device=self.device)
+        self._call("yam_mask_row_moments", self._p(mask), h, w, _dtype_code(mask), self._p(out))
+        return out
+
     # ------------------------------------------------------------------ fused binary segmentation
     def adaptive_threshold_bits(self, img, block_size: int = 11, C_: float = 2.0):
         """Adaptive threshold with a 1-bit-per-pixel result: int32 tensor (..., h, ceil(w/32))."""

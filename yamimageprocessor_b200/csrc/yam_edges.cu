@@ -156,6 +156,35 @@ __global__ void __launch_bounds__(kThreads) edge_kernel(const T* __restrict__ sr
     }
 }
 
+// ---- per-row power sums of the set pixels of a mask: out[y] = (count, sum x, sum x^2, sum x^3) ------------
+// (exact int64; the host combines the rows with powers of y in arbitrary precision -> cv2.moments)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) mask_row_moments_kernel(const T* __restrict__ mask, int h, int w,
+                                                                    long long* __restrict__ out) {
+    const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= h) return;
+    const T* row = mask + (int64_t)warp * w;
+    long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int x = lane; x < w; x += 32) {
+        if (row[x]) {
+            const long long xx = x;
+            s0 += 1;
+            s1 += xx;
+            s2 += xx * xx;
+            s3 += xx * xx * xx;
+        }
+    }
+    s0 = yam_warp_sum(s0);
+    s1 = yam_warp_sum(s1);
+    s2 = yam_warp_sum(s2);
+    s3 = yam_warp_sum(s3);
+    if (lane == 0) {
+        long long* o = out + (int64_t)warp * 4;
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+    }
+}
+
 unsigned stream_blocks(yam_ctx* ctx, int64_t items) {
     int64_t b = (items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -227,6 +256,20 @@ int yam_border_clear(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_
         border_clear_kernel<uint8_t><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, row_elems, channels, d, n);
     else
         border_clear_kernel<uint16_t><<<grid, kThreads, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, (int)h, row_elems, channels, d, n);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+int yam_mask_row_moments(yam_ctx* ctx, const void* mask, int64_t h, int64_t w, int dtype, int64_t* out_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(mask && out_dev && h > 0 && w > 0, "mask_row_moments: bad arguments");
+    YAM_REQUIRE(h < (1 << 30) && w < (1 << 20), "mask_row_moments: image side too large for exact int64 row sums");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "mask_row_moments: unsupported dtype %d", dtype);
+    const unsigned blocks = (unsigned)((h * 32 + kThreads - 1) / kThreads);
+    if (dtype == YAM_U8)
+        mask_row_moments_kernel<uint8_t><<<blocks, kThreads, 0, ctx->stream>>>((const uint8_t*)mask, (int)h, (int)w, (long long*)out_dev);
+    else
+        mask_row_moments_kernel<uint16_t><<<blocks, kThreads, 0, ctx->stream>>>((const uint16_t*)mask, (int)h, (int)w, (long long*)out_dev);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
 }

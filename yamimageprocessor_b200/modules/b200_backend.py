@@ -174,10 +174,38 @@ def region_properties_data(image: np.ndarray) -> Dict[str, np.ndarray]:
     return region_table(be, labels, gray if gray.dtype in _intensity_dtypes() else None)
 
 
+def hu_moments_data(image: np.ndarray) -> Dict[str, float]:
+    """GPU counterpart of core/extraction.py:100-105: Otsu -> cv2.moments(mask) -> cv2.HuMoments,
+    as ``{"hu_1": ..., "hu_7": ...}`` (the mask and its row power sums are formed on the device)."""
+    from ..host import moments as M
+
+    ex = _executor()
+    be = ex.backend
+    gray = be.bgr2gray(be.to_device(np.asarray(image)))
+    mask = be.otsu_threshold(gray, 255)[1]
+    rows = be.to_host(be.mask_row_moments(mask))
+    hu = M.hu_moments(M.complete_moments(M.raw_moments_from_rows(rows)))
+    return {f"hu_{i + 1}": float(v) for i, v in enumerate(hu)}
+
+
+def histogram_data(image: np.ndarray) -> Dict[str, float]:
+    """GPU counterpart of core/extraction.py:280-290 (uint8 gray levels): mean, variance, skewness
+    and kurtosis of the 256-bin histogram, which is computed on the device."""
+    from ..host import moments as M
+
+    ex = _executor()
+    be = ex.backend
+    gray = be.bgr2gray(be.to_device(np.asarray(image)))
+    if str(gray.dtype) != "torch.uint8":
+        raise TypeError("histogram_data: the reference's 256-bin histogram is defined for uint8 images")
+    return M.histogram_statistics(be.to_host(be.histogram(gray))[0])
+
+
 def _intensity_dtypes():
     import torch
 
     return (torch.uint8, torch.uint16)
 
 
-__all__ = [cls.__name__ for cls in MODULE_CLASSES] + ["MODULE_CLASSES", "register_module", "region_properties_data"]
+__all__ = [cls.__name__ for cls in MODULE_CLASSES] + ["MODULE_CLASSES", "register_module", "region_properties_data",
+                                                       "hu_moments_data", "histogram_data"]
