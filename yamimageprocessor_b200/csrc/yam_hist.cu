@@ -540,7 +540,7 @@ struct SmemCounts {
     const uint32_t* sh;
     const uint32_t* ovf;
     bool use_ovf;
-    __device__ __forceinline__ void get(int wi, unsigned long long& c0, unsigned long long& c1) const {
+    __device__ __forceinline__ void get32(int wi, uint32_t& c0, uint32_t& c1) const {
         const uint32_t wv = sh[wi];
         c0 = wv & 0xffffu;
         c1 = wv >> 16;
@@ -553,7 +553,7 @@ struct SmemCounts {
 // counts from a global 32-bit histogram (multi-CTA tiles)
 struct GlobalCounts {
     const uint32_t* gh;
-    __device__ __forceinline__ void get(int wi, unsigned long long& c0, unsigned long long& c1) const {
+    __device__ __forceinline__ void get32(int wi, uint32_t& c0, uint32_t& c1) const {
         const uint2 v = __ldcg(reinterpret_cast<const uint2*>(gh) + wi);
         c0 = v.x;
         c1 = v.y;
@@ -561,79 +561,80 @@ struct GlobalCounts {
 };
 
 // clip -> redistribute -> ordered prefix sum -> LUT for one tile; all kHistThreads threads take part.
+// 32-bit arithmetic throughout (a tile has < 2^31 pixels, host-checked), two passes over the bins:
+//   pass 0  per-warp sums of the clipped counts -> excess, batch, residual, step (cv2's redistribution)
+//   pass 1  ordered prefix sum of the adjusted counts -> LUT.  The warp bases come from pass 0 in
+//           closed form: adjusted total = clipped total + batch * bins + (residual increments that
+//           fall into the warp's bin range), so no third pass is needed.
+// "bin is one of the first `residual` multiples of `step`" is tested without a division:
+// q = umulhi(bin, ceil(2^32 / step)) == bin / step exactly for bin, step <= 65536.
 template <class Counts>
 __device__ __forceinline__ void clahe_lut_passes(const Counts& cnt, const ClaheGeom& g, uint16_t* __restrict__ lut,
                                                  unsigned long long* s_red, unsigned long long* s_base) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long area = (long long)g.tw * g.th;
+    const uint32_t area = (uint32_t)((long long)g.tw * g.th);
     const int wbase = warp * 1024;  // each warp owns words [1024*warp, +1024); lane reads base+32*i+lane
-    const unsigned long long clipv = g.clip > 0 ? (unsigned long long)g.clip : ~0ull;
+    const uint32_t clipv = g.clip > 0 ? (uint32_t)g.clip : 0xffffffffu;
+    uint32_t* s_red32 = reinterpret_cast<uint32_t*>(s_red);
+    uint32_t* s_base32 = reinterpret_cast<uint32_t*>(s_base);
     // pass 0: sum of clipped counts -> excess
-    unsigned long long part = 0;
+    uint32_t part = 0;
+#pragma unroll 4
     for (int i = 0; i < 32; i++) {
-        const int wi = wbase + 32 * i + lane;
-        unsigned long long c0, c1;
-        cnt.get(wi, c0, c1);
-        part += (c0 < clipv ? c0 : clipv) + (c1 < clipv ? c1 : clipv);
+        uint32_t c0, c1;
+        cnt.get32(wbase + 32 * i + lane, c0, c1);
+        part += min(c0, clipv) + min(c1, clipv);
     }
     part = yam_warp_sum(part);
-    if (lane == 0) s_red[warp] = part;
+    if (lane == 0) s_red32[warp] = part;
     __syncthreads();
-    unsigned long long clipped_total = 0;
-    for (int i = 0; i < 32; i++) clipped_total += s_red[i];
+    uint32_t clipped_total = 0, clipped_before = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const uint32_t v = s_red32[i];
+        clipped_total += v;
+        if (i < warp) clipped_before += v;
+    }
     __syncthreads();
-    const unsigned long long excess = (unsigned long long)area - clipped_total;
-    const unsigned long long batch = g.clip > 0 ? excess / kBins16 : 0;
-    const uint32_t residual = g.clip > 0 ? (uint32_t)(excess - batch * kBins16) : 0;
+    const uint32_t excess = area - clipped_total;
+    const uint32_t batch = g.clip > 0 ? excess / kBins16 : 0;
+    const uint32_t residual = g.clip > 0 ? excess - batch * kBins16 : 0;
     const uint32_t step = residual ? max((uint32_t)kBins16 / residual, 1u) : 1u;
-
-    auto adjusted = [&](uint32_t bin, unsigned long long c) -> unsigned long long {
-        unsigned long long a = (c < clipv ? c : clipv) + batch;
-        if (residual && (bin % step) == 0 && (bin / step) < residual) a += 1;
-        return a;
+    // step == 1: magic would be 2^32; q == bin then (handled explicitly)
+    const uint32_t magic = step > 1 ? (uint32_t)((0x100000000ull + step - 1) / step) : 0u;
+    auto bumped = [&](uint32_t bin) -> uint32_t {   // 1 if cv2 increments this bin with the residual
+        if (!residual) return 0u;
+        const uint32_t q = step > 1 ? __umulhi(bin, magic) : bin;
+        return (q * step == bin && q < residual) ? 1u : 0u;
     };
+    // residual increments in bins [0, first_bin): multiples of step below first_bin, at most `residual`
+    const uint32_t first_bin = (uint32_t)warp * 2048u;
+    uint32_t bumps_before = 0;
+    if (residual && first_bin) bumps_before = min((first_bin - 1u) / step + 1u, residual);
+    uint32_t run = clipped_before + batch * first_bin + bumps_before;
 
-    // pass 1: warp totals of adjusted counts
-    part = 0;
+    // pass 1: ordered prefix sum -> LUT
+#pragma unroll 2
     for (int i = 0; i < 32; i++) {
         const int wi = wbase + 32 * i + lane;
-        unsigned long long c0, c1;
-        cnt.get(wi, c0, c1);
-        part += adjusted(2 * wi, c0) + adjusted(2 * wi + 1, c1);
-    }
-    part = yam_warp_sum(part);
-    if (lane == 0) s_red[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long run0 = 0;
-        for (int i = 0; i < 32; i++) {
-            s_base[i] = run0;
-            run0 += s_red[i];
-        }
-    }
-    __syncthreads();
-
-    // pass 2: ordered prefix sum -> LUT
-    unsigned long long run = s_base[warp];
-    for (int i = 0; i < 32; i++) {
-        const int wi = wbase + 32 * i + lane;
-        unsigned long long c0, c1;
-        cnt.get(wi, c0, c1);
-        const unsigned long long a0 = adjusted(2 * wi, c0), a1 = adjusted(2 * wi + 1, c1);
-        unsigned long long incl = a0 + a1;
+        uint32_t c0, c1;
+        cnt.get32(wi, c0, c1);
+        const uint32_t a0 = min(c0, clipv) + batch + bumped(2u * wi);
+        const uint32_t a1 = min(c1, clipv) + batch + bumped(2u * wi + 1u);
+        uint32_t incl = a0 + a1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
         }
-        const unsigned long long before = run + incl - (a0 + a1);
-        const unsigned long long cum0 = before + a0, cum1 = cum0 + a1;
+        const uint32_t cum0 = run + incl - a1, cum1 = run + incl;
         // cv2: saturate_cast<ushort>(sum * lutScale) with sum an int converted to float
-        const uint32_t l0 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum0, g.lut_scale), 65535);
-        const uint32_t l1 = (uint32_t)yam_rint_sat(__fmul_rn((float)(long long)cum1, g.lut_scale), 65535);
+        const uint32_t l0 = (uint32_t)yam_rint_sat(__fmul_rn((float)(int)cum0, g.lut_scale), 65535);
+        const uint32_t l1 = (uint32_t)yam_rint_sat(__fmul_rn((float)(int)cum1, g.lut_scale), 65535);
         reinterpret_cast<uint32_t*>(lut)[wi] = l0 | (l1 << 16);
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    (void)s_base32;
 }
 
 // u16: one CTA per tile at a time (persistent CTAs loop over the tiles of a frame chunk):
