@@ -394,9 +394,10 @@ class Backend:
         self._call("yam_relabel", self._p(labels), labels.numel(), self._p(remap), remap.numel())
         return labels
 
-    def merge_strip_labels(self, edges, offsets):
+    def merge_strip_labels(self, edges, offsets, total: Optional[int] = None):
         """Roots of the cross-strip label union (see yam_merge_strip_labels): ``edges`` int32
-        [world, 2, w] first/last label rows per strip, ``offsets`` int64 [world + 1] on the device.
+        [world, 2, w] first/last label rows per strip, ``offsets`` int64 [world + 1] on the device
+        (``total`` = offsets[-1] when the caller already has it on the host).
         Returns int32 [total + 1]: smallest global id of every id's merged component."""
         torch = _torch()
         edges = self._check(edges, ndim=(3,), dtypes=(torch.int32,), name="edges")
@@ -404,7 +405,8 @@ class Backend:
         world, two, w = (int(v) for v in edges.shape)
         if two != 2 or offsets.numel() != world + 1:
             raise ValueError("edges must be [world, 2, w] and offsets [world + 1]")
-        total = int(offsets[-1].item())
+        if total is None:
+            total = int(offsets[-1].item())
         root = torch.empty((total + 1,), dtype=torch.int32, device=self.device)
         self._call("yam_merge_strip_labels", self._p(edges), self._p(offsets), world, w, total, self._p(root))
         return root

@@ -278,7 +278,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     t = comm.once(scan) if comm is not None else scan()
     otsu_mask = be.threshold(c_core, float(t), 255)
     mark("otsu")
-    n_local = int(be.to_host(counts)[0])
     mark("segment")
 
     # cross-strip merge from boundary rows
@@ -287,27 +286,28 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         edge = torch.cat([be.ccl_emit(bits_core, W, ccl_ws, rows=(0, 1)),
                           be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core))]).contiguous()
         edges = comm.all_gather(edge)
-        cnts = comm.all_gather(torch.tensor([n_local], dtype=torch.int64, device=be.device))
+        cnts = comm.all_gather(counts)             # device tensors: no host round trip before the merge
         def merge():
             # all on the device: union of the ids that touch across strip boundaries, then the
-            # raster-first renumbering (rank of every root among the roots)
-            offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device), torch.cat(cnts).cumsum(0)])
-            root = be.merge_strip_labels(torch.stack(edges), offs_dev).to(torch.int64)
-            ids = torch.arange(root.numel(), dtype=torch.int64, device=be.device)
-            is_root = root == ids
-            is_root[0] = False
-            rank = torch.cumsum(is_root.to(torch.int32), dim=0, dtype=torch.int32)
-            glob = rank[root]
-            glob[0] = 0
+            # raster-first renumbering (rank of every root among the roots); ONE host sync (offsets)
+            offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device),
+                                  torch.cat(cnts).to(torch.int64).cumsum(0)])
             offs = [int(v) for v in offs_dev.tolist()]
-            return glob, offs, int(rank[-1].item()) if root.numel() > 1 else 0
+            root = be.merge_strip_labels(torch.stack(edges), offs_dev, total=offs[-1])
+            is_root = root == torch.arange(root.numel(), dtype=torch.int32, device=be.device)
+            is_root[0] = False
+            ranks = torch.cumsum(is_root, dim=0, dtype=torch.int32)
+            glob = ranks[root]
+            glob[0] = 0
+            return glob, offs, ranks[-1:]
 
-        glob, offs, total = comm.once(merge)
+        glob, offs, total_dev = comm.once(merge)
         remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
         labels = be.ccl_emit(bits_core, W, ccl_ws, remap=remap)   # global labels, written once
     else:
-        total = n_local
+        total_dev = counts
         labels = be.ccl_emit(bits_core, W, ccl_ws)
+    total = int(total_dev[0].item())   # the only wait for the labelling: everything above is enqueued
     mark("merge")
 
     props = None
