@@ -276,8 +276,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         return be.otsu_from_histogram(hist_host.numpy())
 
     t = comm.once(scan) if comm is not None else scan()
-    otsu_mask = be.threshold(c_core, float(t), 255)
-    mark("otsu")
     mark("segment")
 
     # cross-strip merge from boundary rows
@@ -287,24 +285,37 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
                           be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core))]).contiguous()
         edges = comm.all_gather(edge)
         cnts = comm.all_gather(counts)             # device tensors: no host round trip before the merge
+        # label offsets of the strips: the one value the host needs (array sizes).  It is read back
+        # asynchronously and the Otsu threshold kernel is enqueued behind the copy, so the GPU has
+        # work while the host waits for the offsets and prepares the merge.
+        offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device),
+                              torch.cat(cnts).to(torch.int64).cumsum(0)])
+        offs_host = torch.empty(offs_dev.shape, dtype=torch.int64, pin_memory=True)
+        offs_host.copy_(offs_dev, non_blocking=True)
+        offs_ready = torch.cuda.Event()
+        offs_ready.record()
+        otsu_mask = be.threshold(c_core, float(t), 255)
+        mark("otsu")
+        offs_ready.synchronize()
+        offs = [int(v) for v in offs_host.tolist()]
+
         def merge():
             # all on the device: union of the ids that touch across strip boundaries, then the
-            # raster-first renumbering (rank of every root among the roots); ONE host sync (offsets)
-            offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device),
-                                  torch.cat(cnts).to(torch.int64).cumsum(0)])
-            offs = [int(v) for v in offs_dev.tolist()]
+            # raster-first renumbering (rank of every root among the roots)
             root = be.merge_strip_labels(torch.stack(edges), offs_dev, total=offs[-1])
             is_root = root == torch.arange(root.numel(), dtype=torch.int32, device=be.device)
             is_root[0] = False
             ranks = torch.cumsum(is_root, dim=0, dtype=torch.int32)
             glob = ranks[root]
             glob[0] = 0
-            return glob, offs, ranks[-1:]
+            return glob, ranks[-1:]
 
-        glob, offs, total_dev = comm.once(merge)
+        glob, total_dev = comm.once(merge)
         remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
         labels = be.ccl_emit(bits_core, W, ccl_ws, remap=remap)   # global labels, written once
     else:
+        otsu_mask = be.threshold(c_core, float(t), 255)
+        mark("otsu")
         total_dev = counts
         labels = be.ccl_emit(bits_core, W, ccl_ws)
     total = int(total_dev[0].item())   # the only wait for the labelling: everything above is enqueued
