@@ -245,11 +245,28 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         return x, run, ops
 
     if workload == "c2":
-        # Fused schedule: the thresholded mask is binary, so it stays 1 bit/pixel from the threshold
-        # kernel through open/close into the labelling (same labels as the step-by-step chain, which
-        # is listed under roofline.ops_unfused and is what the e2e PipelineManager path dispatches).
+        # The four reference steps dispatched through the executor's device-resident chain -- the very
+        # schedule PipelineManager.apply (the e2e leg) runs between its upload and download.  The
+        # thresholded mask is binary, so the executor keeps it 1 bit/pixel from the threshold kernel
+        # through open/close into the labelling (same labels as the byte-mask chain, whose operators
+        # are listed under roofline.ops_unfused for comparison).
+        from yamimageprocessor_b200.host.executor import B200Executor
+        from yamimageprocessor_b200.modules import b200_backend as plugin
+
+        _mods = {cls().metadata.identifier: cls() for cls in plugin.MODULE_CLASSES}
+
+        def _step(name, **params):
+            st = _mods[name].create_pipeline_step()
+            st.enabled = True
+            st.params.update(params)
+            return st
+
+        _chain = [_step("Adaptive"), _step("Opening", kernel_size=5), _step("Closing", kernel_size=5),
+                  _step("ConnectedComponents")]
+        _ex = B200Executor(be)
+
         def run(inp):
-            return be.segment_fused(inp, 11, 2, 5, 1)[0]
+            return _ex.run_chain_on_device(_chain, inp)
 
         def ops(inp):
             wd = int(inp.shape[-1])

@@ -397,3 +397,50 @@ def test_n3_extraction_tables_on_device(backend, gold_n3):
         assert np.array_equal(rows, want)
     with pytest.raises(TypeError):
         plugin.histogram_data(gold_n3["in_noise_u16"])
+
+
+def test_executor_fuses_binary_runs(backend, mods):
+    """execute_chain keeps Adaptive -> rectangular morphology -> ConnectedComponents packed 1 bit/px;
+    every variant must equal the step-by-step oracle chain."""
+    from yamimageprocessor_b200.host.executor import B200Executor
+
+    def step(name, **params):
+        s = mods[name].create_pipeline_step()
+        s.enabled = True
+        s.params.update(params)
+        return s
+
+    ex = B200Executor(backend)
+    frame = synth.nuclei(200, 328, seed=41)
+    mask = O.adaptive_threshold(frame, 11, 2)
+    opened = O.morph_open(mask, "Rectangular", 5, 1)
+    closed = O.morph_close(opened, "Rectangular", 5, 1)
+    n_want, lab_want = O.ccl_label(closed)
+    # full run, ends in labels
+    backend.launch_count(reset=True)
+    got = ex.execute_chain([step("Adaptive"), step("Opening", kernel_size=5), step("Closing", kernel_size=5),
+                            step("ConnectedComponents")], frame)
+    eq(got, lab_want, "fused run -> labels")
+    fused_launches = backend.launch_count()
+    # run that ends in a mask (unpacked), followed by a non-binary step
+    got = ex.execute_chain([step("Adaptive"), step("Opening", kernel_size=5), step("Closing", kernel_size=5)], frame)
+    eq(got, closed, "fused run -> mask")
+    got = ex.execute_chain([step("Adaptive"), step("Erosion", kernel_size=3, iterations=2), step("BoxFilter", ksize=3)], frame)
+    eq(got, O.box(O.erode(mask, "Rectangular", 3, 2), 3), "fused run, then another step")
+    # an elliptical element ends the run (that step runs on the byte mask)
+    got = ex.execute_chain([step("Adaptive"), step("Opening", kernel_size=5), step("Closing", kernel_shape="Elliptical", kernel_size=5)], frame)
+    eq(got, O.morph_close(opened, "Elliptical", 5, 1), "run stops at a non-rectangular element")
+    # unsupported block size / colour input: plain chain
+    got = ex.execute_chain([step("Adaptive", block_size=9), step("Opening", kernel_size=3)], frame)
+    eq(got, O.morph_open(O.adaptive_threshold(frame, 9, 2), "Rectangular", 3, 1), "block 9 is not fused")
+    stack = np.stack([synth.nuclei(96, 128, seed=s) for s in (1, 2, 3)])
+    got = ex.execute_chain([step("Adaptive"), step("Opening", kernel_size=5), step("ConnectedComponents")], stack)
+    for i in range(3):
+        eq(got[i], O.ccl_label(O.morph_open(O.adaptive_threshold(stack[i], 11, 2), "Rectangular", 5, 1))[1], f"stack {i}")
+    # the fused run really used the bit kernels (7 launches: threshold, morph x2, scan, tile, border, rank, final = 8 at most)
+    assert fused_launches <= 9
+    # a disabled step inside the run is skipped, like PipelineManager does
+    s_closed = step("Closing", kernel_size=5)
+    s_closed.enabled = False
+    got = ex.execute_chain([step("Adaptive"), step("Opening", kernel_size=5), s_closed, step("ConnectedComponents")], frame)
+    eq(got, O.ccl_label(opened)[1], "disabled step")
