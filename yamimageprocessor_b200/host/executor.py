@@ -93,13 +93,24 @@ class B200Executor:
         width = int(tensor.shape[-1])
         self.calls.append("Adaptive")
         bits = be.adaptive_threshold_bits(tensor, int(first.get("block_size", 11)), float(first.get("C", 2)))
-        for step in run[1:]:
+        rest = list(run[1:])
+        i = 0
+        while i < len(rest):
+            step = rest[i]
             self.calls.append(step.name)
             if step.name == "ConnectedComponents":
                 return be.ccl_label_bits(bits, width)[0]
-            p = step.params
-            bits = be.bits_morph(bits, width, self._MORPH_OPS[step.name], int(p.get("kernel_size", 3)),
-                                 int(p.get("iterations", 1)))
+            k, it = int(step.params.get("kernel_size", 3)), int(step.params.get("iterations", 1))
+            nxt = rest[i + 1] if i + 1 < len(rest) else None
+            if (step.name == "Opening" and nxt is not None and nxt.name == "Closing"
+                    and int(nxt.params.get("kernel_size", 3)) == k and int(nxt.params.get("iterations", 1)) == it):
+                # open then close with the same element: one launch (erode, dilate x2, erode in registers)
+                self.calls.append(nxt.name)
+                bits = be.bits_morph(bits, width, 4, k, it)
+                i += 2
+                continue
+            bits = be.bits_morph(bits, width, self._MORPH_OPS[step.name], k, it)
+            i += 1
         return be.bits_unpack(bits, width)
 
     def run_chain_on_device(self, steps: Sequence[Any], tensor):
