@@ -20,19 +20,20 @@ from ..backend import Backend
 _CHUNK_BYTES = 64 << 20
 _DEPTH = 3
 _POOL: Optional[ThreadPoolExecutor] = None
+_WORKERS = max(2, min(16, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))))
 
 
 def _pool() -> ThreadPoolExecutor:
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(16, (os.cpu_count() or 4))), thread_name_prefix="yam-ingest")
+        _POOL = ThreadPoolExecutor(max_workers=_WORKERS, thread_name_prefix="yam-ingest")
     return _POOL
 
 
 def _parallel_copy(dst: np.ndarray, src) -> None:
     """dst[...] = src with the rows split over the pool (np.copyto releases the GIL)."""
     rows = dst.shape[0]
-    parts = min(rows, _pool()._max_workers)
+    parts = min(rows, _WORKERS)
     if parts <= 1 or dst.nbytes < (4 << 20):
         np.copyto(dst, src)
         return
@@ -135,7 +136,7 @@ def download_into(be: Backend, t, out: np.ndarray) -> np.ndarray:
             ev.synchronize()
             src = ring.bufs[slot].numpy()[:nbytes]
             piece = dst[off:off + nbytes]
-            parts = min(_pool()._max_workers, max(1, nbytes >> 22))
+            parts = min(_WORKERS, max(1, nbytes >> 22))
             if parts <= 1:
                 np.copyto(piece, src)
             else:
