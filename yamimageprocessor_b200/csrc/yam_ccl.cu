@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(kThreads) ccl_border_kernel(const uint32_t* __
 // ---- 4. flatten + rank: P[node] = root, P[root] = -(rank + 1) ---------------------------------------------
 constexpr int kRankPer = 8;
 constexpr int kRankSub = kBigThreads * kRankPer;   // nodes per sub-chunk
+constexpr int kRankCtasPerSm = 2;                  // 2 x 1024 threads per SM stay co-resident (32 registers)
 
 // walk kRankPer consecutive nodes to their roots (read-only), store the roots; returns the root bitmask
 __device__ __forceinline__ uint32_t flatten_nodes(int* __restrict__ P, int n0, int total) {
@@ -570,8 +571,8 @@ __device__ __forceinline__ uint32_t flatten_nodes(int* __restrict__ P, int n0, i
     return roots;
 }
 
-// grid <= num_sms; chunks = min(grid, ceil(total / kRankSub)), each a whole number of sub-chunks
-__global__ void __launch_bounds__(kBigThreads) ccl_rank_kernel(const uint32_t* __restrict__ total_nodes,
+// grid = kRankCtasPerSm x num_sms; chunks = min(grid, ceil(total / kRankSub)), each a whole number of sub-chunks
+__global__ void __launch_bounds__(kBigThreads, kRankCtasPerSm) ccl_rank_kernel(const uint32_t* __restrict__ total_nodes,
                                                                int* __restrict__ P,
                                                                unsigned long long* __restrict__ status,
                                                                unsigned int* __restrict__ ticket,
@@ -1104,7 +1105,7 @@ static void ccl_layout(const CclGeom& g, int num_sms, char* base, CclWorkspace* 
     const int64_t scan_chunks = scan_subs < num_sms ? scan_subs : num_sms;
     const int64_t rank_subs = (max_nodes + kRankSub - 1) / kRankSub;
     const size_t words_bytes = yam_align_up((size_t)g.total_words * 4, 256);
-    const size_t sync_bytes = yam_align_up(256 + (size_t)(scan_chunks + num_sms) * 8, 256);
+    const size_t sync_bytes = yam_align_up(256 + (size_t)(scan_chunks + kRankCtasPerSm * num_sms) * 8, 256);
     const size_t chunk_bytes = yam_align_up((size_t)rank_subs * 4, 256);
     const size_t frame_bytes = yam_align_up((size_t)g.frames * 4, 256);
     const size_t node_bytes = yam_align_up((size_t)max_nodes * 4, 256);
@@ -1152,7 +1153,7 @@ static int ccl_resolve(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, 
     ccl_border_kernel<<<(unsigned)((na + nb + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(bits, ws.nbase, g, tiles_x,
                                                                                                   tiles_y, na, nb, ws.P);
     YAM_LAUNCHED(ctx);
-    ccl_rank_kernel<<<(unsigned)ctx->num_sms, kBigThreads, 0, ctx->stream>>>(ws.totals, ws.P, ws.statusB, ws.tickets + 1,
+    ccl_rank_kernel<<<(unsigned)(kRankCtasPerSm * ctx->num_sms), kBigThreads, 0, ctx->stream>>>(ws.totals, ws.P, ws.statusB, ws.tickets + 1,
                                                                             ws.chunk_excl, ws.totals + 1,
                                                                             n == 1 ? counts : nullptr);
     YAM_LAUNCHED(ctx);
