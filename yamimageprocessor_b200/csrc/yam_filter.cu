@@ -454,7 +454,12 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_in = reinterpret_cast<float*>(smem_raw);
     float* s_t = s_in + ROWS * SWP + 8;               // +8 floats slack: the last item may read past its row
-    Tout* s_out = reinterpret_cast<Tout*>(s_t + ROWS * TWP);
+    // Byte outputs (adaptive threshold): the 4 KiB staging tile aliases the start of s_t, which every
+    // warp has copied into registers before the first output is written (barrier below); 45 KB per
+    // block instead of 49 KB lets five blocks share an SM.  Float outputs keep their own tile.
+    constexpr bool ALIAS_OUT = sizeof(Tout) == 1;
+    static_assert(!ALIAS_OUT || TH * TW <= ROWS * TWP * 4, "aliased output tile must fit inside s_t");
+    Tout* s_out = ALIAS_OUT ? reinterpret_cast<Tout*>(s_t) : reinterpret_cast<Tout*>(s_t + ROWS * TWP);
     src += (int64_t)blockIdx.z * h * w;
     if (FEPI != FEPI_ADAPTIVE_BITS) dst += (int64_t)blockIdx.z * h * w;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(kThreads) sep_f32_tiled(const Tin* __restrict_
         float2 c[RB + KS - 1];
 #pragma unroll
         for (int i = 0; i < RB + KS - 1; i++) c[i] = *reinterpret_cast<const float2*>(s_t + (r0 + i) * TWP + cx);
+        if (ALIAS_OUT) __syncthreads();  // all of s_t is in registers: its storage may now take the outputs
         const float2 kc = make_float2(taps.v[R], taps.v[R]);
 #pragma unroll
         for (int j = 0; j < RB; j++) {
@@ -628,7 +634,7 @@ size_t f32_tiled_smem(int ks) {
     const int VEC = 16 / sizeof(Tin);
     const int R = ks / 2, RA = round_up_c(R, VEC > 4 ? VEC : 4), SW = TW + 2 * RA, ROWS = TH + 2 * R;
     const int SWP = ((SW / 4) % 2 == 0) ? SW + 4 : SW, TWP = TW + 4;
-    return ((size_t)ROWS * SWP + 8 + (size_t)ROWS * TWP) * 4 + (size_t)TH * TW * sizeof(Tout);
+    return ((size_t)ROWS * SWP + 8 + (size_t)ROWS * TWP) * 4 + (sizeof(Tout) == 1 ? 0 : (size_t)TH * TW * sizeof(Tout));
 }
 
 template <typename K>
