@@ -93,6 +93,11 @@ int yam_gaussian_taps_fixed(int ksize, double sigma, int bits, int64_t* out);
 int yam_structuring_element(int shape, int ksize, uint8_t* out);
 /* cv2 Otsu recurrence on a histogram of `bins` 64-bit counts (bit-exact incl. >= 2^31 px) */
 int yam_otsu_from_hist(const uint64_t* hist, int bins, int* out_threshold);
+/* the same for n histograms (hists[n][bins], host memory) on the host worker pool */
+int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out_thresholds);
+/* 1 if yam_otsu_threshold would scan a stack of n 16-bit frames on the device (cost model over
+ * this process's host threads), else 0 */
+int yam_otsu_prefers_device(int64_t n);
 
 /* ---- K1 colour -> gray: cv2.cvtColor(BGR2GRAY) --------------------------------------------
  * replaces modules/preprocessing.py:54, core/preprocessing.py:56, core/segmentation.py:48,
@@ -164,6 +169,10 @@ int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w
 /* Otsu threshold per frame from src (cv2.threshold(...THRESH_OTSU) — core/segmentation.py:147,
  * core/extraction.py:59,72): thresholds to thresh_dev[n] (int32, device) and thresh_host[n]
  * (optional), then dst = src > t ? maxval : 0 in the source dtype if dst != NULL. */
+/* dst = src > thresh_dev[frame] ? maxval : 0 per frame (thresholds int32 on the device): the second
+ * half of an Otsu threshold whose scan ran elsewhere (overlapped host scan, all-reduced histogram) */
+int yam_threshold_frames(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+                         const int32_t* thresh_dev, double maxval);
 int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
                        int dtype, double maxval, int32_t* thresh_dev, int32_t* thresh_host);
 /* cv2.equalizeHist — core/preprocessing.py:76. U8 only, like the reference. */

@@ -292,6 +292,22 @@ def test_otsu_stack_staged_scan_distributions(backend, rng):
         assert int(host(backend, t1)[0]) == want_t[i]
 
 
+def test_otsu_begin_finish(backend, rng):
+    """The two-step Otsu (scan overlapped with other work) equals the one-shot operator."""
+    for a in (blobs(rng, (130, 257), U16), np.stack([blobs(rng, (48, 64), U16) for _ in range(5)]),
+              blobs(rng, (64, 80), U8), np.stack([blobs(rng, (48, 64), U16) for _ in range(12)])):
+        x = dev(backend, a)
+        h = backend.otsu_begin(x)
+        other = backend.gaussian(x, 5, 0.0)           # unrelated work enqueued in between
+        t, out = backend.otsu_finish(h, 255)
+        t_want, out_want = backend.otsu_threshold(x, 255)
+        assert host(backend, t).tolist() == host(backend, t_want).tolist()
+        assert_same(host(backend, out), host(backend, out_want), "otsu begin/finish")
+        frames = a if a.ndim == 3 else a[None]
+        assert host(backend, t).tolist() == [O.otsu_value(p) for p in frames]
+        assert other.shape == x.shape
+
+
 def test_equalize_hist(backend, rng):
     for img in (rnd(rng, (64, 80), U8), blobs(rng, (130, 257), U8), np.full((9, 9), 7, U8)):
         got = host(backend, backend.equalize_hist(dev(backend, img)))

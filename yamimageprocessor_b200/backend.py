@@ -342,6 +342,46 @@ class Backend:
                    _dtype_code(img), float(maxval), self._p(t), None)
         return t, out
 
+    def otsu_begin(self, img):
+        """First half of ``otsu_threshold`` for schedules that have other GPU work to enqueue before
+        the thresholds are needed (the fp64 Otsu recurrence is sequential; on the host it can overlap
+        that work).  Returns a handle for ``otsu_finish``."""
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        if img.dtype == torch.uint8 or self.lib.yam_otsu_prefers_device(n):
+            # 256-bin and staged device scans are asynchronous already: run the whole operator now
+            t, _ = self.otsu_threshold(img, want_image=False)
+            return {"img": img, "t": t}
+        hist = self.histogram(img)
+        host = torch.empty(hist.shape, dtype=hist.dtype, pin_memory=True)
+        host.copy_(hist, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        return {"img": img, "hist_host": host, "ready": ready}
+
+    def otsu_finish(self, handle, maxval: float = 255.0, want_image: bool = True):
+        """Second half: (thresholds int32[n] on device, thresholded image or None)."""
+        torch = _torch()
+        img = handle["img"]
+        n, h, w = self._nhw(img)
+        t = handle.get("t")
+        if t is None:
+            handle["ready"].synchronize()
+            hists = handle["hist_host"].numpy()
+            t_pinned = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+            t_host = t_pinned.numpy()
+            _lib.check("yam_otsu_from_hists", self.lib.yam_otsu_from_hists(
+                hists.ctypes.data_as(C.c_void_p), int(hists.shape[-1]), n, t_host.ctypes.data_as(C.c_void_p)))
+            t = t_pinned.to(self.device, non_blocking=True)   # no stream drain: the GPU keeps its queue
+            t._yam_host_ref = t_pinned  # type: ignore[attr-defined]
+        out = None
+        if want_image:
+            out = torch.empty_like(img)
+            self._call("yam_threshold_frames", self._p(img), self._p(out), n, h, w, _dtype_code(img), self._p(t),
+                       float(maxval))
+        return t, out
+
     def equalize_hist(self, img):
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8,))

@@ -1113,6 +1113,43 @@ int yam_set_host_threads(int threads) {
     return host_threads();
 }
 
+// cost model shared by yam_otsu_threshold and yam_otsu_prefers_device (measured on B200 boxes):
+// 0.45 ms per frame and host thread + 12 us read-back per frame on the host, 2.75 ms per launch
+// group of <= kStageChunk frames on the device
+static constexpr int64_t kDeviceScanFrames = 8, kStageChunk = 256;
+static bool otsu_scan_on_device(int64_t n) {
+    const int64_t ht = host_threads();
+    const double host_ms = (double)((n + ht - 1) / ht) * 0.45 + (double)n * 0.012;
+    const double dev_ms = (double)((n + kStageChunk - 1) / kStageChunk) * 2.75;
+    return n >= kDeviceScanFrames && dev_ms < host_ms;
+}
+
+int yam_otsu_prefers_device(int64_t n) { return otsu_scan_on_device(n) ? 1 : 0; }
+
+int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out_thresholds) {
+    YAM_REQUIRE(hists && out_thresholds && bins > 0 && n > 0, "yam_otsu_from_hists: bad arguments");
+    if (n == 1) {
+        out_thresholds[0] = yam_host_otsu(hists, bins);
+        return YAM_OK;
+    }
+    ScanPool& pool = ScanPool::instance();
+    for (int64_t f = 0; f < n; f++) {
+        const uint64_t* hp = hists + f * bins;
+        int32_t* outp = out_thresholds + f;
+        pool.submit([hp, outp, bins] { *outp = yam_host_otsu(hp, bins); });
+    }
+    pool.wait_all();
+    return YAM_OK;
+}
+
+int yam_threshold_frames(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+                         const int32_t* thresh_dev, double maxval) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && thresh_dev && n > 0 && h > 0 && w > 0 && n <= 65535, "threshold_frames: bad arguments");
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "threshold_frames: unsupported dtype %d", dtype);
+    return yam_threshold_dev(ctx, src, dst, n, h * w, dtype, thresh_dev, maxval);
+}
+
 int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, int dtype, uint64_t* hist_dev) {
     if (int rc = yam_enter(ctx)) return rc;
     YAM_REQUIRE(src && hist_dev && n > 0 && h > 0 && w > 0 && n <= 65535, "histogram: bad arguments");
@@ -1135,13 +1172,7 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     // Fewer frames: the fp64 recurrence is sequential per frame, 65536 dependent divisions take
     // ~0.4 ms on a CPU core, so the histograms are read back and scanned on host threads.
     // 256-bin histograms are scanned by one device thread per frame.
-    // Cost model (measured on B200 boxes): 0.45 ms per frame and host thread + 12 us read-back per
-    // frame on the host, 2.75 ms per launch group of <= kStageChunk frames on the device.
-    constexpr int64_t kDeviceScanFrames = 8, kStageChunk = 256;
-    const int64_t ht = host_threads();
-    const double host_ms = (double)((n + ht - 1) / ht) * 0.45 + (double)n * 0.012;
-    const double dev_ms = (double)((n + kStageChunk - 1) / kStageChunk) * 2.75;
-    const bool staged_scan = (dtype == YAM_U16) && n >= kDeviceScanFrames && dev_ms < host_ms;
+    const bool staged_scan = (dtype == YAM_U16) && otsu_scan_on_device(n);
     const bool host_scan = (dtype == YAM_U16) && !staged_scan;
     const int64_t nf_max = n < kStageChunk ? n : kStageChunk;
     const size_t arr_bytes = yam_align_up(sizeof(double) * bins * nf_max, 256);
