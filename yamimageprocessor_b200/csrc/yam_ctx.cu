@@ -309,8 +309,80 @@ static int host_otsu_impl(const CountT* h, int bins) {
     return max_val;
 }
 
+// K frames advanced in lock step by one thread: the recurrence of a frame is a chain of dependent
+// mul -> add -> div (~22 cycles per bin on a CPU core), so K independent chains fill the pipeline
+// that one chain leaves idle.  Same operations per frame as host_otsu_impl, hence the same results.
+template <typename CountT, int K>
+static void host_otsu_multi(const CountT* const* hs, int bins, int32_t* out) {
+    const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
+    double scale[K], mu[K], mu1[K], q1[K], best[K];
+    int first[K], last[K], best_i[K];
+    int lo = bins, hi = -1;
+    for (int f = 0; f < K; f++) {
+        const CountT* h = hs[f];
+        double total = 0, m = 0;
+        first[f] = -1;
+        last[f] = -1;
+        for (int i = 0; i < bins; i++) {
+            if (h[i]) {
+                if (first[f] < 0) first[f] = i;
+                last[f] = i;
+                total += (double)h[i];
+                m += (double)i * (double)h[i];
+            }
+        }
+        scale[f] = first[f] < 0 ? 0.0 : 1.0 / total;
+        mu[f] = m * scale[f];
+        mu1[f] = q1[f] = best[f] = 0;
+        best_i[f] = 0;
+        if (first[f] >= 0) {
+            if (first[f] < lo) lo = first[f];
+            if (last[f] > hi) hi = last[f];
+        }
+    }
+    for (int i = lo; i <= hi; i++) {
+        for (int f = 0; f < K; f++) {
+            if (i < first[f] || i > last[f]) continue;  // outside the occupied range: state unchanged (see above)
+            const double p_i = (double)hs[f][i] * scale[f];
+            mu1[f] *= q1[f];
+            q1[f] += p_i;
+            const double q2 = 1.0 - q1[f];
+            const double mn = q1[f] < q2 ? q1[f] : q2, mx = q1[f] > q2 ? q1[f] : q2;
+            if (mn < eps || mx > 1.0 - eps) continue;
+            mu1[f] = (mu1[f] + (double)i * p_i) / q1[f];
+            const double mu2 = (mu[f] - q1[f] * mu1[f]) / q2;
+            const double sigma = q1[f] * q2 * (mu1[f] - mu2) * (mu1[f] - mu2);
+            if (sigma > best[f]) {
+                best[f] = sigma;
+                best_i[f] = i;
+            }
+        }
+    }
+    for (int f = 0; f < K; f++) out[f] = first[f] < 0 ? 0 : best_i[f];
+}
+
 int yam_host_otsu(const uint64_t* h, int bins) { return host_otsu_impl<uint64_t>(h, bins); }
 int yam_host_otsu32(const uint32_t* h, int bins) { return host_otsu_impl<uint32_t>(h, bins); }
+
+// `count` (1..4) histograms of `bins` counts each, `stride_bytes` apart, scanned by the calling thread
+void yam_host_otsu_group(const void* hists, size_t stride_bytes, int count, int bins, int narrow, int32_t* out) {
+    const char* base = (const char*)hists;
+    if (narrow) {
+        const uint32_t* hs[4];
+        for (int f = 0; f < count; f++) hs[f] = (const uint32_t*)(base + (size_t)f * stride_bytes);
+        if (count == 4) host_otsu_multi<uint32_t, 4>(hs, bins, out);
+        else if (count == 3) host_otsu_multi<uint32_t, 3>(hs, bins, out);
+        else if (count == 2) host_otsu_multi<uint32_t, 2>(hs, bins, out);
+        else out[0] = host_otsu_impl<uint32_t>(hs[0], bins);
+    } else {
+        const uint64_t* hs[4];
+        for (int f = 0; f < count; f++) hs[f] = (const uint64_t*)(base + (size_t)f * stride_bytes);
+        if (count == 4) host_otsu_multi<uint64_t, 4>(hs, bins, out);
+        else if (count == 3) host_otsu_multi<uint64_t, 3>(hs, bins, out);
+        else if (count == 2) host_otsu_multi<uint64_t, 2>(hs, bins, out);
+        else out[0] = host_otsu_impl<uint64_t>(hs[0], bins);
+    }
+}
 
 extern "C" {
 

@@ -1124,6 +1124,13 @@ static bool otsu_scan_on_device(int64_t n) {
     return n >= kDeviceScanFrames && dev_ms < host_ms;
 }
 
+// frames one pool task scans in lock step: 1 while there are idle threads, up to 4 beyond that
+static int64_t otsu_group_size(int64_t frames) {
+    const int64_t ht = host_threads();
+    int64_t g = (frames + ht - 1) / ht;
+    return g < 1 ? 1 : (g > 4 ? 4 : g);
+}
+
 int yam_otsu_prefers_device(int64_t n) { return otsu_scan_on_device(n) ? 1 : 0; }
 
 int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out_thresholds) {
@@ -1133,10 +1140,12 @@ int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out
         return YAM_OK;
     }
     ScanPool& pool = ScanPool::instance();
-    for (int64_t f = 0; f < n; f++) {
+    const int64_t group = otsu_group_size(n);
+    for (int64_t f = 0; f < n; f += group) {
+        const int cnt = (int)((n - f) < group ? (n - f) : group);
         const uint64_t* hp = hists + f * bins;
         int32_t* outp = out_thresholds + f;
-        pool.submit([hp, outp, bins] { *outp = yam_host_otsu(hp, bins); });
+        pool.submit([hp, outp, bins, cnt] { yam_host_otsu_group(hp, sizeof(uint64_t) * (size_t)bins, cnt, bins, 0, outp); });
     }
     pool.wait_all();
     return YAM_OK;
@@ -1243,14 +1252,18 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
                 const int64_t s0 = k * sub, sn = (nf - s0) < sub ? (nf - s0) : sub;
                 if (ev_err == cudaSuccess) ev_err = cudaEventSynchronize(ev[k]);
                 if (ev_err != cudaSuccess) break;
-                for (int64_t f = s0; f < s0 + sn; f++) {
+                // frames per task: enough tasks for every host thread, then up to 4 frames in lock step
+                const int64_t group = otsu_group_size(nf);
+                for (int64_t f = s0; f < s0 + sn; f += group) {
+                    const int cnt = (int)((s0 + sn - f) < group ? (s0 + sn - f) : group);
                     const char* hp = (const char*)pinned + (size_t)f * count_bytes * bins;
                     int32_t* outp = t_stage + f;
+                    const size_t stride = count_bytes * bins;
                     if (nf == 1) {
-                        *outp = narrow ? yam_host_otsu32((const uint32_t*)hp, bins) : yam_host_otsu((const uint64_t*)hp, bins);
+                        yam_host_otsu_group(hp, stride, 1, bins, narrow ? 1 : 0, outp);
                     } else {
-                        pool.submit([hp, outp, bins, narrow] {
-                            *outp = narrow ? yam_host_otsu32((const uint32_t*)hp, bins) : yam_host_otsu((const uint64_t*)hp, bins);
+                        pool.submit([hp, outp, bins, narrow, cnt, stride] {
+                            yam_host_otsu_group(hp, stride, cnt, bins, narrow ? 1 : 0, outp);
                         });
                     }
                 }

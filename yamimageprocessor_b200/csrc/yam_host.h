@@ -1,5 +1,6 @@
 // Host-side parameter preparation shared by the .cu translation units.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #define YAM_MAX_TAPS 127  // adaptive threshold block size goes to 101 (ui/control_metadata.py:301-309)
@@ -10,3 +11,6 @@ void yam_host_fixed_taps(const double* kf, int k, int bits, int64_t* out);
 void yam_host_structuring_element(int shape, int k, uint8_t* out);
 int yam_host_otsu(const uint64_t* h, int bins);
 int yam_host_otsu32(const uint32_t* h, int bins);  // same recurrence on 32-bit counts (frames < 2^32 px)
+// 1..4 histograms (stride_bytes apart; 32-bit counts if narrow) advanced in lock step by the calling
+// thread: independent dependency chains fill the pipeline one chain leaves idle
+void yam_host_otsu_group(const void* hists, size_t stride_bytes, int count, int bins, int narrow, int32_t* out);
