@@ -197,10 +197,21 @@ __device__ uint32_t ordered_exclusive(unsigned long long* status, int chunk, uin
         const int lane = threadIdx.x;
         if (lane == 0) st_status(status + chunk, kFlagValid | aggregate);
         uint32_t excl = 0;
-        for (int idx = lane; idx < chunk; idx += 32) {
-            unsigned long long st = ld_status(status + idx);
-            while (!(st & kFlagValid)) st = ld_status(status + idx);
-            excl += (uint32_t)st;
+        // 8 status words per lane are requested together (one L2 round trip instead of eight), then
+        // the few that were not published yet are polled
+        for (int base = 0; base < chunk; base += 256) {
+            unsigned long long st[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + 32 * j + lane;
+                st[j] = idx < chunk ? ld_status(status + idx) : kFlagValid;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + 32 * j + lane;
+                while (!(st[j] & kFlagValid)) st[j] = ld_status(status + idx);
+                excl += (uint32_t)st[j];
+            }
         }
         excl = yam_warp_sum(excl);
         if (lane == 0) *s_prefix = excl;
