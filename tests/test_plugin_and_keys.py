@@ -88,3 +88,54 @@ def test_unknown_step_has_no_fallback():
     ex = B200Executor(backend=object())
     with pytest.raises(KeyError, match="no CPU fallback"):
         ex.run_on_device("Watershed", None, {})
+
+
+def test_n3_step_names_and_parameter_names_are_the_references():
+    """the names / parameter keys that feed the cache signatures.  Names from
+    processing/segmentation_pipeline.py:114-122,178-180 and modules/preprocessing.py:161,182; keys and
+    defaults from ui/control_metadata.py:220-245,381-402,677-686."""
+    expected = {
+        "Sharpen": {"strength": 1.0},
+        "SelectChannel": {"channel": "All"},
+        "Sobel": {"ksize": 3},
+        "Prewitt": {},
+        "Laplacian": {"ksize": 3},
+        "Border Removal": {"border_distance": 100},
+    }
+    mods = {cls().metadata.identifier: cls() for cls in plugin.MODULE_CLASSES}
+    for name, defaults in expected.items():
+        assert name in DEVICE_STEPS and name in mods
+        step = mods[name].create_pipeline_step()
+        assert step.name == name and dict(step.params) == defaults
+    # sanitising follows the reference's coercions (odd kernel sizes, clamped ranges, choices)
+    assert mods["Sobel"].sanitize_parameters({"ksize": 4})["ksize"] == 5
+    assert mods["Laplacian"].sanitize_parameters({"ksize": 99})["ksize"] == 31
+    assert mods["Sharpen"].sanitize_parameters({"strength": 9.0})["strength"] == 5.0
+    assert mods["SelectChannel"].sanitize_parameters({"channel": "XYZ"})["channel"] == "All"
+    assert mods["Border Removal"].sanitize_parameters({"border_distance": -3})["border_distance"] == 0
+
+
+def test_executor_bit_run_detection_is_pure_host_logic():
+    """_bit_run_length only looks at names, params and tensor metadata (no GPU needed)."""
+    import torch
+
+    ex = B200Executor(backend=object())
+    mods = {cls().metadata.identifier: cls() for cls in plugin.MODULE_CLASSES}
+
+    def step(name, **params):
+        s = mods[name].create_pipeline_step()
+        s.params.update(params)
+        return s
+
+    plane = torch.empty((8, 8), dtype=torch.uint16)
+    colour = torch.empty((8, 8, 3), dtype=torch.uint8)
+    chain = [step("Adaptive"), step("Opening", kernel_size=5), step("Closing", kernel_size=5), step("ConnectedComponents"),
+             step("BoxFilter")]
+    assert ex._bit_run_length(chain, 0, plane) == 4
+    assert ex._bit_run_length(chain, 1, plane) == 0                       # a run starts at Adaptive
+    assert ex._bit_run_length(chain, 0, colour) == 0                      # colour input: Adaptive converts to gray first
+    assert ex._bit_run_length([step("Adaptive", block_size=9), step("Opening")], 0, plane) == 0
+    assert ex._bit_run_length([step("Adaptive"), step("Opening", kernel_shape="Elliptical")], 0, plane) == 0
+    assert ex._bit_run_length([step("Adaptive"), step("Erosion"), step("Dilation", kernel_shape="Cross")], 0, plane) == 2
+    assert ex._bit_run_length([step("Adaptive")], 0, plane) == 0          # nothing to fuse with
+    assert ex._bit_run_length([step("Adaptive"), step("ConnectedComponents")], 0, torch.empty((2, 8, 8), dtype=torch.uint8)) == 2
