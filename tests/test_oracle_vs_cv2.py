@@ -154,3 +154,44 @@ def test_edge_operators(rng, dt):
         want = np.uint8(np.clip(cv2.magnitude(fx.astype(np.float32), fy.astype(np.float32)), 0, 255))
         diff = O.prewitt_magnitude(small).astype(np.int16) - want.astype(np.int16)
         assert diff.min() >= 0 and diff.max() <= 1  # approximate float32 sqrt inside cv2.magnitude (see test_golden.py)
+
+
+def test_moment_algebra_vs_cv2(rng):
+    """host/moments.py (product-side float64 algebra on exact integer sums) against cv2.moments /
+    cv2.HuMoments on random masks: raw moments exact while they fit 2^53, Hu moments to 1e-9."""
+    from yamimageprocessor_b200.host import moments as M
+
+    for shape in ((48, 64), (33, 71), (200, 300), (480, 640)):
+        mask = ((rng.random(shape) < 0.3).astype(np.uint8)) * 255
+        mask[shape[0] // 4: shape[0] // 2, shape[1] // 3: shape[1] // 2] = 255
+        rows = np.zeros((shape[0], 4), np.int64)
+        ys, xs = np.nonzero(mask)
+        for p in range(4):
+            np.add.at(rows[:, p], ys, xs.astype(np.int64) ** p)
+        raw = M.raw_moments_from_rows(rows)
+        ref = cv2.moments(mask)
+        for key, val in raw.items():
+            assert val == ref[key], key
+        full = M.complete_moments(raw)
+        for key in ("mu20", "mu11", "mu02", "mu30", "mu21", "mu12", "mu03", "nu20", "nu11", "nu02", "nu30", "nu21", "nu12", "nu03"):
+            assert abs(full[key] - ref[key]) <= 1e-9 * max(1.0, abs(ref[key])), key
+        np.testing.assert_allclose(M.hu_moments(full), cv2.HuMoments(ref).ravel(), rtol=1e-9, atol=0)
+    empty = M.complete_moments(M.raw_moments_from_rows(np.zeros((8, 4), np.int64)))
+    assert all(v == 0.0 for v in empty.values())
+
+
+def test_histogram_statistics_vs_reference_formula(rng):
+    from scipy.stats import kurtosis, skew
+
+    from yamimageprocessor_b200.host import moments as M
+
+    for img in (rnd(rng, (64, 80), U8), (rnd(rng, (90, 70), U8) >> 2).astype(U8)):
+        hist = cv2.calcHist([img], [0], None, [256], [0, 256]).flatten()
+        total = np.sum(hist)
+        pixels = np.arange(256)
+        mean_val = np.sum(pixels * hist) / total
+        var_val = np.sum(((pixels - mean_val) ** 2) * hist) / total
+        data = np.repeat(pixels, hist.astype(int))
+        want = [mean_val, var_val, skew(data), kurtosis(data)]
+        st = M.histogram_statistics(np.bincount(img.ravel(), minlength=256))
+        np.testing.assert_allclose([st["mean"], st["variance"], st["skewness"], st["kurtosis"]], want, rtol=1e-9, atol=0)
