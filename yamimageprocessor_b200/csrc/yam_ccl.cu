@@ -866,7 +866,7 @@ constexpr int kBand = 32;   // rows per block band
 constexpr int kRowsPerIter = 4;
 
 template <typename TI>
-__global__ void __launch_bounds__(kThreads) props_kernel(const int32_t* __restrict__ labels,
+__global__ void __launch_bounds__(kThreads, 4) props_kernel(const int32_t* __restrict__ labels,
                                                          const TI* __restrict__ intensity, int h, int w,
                                                          int64_t n_labels, long long* __restrict__ props,
                                                          const int64_t* __restrict__ frame_offsets) {
