@@ -10,6 +10,9 @@
 //   * CLAHE: ONE CTA per CLAHE tile does histogram -> clip -> redistribute -> prefix sum -> LUT
 //     entirely on chip and writes only the 128 KiB LUT (no histogram ever reaches HBM).
 // 8-bit histograms use per-warp privatised 256-bin shared histograms.
+// Otsu's fp64 recurrence over the 65536 bins is sequential per frame: single frames are scanned on
+// a host thread (0.47 ms), stacks on a pool of host threads (up to 4 frames in lock step per
+// thread) or, when this rank has few host threads, by the staged device scan below.
 #include <math.h>
 
 #include <atomic>
