@@ -114,7 +114,7 @@ def test_n3_steps(gold_n3, tag):
     for name, img in (("noise", noise), ("ramp", ramp)):
         got, want = O.prewitt_magnitude(img), g[f"prewitt_{name}_{tag}"]
         diff = got.astype(np.int16) - want.astype(np.int16)
-        assert diff.min() >= 0 and diff.max() <= 1, f"Prewitt {name}"
+        assert np.abs(diff).max() <= 1, f"Prewitt {name}"   # tolerance: 1 LSB either way (SIMD-path dependent sqrt)
         assert (diff != 0).mean() < 0.01
 
 

@@ -226,12 +226,14 @@ def test_n3_plugin_steps_match_reference_outputs(backend, gold_n3, mods, tag):
         eq(mods["Border Removal"].process(noise, border_distance=bd), g[f"border{bd}_{tag}"], f"Border Removal {bd}")
     eq(mods["Border Removal"].process(bgr, border_distance=5), g[f"border5_bgr_{tag}"], "Border Removal colour")
     for name, img in (("noise", noise), ("ramp", ramp)):
-        # bit-exact against the oracle; <= 1 LSB against the reference (approximate float32 sqrt in
-        # the wheel's cv2.magnitude, see tests/test_golden.py)
+        # bit-exact against the oracle; |diff| <= 1 LSB against the reference fixture: the wheel's float32
+        # cv2.magnitude goes through an approximate square root whose last bit depends on the SIMD path
+        # the wheel dispatches to, so a regenerated fixture moves a few pixels by +-1 either way
+        # (tests/test_golden.py states the same tolerance)
         got = mods["Prewitt"].process(img)
         eq(got, O.prewitt_magnitude(img), f"Prewitt {name} vs oracle")
         diff = got.astype(np.int16) - g[f"prewitt_{name}_{tag}"].astype(np.int16)
-        assert diff.min() >= 0 and diff.max() <= 1
+        assert np.abs(diff).max() <= 1   # tolerance: 1 LSB of the uint8 output
 
 
 def test_n3_channel_means_and_limits(backend, gold_n3, mods):

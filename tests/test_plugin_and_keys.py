@@ -34,7 +34,7 @@ def test_register_module_registers_every_operator():
     ids = [cls().metadata.identifier for cls in core.registered]
     assert len(ids) == len(set(ids)) == len(plugin.MODULE_CLASSES)
     for expected in ("Grayscale", "NoiseReduction", "IntensityNormalization", "BrightnessContrast", "Gamma",
-                     "Otsu", "Adaptive", "Opening", "Closing", "Dilation", "Erosion", "Region Properties"):
+                     "Otsu", "Adaptive", "Opening", "Closing", "Dilation", "Erosion", "RegionLabels"):
         assert expected in ids
     assert set(ids) == set(DEVICE_STEPS)  # every registered step has a kernel, and vice versa
     for i in ids:
@@ -50,7 +50,8 @@ def test_pipeline_steps_keep_reference_names_params_and_are_gpu_marked():
     assert mods["Opening"].create_pipeline_step().params == {"kernel_shape": "Rectangular", "kernel_size": 3, "iterations": 1}
     assert mods["Adaptive"].create_pipeline_step().params == {"block_size": 11, "C": 2}
     assert mods["Adaptive"].metadata.stage is ModuleStage.SEGMENTATION
-    assert mods["Region Properties"].metadata.stage is ModuleStage.ANALYSIS
+    assert mods["RegionLabels"].metadata.stage is ModuleStage.ANALYSIS
+    assert "Region Properties" not in mods  # the reference step of that name returns an annotated image
 
 
 def test_sanitize_parameters_matches_reference_registry():

@@ -201,8 +201,8 @@ class Backend:
         if img.dim() == 2 or (img.dim() == 3 and img.shape[-1] not in (3, 4)):
             return img
         img = self._check(img, ndim=(3, 4), dtypes=(torch.uint8, torch.uint16, torch.float32))
-        if img.shape[-1] == 4:  # cv2 BGRA2GRAY ignores alpha; BGR2GRAY itself rejects 4 channels
-            raise ValueError("bgr2gray expects 3 channels (cv2.COLOR_BGR2GRAY)")
+        if img.shape[-1] == 4:  # cv2.cvtColor(BGRA, COLOR_BGR2GRAY) ignores alpha (verified against cv2 4.13)
+            img = img[..., :3].contiguous()
         lead = img.shape[:-1]
         n = 1 if img.dim() == 3 else int(img.shape[0])
         h, w = int(lead[-2]), int(lead[-1])

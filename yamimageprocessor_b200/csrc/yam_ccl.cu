@@ -1232,7 +1232,7 @@ static int region_props_impl(yam_ctx* ctx, const int32_t* labels, const void* in
                              int64_t h, int64_t w, const int64_t* offsets_dev, int64_t n_labels, int64_t* props_dev) {
     if (int rc = yam_enter(ctx)) return rc;
     YAM_REQUIRE(labels && n > 0 && n <= 65535 && h > 0 && w > 0 && n_labels >= 0, "region_props: bad arguments");
-    YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "region_props: image side too large");
+    YAM_REQUIRE(h < (1 << 24) && w < (1 << 24), "region_props: image side must be below 2^24 (32-bit band partial sums)");
     if (n_labels == 0) return YAM_OK;
     YAM_REQUIRE(props_dev, "region_props: props_dev is NULL");
     YAM_REQUIRE(!intensity || intensity_dtype == YAM_U8 || intensity_dtype == YAM_U16,

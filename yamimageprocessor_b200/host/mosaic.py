@@ -409,5 +409,46 @@ def run_local_strips(be: Backend, source, local: int, use_dist: bool, params: Op
     return results
 
 
-__all__ = ["HybridComm", "LocalComm", "MosaicParams", "run_local_strips", "StripResult", "TorchComm", "input_rows", "run_emulated", "run_strip",
+class RowSource:
+    """(H, W) row-sliceable view of a lazy image handle for ``ingest.upload_rows``.
+
+    Accepts a ``TiledPipelineImage`` / ``TiledImageRecord`` (the reference's, ``processing/tiled_records.py:15``
+    and ``core/tiled_image.py:52``, or this package's mirrors): rows come from
+    ``read_region((0, r0, W, r1))``, which is a zero-copy memmap slice for ``.npy`` sources
+    (``core/tiled_image.py:137-146``) and a PIL crop otherwise.  Nothing is densified."""
+
+    ndim = 2
+
+    def __init__(self, image):
+        self._image = image
+        shape = image.infer_shape() if hasattr(image, "infer_shape") else tuple(image.shape)
+        if len(shape) != 2:
+            raise ValueError(f"the mosaic pipeline takes a single-channel (H, W) image, got shape {tuple(shape)}")
+        self.shape = (int(shape[0]), int(shape[1]))
+        dt = getattr(image, "dtype", None)
+        if dt is None:
+            dt = image.read_region((0, 0, 1, 1)).dtype
+        self.dtype = np.dtype(dt)
+
+    def __getitem__(self, rows):
+        if not isinstance(rows, slice) or rows.step not in (None, 1):
+            raise TypeError("RowSource supports contiguous row slices only")
+        r0, r1, _ = rows.indices(self.shape[0])
+        return self._image.read_region((0, r0, self.shape[1], r1))
+
+
+def run_source(be: Backend, image, params: Optional[MosaicParams] = None, strips_per_process: int = 1,
+               with_props: bool = False):
+    """The sharded pipeline over a lazy handle or a dense (H, W) array: this process's strips
+    (``strips_per_process`` x world_size strips in total when ``torch.distributed`` is initialised,
+    else ``strips_per_process`` strips on this GPU).  Rows stream host -> pinned ring -> HBM
+    (``ingest.upload_rows``).  Returns the StripResults of this process in strip order."""
+    import torch.distributed as dist
+
+    source = image if isinstance(image, np.ndarray) else RowSource(image)
+    use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return run_local_strips(be, source, int(strips_per_process), use_dist, params, with_props)
+
+
+__all__ = ["HybridComm", "RowSource", "run_source", "LocalComm", "MosaicParams", "run_local_strips", "StripResult", "TorchComm", "input_rows", "run_emulated", "run_strip",
            "strip_rows"]

@@ -111,7 +111,20 @@ MODULE_PARAMS: Dict[str, Dict[str, ParamSpec]] = {
     "Erosion": _morph(),
     "ConnectedComponents": {},
     # ---- extraction (core/extraction.py:57-87) ----
-    "Region Properties": {},
+    # (labels of the Otsu mask; the reference's "Region Properties" STEP returns an annotated copy of its
+    #  input, core/extraction.py:57-68, so the label-producing step carries its own name and signature)
+    "RegionLabels": {},
+    # ---- BASELINE config 4: the whole chain over a tiled handle (supports_tiled_input) ----
+    "Mosaic": {
+        "gauss_ksize": ParamSpec(11, "int", 1, 15, coerce_fn=ensure_odd),
+        "clip_limit": ParamSpec(2.0, "float", 0.0, 40.0, decimals=2),
+        "tile_grid_x": ParamSpec(8, "int", 1, 64),
+        "tile_grid_y": ParamSpec(8, "int", 1, 64),
+        "block_size": ParamSpec(11, "int", 3, 15, coerce_fn=ensure_odd),
+        "C": ParamSpec(2, "int", -10, 10),
+        "morph_ksize": ParamSpec(5, "int", 1, 31, coerce_fn=ensure_odd),
+        "strips": ParamSpec(1, "int", 1, 64),
+    },
 }
 
 __all__ = ["MODULE_PARAMS", "ParamSpec", "ensure_odd"]

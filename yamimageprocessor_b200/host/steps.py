@@ -2,9 +2,12 @@
 
 Keys are the step names the reference uses (they enter the ``pipeline_cache`` signatures):
 preprocessing module identifiers (``modules/preprocessing.py:46,66,89,113,134,161,182``), segmentation
-method names (``processing/segmentation_pipeline.py:84-184``) and the extraction name
-``Region Properties`` (``processing/extraction_pipeline.py:77-127``), plus the north_star ops the
-reference lacks (``CLAHE``, ``BoxFilter``, ``HistogramEqualization``, ``ConnectedComponents``).
+method names (``processing/segmentation_pipeline.py:84-184``), plus the north_star ops the reference
+lacks (``CLAHE``, ``BoxFilter``, ``HistogramEqualization``, ``ConnectedComponents``, ``RegionLabels``).
+The reference's extraction STEP ``Region Properties`` (``processing/extraction_pipeline.py:84-86``)
+returns an annotated copy of its input (``cv2.rectangle`` / ``cv2.circle`` drawing, UI); it is not a
+device step -- a step of that name returning labels would share its cache signature while holding
+different content.  The numbers behind it come from ``region_properties_data``.
 
 Every function takes ``(backend, tensor, params)`` with a CUDA tensor shaped ``(h, w)``,
 ``(n, h, w)`` (stack, processed per frame like ``_apply_slice_wise``) or ``(h, w, 3)`` BGR and
@@ -160,6 +163,21 @@ def region_properties_labels(be: Backend, t, p):
     return be.ccl_label(_as_mask_u8(be, mask))[0]
 
 
+def mosaic_dense(be: Backend, t, p):
+    """The ``Mosaic`` chain on a frame that is already resident (one strip, no collectives): Gaussian ->
+    CLAHE -> adaptive threshold -> open -> close -> labels.  The lazy-handle entry is MosaicModule.process."""
+    from . import mosaic
+
+    mp = mosaic.MosaicParams(gauss_ksize=int(p.get("gauss_ksize", 11)), clip_limit=float(p.get("clip_limit", 2.0)),
+                             tile_grid=(int(p.get("tile_grid_x", 8)), int(p.get("tile_grid_y", 8))),
+                             block_size=int(p.get("block_size", 11)), C=float(p.get("C", 2)),
+                             morph_ksize=int(p.get("morph_ksize", 5)))
+    t = _plane_only(t, "Mosaic")
+    if t.dim() != 2:
+        raise UnsupportedOnDevice("Mosaic: one (H, W) frame at a time")
+    return mosaic.run_strip(be, t, 0, 1, mp, device_source=t).labels
+
+
 DEVICE_STEPS: Dict[str, Callable] = {
     "Grayscale": grayscale,
     "BrightnessContrast": brightness_contrast,
@@ -183,7 +201,8 @@ DEVICE_STEPS: Dict[str, Callable] = {
     "Dilation": _morph(MORPH_DILATE),
     "Erosion": _morph(MORPH_ERODE),
     "ConnectedComponents": connected_components,
-    "Region Properties": region_properties_labels,
+    "RegionLabels": region_properties_labels,
+    "Mosaic": mosaic_dense,
 }
 
 

@@ -76,7 +76,7 @@ def _module(identifier: str, title: str, stage, description: str, menu=("Pre-Pro
         identifier.replace(" ", "") + "Module",
         (_GpuModule,),
         {"IDENTIFIER": identifier, "TITLE": title, "STAGE": stage, "DESCRIPTION": description, "MENU": menu,
-         "__doc__": description},
+         "__doc__": description, "__module__": __name__},
     )
 
 
@@ -125,8 +125,57 @@ ErosionModule = _module("Erosion", "Erosion", ModuleStage.SEGMENTATION,
                         "cv2.erode (core/segmentation.py:303-314).", _SEG)
 ConnectedComponentsModule = _module("ConnectedComponents", "Connected Components", ModuleStage.SEGMENTATION,
                                     "8-connected labels in raster-first order (core/segmentation.py:108, core/extraction.py:60).", _SEG)
-RegionPropertiesModule = _module("Region Properties", "Region Properties", ModuleStage.ANALYSIS,
-                                 "Otsu -> label -> per-region table (core/extraction.py:57-87).", ("Extraction",))
+RegionLabelsModule = _module("RegionLabels", "Region Labels", ModuleStage.ANALYSIS,
+                             "Otsu -> 8-connected labels (core/extraction.py:58-60,72-73); table: region_properties_data().", ("Extraction",))
+
+class MosaicModule(_GpuModule):
+    """Whole preprocess + segment pipeline over a LAZY tiled handle (BASELINE config 4).
+
+    ``supports_tiled_input() -> True`` makes ``PipelineManager._apply_tiled`` hand the
+    ``TiledPipelineImage`` itself to this step (``processing/pipeline_manager.py:412-416``,
+    ``PipelineStep.apply`` ``:98-99``) instead of cutting halo-less tiles: rows are
+    streamed from the handle (memmap slices) through a pinned ring into HBM and processed as row
+    strips with over-fetched halos -- Gaussian -> CLAHE -> (Otsu) -> adaptive threshold -> open ->
+    close -> connected components -- giving exactly the labels of the dense chain.  Under
+    ``torch.distributed`` every process runs its own strips (LUT all-gather, histogram all-reduce,
+    cross-strip label merge) and returns the label rows it owns.
+
+    ``requires_gpu`` stays False here on purpose: ``_run_step`` densifies tiled input before calling a
+    ``GpuExecutor`` (``:449-454``); this step's ``process`` is itself the GPU call."""
+
+    IDENTIFIER = "Mosaic"
+    TITLE = "Mosaic Preprocess + Segment"
+    STAGE = ModuleStage.SEGMENTATION
+    DESCRIPTION = "Row-strip sharded Gaussian -> CLAHE -> adaptive threshold -> open/close -> labels over a tiled handle."
+    MENU = ("Segmentation",)
+
+    def supports_tiled_input(self) -> bool:
+        return True
+
+    def pipeline_execution_metadata(self):
+        return StepExecutionMetadata(supports_inplace=False, requires_gpu=False)
+
+    def process(self, image, **kwargs: Any) -> np.ndarray:
+        from ..host import ingest, mosaic
+
+        p = self.sanitize_parameters(kwargs)
+        mp = mosaic.MosaicParams(gauss_ksize=int(p["gauss_ksize"]), clip_limit=float(p["clip_limit"]),
+                                 tile_grid=(int(p["tile_grid_x"]), int(p["tile_grid_y"])),
+                                 block_size=int(p["block_size"]), C=float(p["C"]), morph_ksize=int(p["morph_ksize"]))
+        be = _executor().backend
+        if isinstance(image, np.ndarray) and image.ndim != 2:
+            raise ValueError("Mosaic expects a single-channel (H, W) image or tiled handle")
+        results = mosaic.run_source(be, image, mp, strips_per_process=int(p["strips"]))
+        self.last_results = results              # Otsu threshold / mask / CLAHE rows stay on the device for callers
+        rows = sum(int(r.labels.shape[0]) for r in results)
+        out = np.empty((rows, int(results[0].labels.shape[1])), np.int32)
+        y = 0
+        for r in results:
+            n = int(r.labels.shape[0])
+            ingest.download_into(be, r.labels, out[y:y + n])
+            y += n
+        return out
+
 
 MODULE_CLASSES = (
     GrayscaleModule,
@@ -151,7 +200,8 @@ MODULE_CLASSES = (
     DilationModule,
     ErosionModule,
     ConnectedComponentsModule,
-    RegionPropertiesModule,
+    RegionLabelsModule,
+    MosaicModule,
 )
 
 
@@ -170,7 +220,7 @@ def region_properties_data(image: np.ndarray) -> Dict[str, np.ndarray]:
     be = ex.backend
     t = be.to_device(np.asarray(image))
     gray = be.bgr2gray(t)
-    labels = ex.run_on_device("Region Properties", gray, {})
+    labels = ex.run_on_device("RegionLabels", gray, {})
     return region_table(be, labels, gray if gray.dtype in _intensity_dtypes() else None)
 
 
