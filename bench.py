@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the hot path (megapixels/s per pipeline, HBM-roofline fraction, CPU reference).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
 
-A "step" is one pass of the named pipeline over one batch of synthetic frames on every rank.
-Default workload = BASELINE.json configs[1]: segmentation (adaptive threshold 11/2 -> open 5x5 ->
-close 5x5 -> connected components) on a synthetic 8192x8192 uint16 frame per GPU.
-N > 1 (torchrun, one rank per GPU): frames are independent units, every rank processes its own
-frame(s), no data-path collective -> weak scaling; time = max over ranks.
+A "step" is one pass of the named pipeline over the whole synthetic job.
+Default workload = c4, BASELINE.json configs[3]: the 65536x65536 uint16 mosaic, full preprocess +
+segment, as ONE row strip per GPU (whole CLAHE tile rows, over-fetched halos, LUT all-gather,
+histogram all-reduce, cross-strip label merge) -> STRONG scaling over N = 1, 2, 4, 8 (the config the
+north_star's 8-GPU target is quoted on; it fits one B200, so N = 1 runs it as a single strip with no
+collective).  c5 = 1024 frames of 2048x2048 split N ways (strong).  c1 / c2 / c3 are the single-frame
+configs (replicas only: every rank runs its own frame, weak).  Time = max over ranks.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §6 for the definition of every key.
 """
@@ -41,11 +43,13 @@ WORKLOADS = {
                name="extraction: per-region area/centroid/bbox/mean-intensity on the labelled 8192x8192 frame (~99k nuclei)"),
     "c4": dict(h=65536, w=65536, frames=1, bpp=28.0,
                name="mosaic: 65536x65536 uint16, preprocess (Gaussian k=11 -> CLAHE 8x8 -> Otsu) + segment (adaptive -> "
-                    "open/close 5x5 -> connected components) in 8 row strips of whole CLAHE tile rows, halo over-fetch, "
-                    "LUT all-gather, histogram all-reduce, cross-strip label merge"),
-    "c5": dict(h=2048, w=2048, frames=32, bpp=34.0,
-               name="time-lapse: preprocess+segment+extract on a batch of 2048x2048 uint16 frames, frame-sharded"),
+                    "open/close 5x5 -> connected components), one row strip of whole CLAHE tile rows per GPU, halo "
+                    "over-fetch, LUT all-gather, histogram all-reduce, cross-strip label merge"),
+    "c5": dict(h=2048, w=2048, frames=1024, bpp=34.0,
+               name="time-lapse: 1024 frames of 2048x2048 uint16 through preprocess+segment+extract, frame-sharded "
+                    "(1024/N frames per GPU, batches of 32 frames per launch)"),
 }
+C5_BATCH = 32
 
 
 def _peaks():
@@ -60,50 +64,63 @@ def _peaks():
 
 
 def _traffic(op_name: str, px: int):
-    """Measured DRAM bytes per launch of an operator (ncu --set full, profiles/r01_traffic_c2.json);
-    None when no capture exists for this operator at this frame size."""
-    p = ROOT / "profiles" / "r01_traffic_c2.json"
-    try:
-        d = json.loads(p.read_text())
-    except Exception:
-        return None
-    if int(d.get("pixels", 0)) != int(px):
-        return None
-    for key, row in d.get("ops", {}).items():
-        if op_name.startswith(key):
-            return int(row["dram_read_bytes"]) + int(row["dram_write_bytes"])
+    """Measured DRAM bytes per launch of an operator (ncu --set full; profiles/r0*_traffic_*.json);
+    None when no capture exists for this operator at this pixel count."""
+    for name in ("r02_traffic_c4.json", "r02_traffic_c2.json", "r01_traffic_c2.json"):
+        try:
+            d = json.loads((ROOT / "profiles" / name).read_text())
+        except Exception:
+            continue
+        if int(d.get("pixels", 0)) != int(px):
+            continue
+        for key, row in d.get("ops", {}).items():
+            if op_name.startswith(key):
+                return int(row["dram_read_bytes"]) + int(row["dram_write_bytes"])
     return None
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU reference arm
+# CPU reference arm: the unmodified reference when its checkout is importable (build container),
+# else its call sites restated on the same cv2 (oracle/ref_path.py says which) -- all host threads.
 def _cpu_pipeline(workload: str):
-    from oracle import cv2_path as P
+    from oracle import ref_path as R
 
     if workload == "c1":
-        return lambda fr, aux: [P.preprocess(f) for f in fr], P
+        return lambda fr, aux: [R.preprocess(f) for f in fr], R
     if workload == "c2":
-        return lambda fr, aux: [P.segment(f) for f in fr], P
+        return lambda fr, aux: [R.segment(f) for f in fr], R
     if workload == "c3":
-        return lambda fr, aux: [P.extract(l, f) for f, l in zip(fr, aux)], P
-    return lambda fr, aux: [P.full_chain(f) for f in fr], P  # c4 / c5
+        return lambda fr, aux: [R.extract(l, f) for f, l in zip(fr, aux)], R
+    if workload == "c4":
+        return lambda fr, aux: [R.mosaic_chain(f) for f in fr], R
+    return lambda fr, aux: [R.full_chain(f) for f in fr], R  # c5
 
 
-def _cpu_inputs(workload: str, cfg, sample_frames: int, sample_hw):
-    h, w = sample_hw
-    frames = [synth.nuclei(h, w, seed=100 + i) for i in range(sample_frames)]
+def cpu_sample(workload: str):
+    """(frames, aux, description): the bounded sample of the workload one CPU step processes."""
+    cfg = WORKLOADS[workload]
+    if workload == "c4":
+        # an 8192 x 8192 crop of the mosaic (two by two of its 4096^2 source frames): ~3 s of CPU work per step
+        tiles = mosaic_tiles(4096)
+        frame = mosaic_rows(8192, 0, 8192, 4096, tiles)
+        return [frame], None, "rows 0..8191 x cols 0..8191 of the same synthetic 65536^2 mosaic (1/64 of the job)"
+    if workload == "c5":
+        frames = [synth.nuclei(cfg["h"], cfg["w"], seed=1000 + i) for i in range(8)]
+        return frames, None, "frames 0..7 of the 1024-frame job (1/128 of the job)"
+    frames = [synth.nuclei(cfg["h"], cfg["w"], seed=1000)]
     aux = None
     if workload == "c3":
-        from oracle import cv2_path as P
+        from oracle import ref_path as R
 
-        aux = [P.segment(f) for f in frames]
-    return frames, aux
+        aux = [R.segment(f) for f in frames]
+    return frames, aux, f"the whole job: 1 frame of {cfg['h']}x{cfg['w']} uint16 (seed 1000)"
 
 
-def cpu_measure(workload: str, cfg, repeats: int, warmup: int, sample_hw, sample_frames: int = 1):
-    fn, P = _cpu_pipeline(workload)
-    frames, aux = _cpu_inputs(workload, cfg, sample_frames, sample_hw)
-    px = sample_frames * sample_hw[0] * sample_hw[1]
+def cpu_measure(workload: str, repeats: int, warmup: int):
+    """Mean over `repeats` timed passes of the CPU path on the bounded sample (same statistic as the GPU arm)."""
+    fn, R = _cpu_pipeline(workload)
+    frames, aux, what = cpu_sample(workload)
+    px = sum(int(f.shape[0]) * int(f.shape[1]) for f in frames)
     for _ in range(warmup):
         fn(frames, aux)
     times = []
@@ -111,16 +128,16 @@ def cpu_measure(workload: str, cfg, repeats: int, warmup: int, sample_hw, sample
         t0 = time.perf_counter()
         fn(frames, aux)
         times.append(time.perf_counter() - t0)
-    best = min(times)
+    mean_s = statistics.mean(times)
+    kind, detail = R.describe()
     return dict(
-        value=px / MP / best,
+        value=px / MP / mean_s,
         unit="megapixels/s",
-        cores=int(P.THREADS),
-        kind="port",
-        sample=f"{sample_frames} frame(s) of {sample_hw[0]}x{sample_hw[1]} uint16 of the same synthetic workload, "
-               f"best of {repeats}; {P.KIND}; host cores visible {os.cpu_count()}",
-        ms=best * 1e3,
-    ), statistics.mean(times)
+        cores=int(R.THREADS),
+        kind=kind,
+        sample=f"{what}; mean of {repeats} pass(es) after {warmup} warm-up; {detail}; host cores visible {os.cpu_count()}",
+        ms=mean_s * 1e3,
+    ), mean_s
 
 
 def run_reference(args):
@@ -128,12 +145,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = WORKLOADS[args.workload]
-    sample_hw = (cfg["h"], cfg["w"]) if cfg["h"] <= 4096 else (4096, 4096)
-    sample_frames = 1 if args.workload != "c5" else 2
-    base, mean_s = cpu_measure(args.workload, cfg, max(1, args.steps), max(0, args.warmup), sample_hw, sample_frames)
-    px = sample_frames * sample_hw[0] * sample_hw[1]
-    value = px / MP / mean_s
-    base["value"] = value
+    base, mean_s = cpu_measure(args.workload, max(1, args.steps), max(0, args.warmup))
+    value = base["value"]
     line = {
         "impl": "reference",
         "metric": "megapixels/s per pipeline",
@@ -144,11 +157,13 @@ def run_reference(args):
         "warmup": args.warmup,
         "ms_per_step": mean_s * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if args.workload in ("c4", "c5") else "weak",
         "vs_baseline": None,
         "dtype": "u16",
         "data": "synthetic",
-        "config": {"workload": cfg["name"], "sample": base["sample"]},
+        "config": {"workload": cfg["name"], "sample": base["sample"],
+                   "note": "CPU arm: each step is the bounded sample named in `sample`; value = sample megapixels / mean step time "
+                           "(the CPU path does not speed up with --gpus)"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "megapixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,6 +241,9 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
 
     stack = np.stack(frames_np) if len(frames_np) > 1 else frames_np[0]
     x = be.to_device(stack)
+    if workload == "c5" and cfg.get("frames_rank", len(frames_np)) > len(frames_np):
+        # this rank's share of the 1024 frames, resident in HBM: the distinct synthetic frames, cycled
+        x = x.repeat(cfg["frames_rank"] // len(frames_np), 1, 1)
 
     if workload == "c1":
         def run(inp):
@@ -302,8 +320,8 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             return [("region_props (props_kernel)", 6.0, lambda: be.region_props(inp_[0], inp_[1], inp_[2]))]
         return inp, run, ops
 
-    # c5: per-frame full chain on a stack (n, h, w)
-    def run(inp):
+    # c5: per-frame full chain on stacks (n, h, w), C5_BATCH frames per launch, over this rank's share
+    def run_batch(inp):
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
         t, otsu_mask = be.otsu_threshold(c, 255)
@@ -311,7 +329,14 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         tables, offsets = be.region_props_stack(labels, c, counts)
         return otsu_mask, labels, tables
 
+    def run(inp):
+        out = None
+        for b0 in range(0, int(inp.shape[0]), C5_BATCH):
+            out = run_batch(inp[b0:b0 + C5_BATCH])
+        return out
+
     def ops(inp):
+        inp = inp[:C5_BATCH]
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
         wd = int(inp.shape[-1])
@@ -330,7 +355,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
     return x, run, ops
 
 
-def e2e_callable(workload: str, be, frames_np):
+def e2e_callable(workload: str, be, frames_np, pinned: bool = False):
     """The same pipeline through the reference-facing API with HOST buffers (H2D + D2H inside)."""
     from yamimageprocessor_b200.host.executor import B200Executor
     from yamimageprocessor_b200.host.pipeline import PipelineManager
@@ -346,8 +371,11 @@ def e2e_callable(workload: str, be, frames_np):
 
     ex = B200Executor(be)
     stack = np.stack(frames_np) if len(frames_np) > 1 else frames_np[0]
-    host_in = be.pinned_empty(stack.shape, stack.dtype)
-    host_in[...] = stack
+    if pinned:
+        host_in = be.pinned_empty(stack.shape, stack.dtype)
+        host_in[...] = stack
+    else:
+        host_in = np.array(stack, copy=True)   # ordinary pageable memory, what the reference's callers hold
     if workload == "c1":
         pm = PipelineManager([step("NoiseReduction", method="Gaussian", ksize=11), step("CLAHE"), step("Otsu")],
                              gpu_executor=ex)
@@ -375,6 +403,11 @@ class _Shape:
         self.shape = (h, w)
 
 
+def mosaic_tiles(tile: int):
+    """The distinct seeded source frames the synthetic mosaic is assembled from (seeds 100..103)."""
+    return [synth.nuclei(tile, tile, seed=100 + i) for i in range(4)]
+
+
 def mosaic_rows(size: int, r0: int, r1: int, tile: int, tiles: list) -> np.ndarray:
     """Rows [r0, r1) of the synthetic mosaic: a size x size grid of `tile`-sized frames drawn from a
     small set of distinct seeded frames (pattern (7*ty + 3*tx) % len(tiles))."""
@@ -390,44 +423,72 @@ def mosaic_rows(size: int, r0: int, r1: int, tile: int, tiles: list) -> np.ndarr
     return out
 
 
+class RowWindowRecord:
+    """Lazy-handle stand-in with the TiledImageRecord surface (core/tiled_image.py:52): a 65536^2
+    mosaic of which THIS process keeps only the rows it will read (its strip + halo) in ordinary
+    pageable memory, served as zero-copy views like slices of a warmed np.memmap.  Reading anything
+    else, or densifying, is an error -- which is the point of the tiled route."""
+
+    def __init__(self, size: int, r0: int, rows: np.ndarray):
+        self.shape, self.dtype, self.size = (size, size), rows.dtype, None
+        self._r0, self._rows = r0, rows
+
+    def read_region(self, box):
+        left, top, right, bottom = box
+        if top < self._r0 or bottom > self._r0 + self._rows.shape[0]:
+            raise IndexError(f"rows [{top}, {bottom}) are not resident in this process")
+        return self._rows[top - self._r0: bottom - self._r0, left:right]
+
+    def to_array(self):
+        raise RuntimeError("the mosaic handle must not be densified")
+
+    def close(self):
+        pass
+
+
+def _u64hex(v: int) -> str:
+    return f"{int(v) & 0xFFFFFFFFFFFFFFFF:016x}"
+
+
 def run_gpu_mosaic(args):
     import torch
     import torch.distributed as dist
 
     from yamimageprocessor_b200.backend import get_backend
     from yamimageprocessor_b200.host import ingest, mosaic
+    from yamimageprocessor_b200.host.pipeline import PipelineManager
+    from yamimageprocessor_b200.host.tiles import TiledPipelineImage
+    from yamimageprocessor_b200.modules import b200_backend as plugin
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     be = get_backend(local_rank)
     cfg = WORKLOADS["c4"]
     size = int(args.mosaic_size)
-    strips_total = 8
-    if strips_total % world:
-        raise SystemExit("c4 needs 1, 2, 4 or 8 ranks")
-    local = strips_total // world
+    if 8 % world:
+        raise SystemExit("c4 needs 1, 2, 4 or 8 ranks (strips are whole rows of the 8x8 CLAHE grid)")
     tile = min(4096, size // 8)
-    tiles = [synth.nuclei(tile, tile, seed=100 + i) for i in range(4)]
+    tiles = mosaic_tiles(tile)
     shape = _Shape(size, size)
     p = mosaic.MosaicParams()
     trace_marks = []
     if os.environ.get("YAM_MOSAIC_TRACE") and rank == 0:
-        # diagnostics: phase end times of rank 0's strips (adds a device sync per phase; not for reported numbers)
+        # diagnostics: phase end times of rank 0 (adds a device sync per phase; not for reported numbers)
         def _trace(name, strip):
             torch.cuda.synchronize()
             trace_marks.append((time.perf_counter(), strip, name))
         p.trace = _trace
-    host_strips, dev_strips = [], []
-    for li in range(local):
-        s = rank * local + li
-        r0, r1 = mosaic.input_rows(size, s, strips_total, p)
-        hs = mosaic_rows(size, r0, r1, tile, tiles)
-        host_strips.append(hs)
-        dev_strips.append(be.to_device(hs))
+    r0, r1 = mosaic.input_rows(size, rank, world, p)
+    c0, c1 = mosaic.strip_rows(size, p.tile_grid[1], rank, world)
+    host_rows = mosaic_rows(size, r0, r1, tile, tiles)          # pageable host memory
+    dev_rows = ingest.upload_rows(be, host_rows, 0, host_rows.shape[0])
+    comm = mosaic.TorchComm() if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -435,12 +496,12 @@ def run_gpu_mosaic(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(device_sources):
-        return mosaic.run_local_strips(be, shape, local, world > 1, p, with_props=False, device_sources=device_sources)
+    def step():
+        return mosaic.run_strip(be, shape, rank, world, p, device_source=dev_rows, comm=comm)
 
-    for _ in range(max(3, args.warmup)):
-        res = step(dev_strips)
-    n_components = res[0].n_components
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        res = step()
     del res
     barrier()
     sampler = ClockSampler(local_rank)
@@ -448,13 +509,15 @@ def run_gpu_mosaic(args):
         sampler.start()
     be.launch_count(reset=True)
     times = []
+    res = None
     for _ in range(args.steps):
+        del res
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         t_step = time.perf_counter()
         trace_marks.clear()
-        res = step(dev_strips)
+        res = step()
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
@@ -464,26 +527,114 @@ def run_gpu_mosaic(args):
                 sys.stderr.write(f"[trace] +{1e3 * (tm - last):7.2f} ms strip {strip} {name}\n")
                 last = tm
             sys.stderr.write(f"[trace] step total {1e3 * (time.perf_counter() - t_step):.2f} ms\n")
-        del res
     barrier()
     launches = be.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(times))
-    # end to end: host strips in, labels + Otsu mask out (pageable host memory of this size is not pinned)
-    barrier()
-    t0 = time.perf_counter()
-    res = mosaic.run_local_strips(be, shape, local, world > 1, p, with_props=False,
-                                  device_sources=[ingest.upload_rows(be, h, 0, h.shape[0]) for h in host_strips])
-    outs = []
-    for r in res:  # results land in fresh pageable arrays, streamed through the pinned ring
-        lab = np.empty(tuple(r.labels.shape), np.int32)
-        msk = np.empty(tuple(r.otsu_mask.shape), np.uint16)
-        outs.append((ingest.download_into(be, r.labels, lab), ingest.download_into(be, r.otsu_mask, msk)))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    h2d = sum(h.nbytes for h in host_strips)
-    d2h = sum(a_.nbytes + b_.nbytes for a_, b_ in outs)
-    del outs, res
+
+    # ---- parity evidence: identical for every N (and equal to the dense single-strip run of
+    # tests/test_gpu_mosaic.py at reduced size): Otsu t, component count, content checksums
+    W = size
+    sums = torch.zeros((2,), dtype=torch.int64, device=be.device)
+    be.checksum64(res.labels, index_base=c0 * W, accumulate=sums[0:1])
+    be.checksum64(res.otsu_mask, index_base=c0 * W, accumulate=sums[1:2])
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)       # int64 addition wraps mod 2^64, like the checksum
+    sums_host = sums.cpu().tolist()
+    check = {"otsu_threshold": int(res.otsu_threshold), "components": int(res.n_components),
+             "labels_checksum64": _u64hex(sums_host[0]), "otsu_mask_checksum64": _u64hex(sums_host[1]),
+             "definition": "yam_checksum64 (include/yamb200.h): sum of mix64(linear index * golden + value) mod 2^64, "
+                           "per-strip sums all-reduced; must be identical for N = 1, 2, 4, 8"}
+    n_components = int(res.n_components)
+    del res
+
+    # ---- per-operator times on this rank's strip (CUDA events, inputs > L2), rank 0 reports
+    strip_px = (c1 - c0) * W
+
+    def measure(fn, reps=3):
+        fn()
+        evs = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            del out
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return statistics.mean(x.elapsed_time(y) for x, y in evs)
+
+    g = be.gaussian(dev_rows, p.gauss_ksize, 0.0)
+    g_core = g[c0 - r0: c1 - r0]
+    luts = be.clahe_luts(g_core, p.clip_limit, (p.tile_grid[0], p.tile_grid[1] // world))
+    th, tw = size // p.tile_grid[1], size // p.tile_grid[0]
+    c = be.clahe_apply(g_core, luts, (tw, th), y_offset=0)
+    bits = be.adaptive_threshold_bits(c, p.block_size, p.C)
+    bits2 = be.bits_morph(bits, W, 4, p.morph_ksize, 1)
+    t_dev = torch.full((1,), 30000, dtype=torch.int32, device=be.device)
+
+    def otsu_op():
+        h = be.histogram(c)
+        return be.threshold(c, 30000.0, 255), h
+
+    def ccl_op():
+        ws, cnt = be.ccl_resolve_bits(bits2, W)
+        return be.ccl_emit(bits2, W, ws)
+
+    op_rows = [
+        ("gaussian_fixed_u16_k11 (sep_fixed_tiled)", 4.0, measure(lambda: be.gaussian(g_core, p.gauss_ksize, 0.0))),
+        ("clahe_u16 (tile LUTs + apply)", 6.0, measure(lambda: be.clahe_apply(
+            g_core, be.clahe_luts(g_core, p.clip_limit, (p.tile_grid[0], p.tile_grid[1] // world)), (tw, th), 0))),
+        ("otsu_u16 (histogram + threshold; the fp64 scan overlaps the segmentation kernels)", 6.0, measure(otsu_op)),
+        ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125,
+         measure(lambda: be.adaptive_threshold_bits(c, p.block_size, p.C))),
+        ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, measure(lambda: be.bits_morph(bits, W, 4, p.morph_ksize, 1))),
+        ("ccl from bits (resolve: scan, tile, border, rank; emit: final_warp)", 4.125, measure(ccl_op)),
+    ]
+    del g, g_core, luts, c, bits, bits2
+
+    # ---- N = 1 only: the same mosaic as 8 lock-step strips on this GPU (round 1's schedule), for comparison
+    alt = None
+    if world == 1 and not args.no_alt:
+        dev8 = []
+        for s8 in range(8):
+            a0, a1 = mosaic.input_rows(size, s8, 8, p)
+            dev8.append(dev_rows[a0:a1])   # views of the resident mosaic
+        for _ in range(2):
+            r8 = mosaic.run_local_strips(be, shape, 8, False, p, device_sources=dev8)
+            del r8
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r8 = mosaic.run_local_strips(be, shape, 8, False, p, device_sources=dev8)
+        b.record()
+        torch.cuda.synchronize()
+        alt = {"schedule": "8 row strips in lock-step host threads on one GPU (in-process collectives)",
+               "ms_per_step": a.elapsed_time(b), "components": int(r8[0].n_components)}
+        del r8, dev8
+
+    # ---- end to end through the reference-facing API: PipelineManager.apply(TiledPipelineImage) ->
+    # supports_tiled_input step (MosaicModule.process): pageable host rows -> pinned ring -> HBM ->
+    # kernels + collectives -> labels back into a fresh pageable array
+    del dev_rows
+    torch.cuda.empty_cache()
+    step_mod = plugin.MosaicModule().create_pipeline_step()
+    step_mod.enabled = True
+    pm = PipelineManager([step_mod])
+    handle = TiledPipelineImage(RowWindowRecord(size, r0, host_rows), tile_size=(tile, tile))
+    e2e_times = []
+    out = None
+    for it in range(2):
+        del out
+        barrier()
+        t0 = time.perf_counter()
+        out = pm.apply(handle)
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = min(e2e_times) if args.e2e_best else statistics.mean(e2e_times)
+    h2d, d2h = int(host_rows.nbytes), int(out.nbytes)
+    e2e_labels_ok = bool(out.shape == (c1 - c0, W) and out.dtype == np.int32)
+    del out
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=be.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -496,25 +647,42 @@ def run_gpu_mosaic(args):
         px = size * size
         ms_per_step = total_ms / args.steps
         value = px / MP / (ms_per_step / 1e3)
-        achieved = px * cfg["bpp"] / (ms_per_step / 1e3) / 1e9
-        cpu, _ = cpu_measure("c5", cfg, 2, 1, (4096, 4096), 1)
+        pipe_achieved = strip_px * cfg["bpp"] / (ms_per_step / 1e3) / 1e9
+        dom = max(op_rows, key=lambda r: r[2])
+        achieved = strip_px * dom[1] / (dom[2] / 1e3) / 1e9
+        cpu, _ = cpu_measure("c4", 2, 1)
         line = {
             "metric": "megapixels/s per pipeline", "value": value, "unit": "megapixels/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": cfg["name"] if size == 65536 else cfg["name"].replace("65536x65536", f"{size}x{size}"),
-                       "mosaic": [size, size], "strips": strips_total, "strips_per_gpu": local,
-                       "components": int(n_components), "algorithmic_bytes_per_px": cfg["bpp"],
-                       "l2": "every strip (>= 1 GiB at 65536^2) exceeds the 126 MB L2", "seed": "tiles 100..103"},
-            "roofline": {"bound": "hbm", "kernel": "whole mosaic pipeline (all kernels of all strips of the slowest rank)",
-                         "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
-                         "traffic": None, "peak_source": peak_src, "per_gpu": True},
+                       "mosaic": [size, size], "strips": world, "strips_per_gpu": 1, "rows_per_gpu": c1 - c0,
+                       "halo_rows_overfetched": [c0 - r0, r1 - c1],
+                       "chain": "Gaussian k=11 -> CLAHE(2.0, 8x8) -> [Otsu mask of the CLAHE output] ; adaptive(11, 2) on the CLAHE "
+                                "output -> open 5x5 -> close 5x5 -> 8-connected labels (SURVEY.md 8(d) chain definition)",
+                       "algorithmic_bytes_per_px": cfg["bpp"],
+                       "l2": "every strip (>= 1 GiB at 65536^2) exceeds the 126 MB L2; no flush needed",
+                       "seed": "source frames 100..103, pattern (7*ty + 3*tx) % 4",
+                       "otsu_scan": "host worker thread, overlapped with the segmentation kernels (fp64 recurrence of 65536 dependent steps)"},
+            "check": check,
+            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": _traffic(dom[0], strip_px),
+                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes": int(strip_px * dom[1]), "peak_source": peak_src,
+                         "scope": f"rank 0's strip ({c1 - c0} rows x {W} px), each operator timed alone with CUDA events",
+                         "pipeline_achieved": pipe_achieved, "pipeline_frac": pipe_achieved / peak, "per_gpu": True,
+                         "ops": [{"op": n, "bytes_per_px": bpp, "ms": m, "GBps": strip_px * bpp / (m / 1e3) / 1e9,
+                                  "frac": strip_px * bpp / (m / 1e3) / 1e9 / peak} for n, bpp, m in op_rows]},
             "cpu_baseline": cpu,
             "e2e": {"value": px / MP / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h),
-                    "api": "host.ingest.upload_rows(pageable strips) -> host.mosaic.run_local_strips -> host.ingest.download_into(fresh pageable arrays): labels + Otsu mask"},
+                    "d2h_bytes_per_step": int(d2h), "host_memory": "pageable in, fresh pageable out",
+                    "statistic": "mean of 2 passes", "labels_shape_ok": e2e_labels_ok,
+                    "api": "PipelineManager([Mosaic step]).apply(TiledPipelineImage) -> MosaicModule.process "
+                           "(supports_tiled_input route, processing/pipeline_manager.py:412-416): int32 label rows"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if alt is not None:
+            line["n1_schedules"] = {"one_strip_ms": ms_per_step, "eight_strips_lockstep": alt}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -541,11 +709,26 @@ def run_gpu(args):
     from yamimageprocessor_b200.backend import get_backend
 
     be = get_backend(local_rank)
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
     h, w, nfr = cfg["h"], cfg["w"], cfg["frames"]
-    frames_np = [synth.nuclei(h, w, seed=1000 + rank * nfr + i) for i in range(nfr)]
+    strong = args.workload == "c5"
+    if strong:
+        # 1024 frames split N ways: this rank's contiguous block (host/sharding.frame_block), resident in HBM
+        from yamimageprocessor_b200.host.sharding import frame_block
+
+        nfr = int(args.frames) if args.frames else nfr
+        f0, f1 = frame_block(nfr, rank, world)
+        if (f1 - f0) % C5_BATCH:
+            raise SystemExit(f"c5: {nfr} frames over {world} ranks must give whole batches of {C5_BATCH}")
+        cfg["frames_rank"] = f1 - f0
+        frames_np = [synth.nuclei(h, w, seed=1000 + i) for i in range(C5_BATCH)]   # distinct frames, cycled
+        frames_rank = f1 - f0
+    else:
+        frames_np = [synth.nuclei(h, w, seed=1000 + rank * nfr + i) for i in range(nfr)]
+        frames_rank = nfr
     inp, run, ops = build_gpu_workload(args.workload, cfg, be, frames_np)
-    px_per_rank = nfr * h * w
+    px_per_rank = frames_rank * h * w
+    px_ops = (C5_BATCH if strong else nfr) * h * w   # the per-operator table is measured on one batch
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=be.device)  # > 126 MB L2
 
@@ -599,36 +782,44 @@ def run_gpu(args):
     breakdown = measure_ops(ops(inp))
     breakdown_unfused = measure_ops(ops.unfused(inp)) if hasattr(ops, "unfused") else []
 
-    # end to end through the reference-facing API, host buffers, wall clock
-    call, h2d_bytes, _pm = e2e_callable(args.workload, be, frames_np)
-    out = call()
-    d2h_bytes = int(getattr(out, "nbytes", 0))
-    for _ in range(2):
+    # end to end through the reference-facing API, HOST buffers, wall clock.  Headline: ordinary pageable
+    # input (what the reference's callers hold); the page-locked variant is reported next to it.
+    # c5: one call per 32-frame batch over this rank's whole share of the job.
+    calls_per_step = frames_rank // C5_BATCH if strong else 1
+
+    def time_e2e(pinned: bool):
+        call, h2d_b, _pm = e2e_callable(args.workload, be, frames_np, pinned=pinned)
+        out = call()
+        d2h_b = int(getattr(out, "nbytes", 0))
+        del out
         call()
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        call()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0)
+        barrier()
+        reps = 1 if strong else max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(reps * calls_per_step):
+            call()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, h2d_b * calls_per_step, d2h_b * calls_per_step
+
+    e2e_s, h2d_bytes, d2h_bytes = time_e2e(pinned=False)
+    e2e_pinned_s, _, _ = time_e2e(pinned=True)
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=be.device)
+        t = torch.tensor([total_ms, e2e_s, e2e_pinned_s], dtype=torch.float64, device=be.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, e2e_pinned_s = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peak, peak_src = _peaks()
         ms_per_step = total_ms / args.steps
-        value = world * px_per_rank / MP / (ms_per_step / 1e3)
-        e2e_value = world * px_per_rank / MP / (e2e_s / e2e_steps)
+        job_px = (nfr if strong else world * nfr) * h * w
+        value = job_px / MP / (ms_per_step / 1e3)
+        e2e_value = job_px / MP / e2e_s
         dom = max(breakdown, key=lambda r: r[2])
-        achieved = px_per_rank * dom[1] / (dom[2] / 1e3) / 1e9
+        achieved = px_ops * dom[1] / (dom[2] / 1e3) / 1e9
         pipe_achieved = px_per_rank * cfg["bpp"] / (ms_per_step / 1e3) / 1e9
-        cpu_hw = (h, w) if h <= 4096 else (4096, 4096)
-        cpu, _ = cpu_measure(args.workload, cfg, 2, 1, cpu_hw, 1 if args.workload != "c5" else 2)
+        cpu, _ = cpu_measure(args.workload, 2, 1)
         line = {
             "metric": "megapixels/s per pipeline",
             "value": value,
@@ -638,17 +829,20 @@ def run_gpu(args):
             "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None,
             "dtype": "u16",
             "data": "synthetic",
             "config": {
                 "workload": cfg["name"],
-                "frames_per_gpu": nfr,
+                "frames_per_gpu": frames_rank,
+                "frames_total": nfr if strong else world * nfr,
                 "frame": [h, w],
                 "algorithmic_bytes_per_px": cfg["bpp"],
                 "l2": "256 MiB flush write between timed steps (not timed)",
-                "seed": "1000 + rank*frames + i",
+                "seed": "1000 + i for 32 distinct frames, cycled over the job" if strong else "1000 + rank*frames + i",
+                "multi_gpu": ("contiguous frame blocks per rank, no data-path collective" if strong
+                              else "replicas only: every rank runs its own frame (SURVEY.md 8e)"),
             },
             "roofline": {
                 "bound": "hbm",
@@ -657,20 +851,22 @@ def run_gpu(args):
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": _traffic(dom[0], px_per_rank),
+                "traffic": _traffic(dom[0], px_ops),
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "algorithmic_bytes": int(px_per_rank * dom[1]),
+                "algorithmic_bytes": int(px_ops * dom[1]),
                 "peak_source": peak_src,
                 "pipeline_achieved": pipe_achieved,
                 "pipeline_frac": pipe_achieved / peak,
-                "ops": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_per_rank * b / (m / 1e3) / 1e9,
-                         "frac": px_per_rank * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown],
-                "ops_unfused": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_per_rank * b / (m / 1e3) / 1e9,
-                                 "frac": px_per_rank * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown_unfused],
+                "ops": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_ops * b / (m / 1e3) / 1e9,
+                         "frac": px_ops * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown],
+                "ops_unfused": [{"op": n, "bytes_per_px": b, "ms": m, "GBps": px_ops * b / (m / 1e3) / 1e9,
+                                 "frac": px_ops * b / (m / 1e3) / 1e9 / peak} for n, b, m in breakdown_unfused],
             },
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": d2h_bytes, "api": "PipelineManager(gpu_executor=B200Executor).apply(ndarray)"},
+            "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": int(h2d_bytes) * (world if strong else world),
+                    "d2h_bytes_per_step": int(d2h_bytes) * world, "host_memory": "pageable in, fresh array out",
+                    "value_pinned_input": job_px / MP / e2e_pinned_s,
+                    "api": "PipelineManager(gpu_executor=B200Executor).apply(ndarray)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -686,9 +882,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--mosaic-size", type=int, default=65536, help="side of the c4 mosaic (multiple of 64)")
+    ap.add_argument("--frames", type=int, default=0, help="c5: total frames of the job (default 1024)")
+    ap.add_argument("--no-alt", action="store_true", help="c4, N=1: skip the 8-lock-step-strips comparison run")
+    ap.add_argument("--e2e-best", action="store_true", help="c4: report the better of the two e2e passes instead of the mean")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -698,7 +897,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
                str(Path(__file__).resolve()), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--workload", args.workload, "--mosaic-size", str(args.mosaic_size)]
+               "--warmup", str(args.warmup), "--workload", args.workload, "--mosaic-size", str(args.mosaic_size),
+               "--frames", str(args.frames)] + (["--no-alt"] if args.no_alt else []) + (["--e2e-best"] if args.e2e_best else [])
         return subprocess.call(cmd)
     return run_gpu(args)
 

@@ -228,6 +228,27 @@ int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* rem
 int yam_merge_strip_labels(yam_ctx* ctx, const int32_t* edges_dev, const int64_t* offsets_dev, int world,
                            int64_t w, int64_t total, int32_t* root_dev);
 
+/* The whole cross-strip step in one call (merge + raster-first renumbering, no host arithmetic on
+ * label arrays).  packed_dev is [world][stride] int32 (stride >= 2w): per strip its first label row
+ * (w values) followed by its last label row (w values) -- what an all-gather of every rank's two
+ * boundary rows delivers; anything after 2w in a row (e.g. the strip's count) is ignored.
+ * offsets_host[world + 1] (HOST memory) is the exclusive prefix of the per-strip component counts.
+ * Writes remap_dev[0 .. count_rank] for strip `rank`: remap[l] = global label of local label l
+ * (remap[0] = 0; labels number merged components by their first pixel in raster order, the same
+ * numbering a dense run produces), and total_dev[0] = number of merged components.  `workspace`:
+ * yam_merge_strips_workspace_bytes(offsets_host[world]) bytes of 256-byte aligned device memory. */
+int64_t yam_merge_strips_workspace_bytes(int64_t total);
+int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                           const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
+                           int32_t* total_dev);
+
+/* Order-independent 64-bit content checksum: ADDS to *sum_dev (device, caller zeroes it) the sum over
+ * i < count of mix64((index_base + i) * 0x9E3779B97F4A7C15 + value_i) mod 2^64 (mix64 = splitmix64's
+ * finalizer; values zero-extended from U8 | U16 | I32 bit patterns).  A row strip passes the linear
+ * index of its first pixel as index_base, so the per-strip sums of a sharded run add up (all-reduce)
+ * to the checksum of the dense image -- bench.py's `check` block and the mosaic parity tests. */
+int yam_checksum64(yam_ctx* ctx, const void* src, int64_t count, int dtype, int64_t index_base, uint64_t* sum_dev);
+
 /* ---- K11 region properties -----------------------------------------------------------------
  * skimage.measure.regionprops restated (core/extraction.py:61,74): for a single labelled frame
  * with labels 1..n_labels writes, per label (row i = label i+1), 8 int64 accumulators to

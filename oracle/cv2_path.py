@@ -92,6 +92,12 @@ def label(mask):  # core/extraction.py:60,73 (skimage.measure.label == scipy.ndi
     return O.ccl_label(mask)[1]
 
 
+def connected_components(mask):  # core/segmentation.py:108 -- the SEGMENTATION call site (8-conn, int32)
+    if not HAVE_CV2:
+        return O.ccl_label(mask)[1]
+    return cv2.connectedComponents(mask)[1]
+
+
 def region_table(labels, intensity):  # core/extraction.py:74-87 (regionprops restated, + mean intensity)
     return O.region_props(labels, intensity)
 
@@ -106,11 +112,12 @@ def preprocess(frame):
 
 
 def segment(frame):
-    """C2: adaptive threshold (11, 2) -> open 5x5 -> close 5x5 -> 8-connected labels."""
+    """C2: adaptive threshold (11, 2) -> open 5x5 -> close 5x5 -> 8-connected labels
+    (cv2.connectedComponents, the segmentation call site; same partition as the raster-first numbering)."""
     m = adaptive_threshold(frame, 11, 2)
     m = morphological_opening(m, "Rectangular", 5, 1)
     m = morphological_closing(m, "Rectangular", 5, 1)
-    return label(m)
+    return connected_components(m)
 
 
 def extract(labels, intensity):
@@ -122,4 +129,10 @@ def full_chain(frame):
     """C4/C5 chain: preprocess, then segment the CLAHE output, then extract."""
     g, otsu_mask = preprocess(frame)
     lab = segment(g)
-    return otsu_mask, lab, extract(lab, g)
+    return otsu_mask, lab, extract(label((lab > 0).astype(np.uint8)), g)   # extraction labels: core/extraction.py:73
+
+
+def mosaic_chain(frame):
+    """C4 chain: preprocess, then segment the CLAHE output (no extraction)."""
+    g, otsu_mask = preprocess(frame)
+    return otsu_mask, segment(g)

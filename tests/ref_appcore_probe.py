@@ -8,7 +8,6 @@ module is imported -- host/plugin.py:binding() picks the base class at import ti
 Prints one JSON object: the module catalogue (identifier -> defining module, requires_gpu, stage),
 the unified pipeline's step names, and PipelineCache.predict signatures for SURVEY.md App. B's chain.
 """
-import importlib.util
 import json
 import sys
 import tempfile
@@ -21,10 +20,9 @@ def main() -> None:
     ref, order = sys.argv[1], sys.argv[2]
     sys.path.insert(0, str(REPO))
     sys.path.insert(0, ref)
-    spec = importlib.util.spec_from_file_location("make_golden", REPO / "tests" / "golden" / "make_golden.py")
-    mg = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mg)
-    mg.install_stubs()  # PyQt5 / skimage stubs of SURVEY.md App. C
+    from oracle.ref_stubs import install_stubs
+
+    install_stubs()  # PyQt5 / skimage stubs of SURVEY.md App. C
 
     import numpy as np
     from core.app_core import AppConfiguration, AppCore  # the reference's own classes

@@ -84,6 +84,21 @@ def _worker(rank: int, world: int, port: int, tmpdir: str):
         mine = [(i, int(i * i)) for i in range(f0, f1)]
         gathered = sharding.gather_tables(mine)
         assert gathered == [(i, i * i) for i in range(7)]
+        # --- the mosaic's collectives (host/mosaic.py TorchComm): stacked all-gather of byte views
+        # (uint16 LUT rows, int32 boundary rows + count) and the int64 histogram all-reduce
+        from yamimageprocessor_b200.host.mosaic import TorchComm
+
+        comm = TorchComm()
+        assert (comm.world, comm.rank) == (world, rank)
+        lut = torch.from_numpy((np.arange(12, dtype=np.uint16).reshape(1, 3, 4) + 100 * rank))
+        got = comm.all_gather(lut)
+        assert tuple(got.shape) == (world, 1, 3, 4) and got.dtype == torch.uint16
+        for r in range(world):
+            assert np.array_equal(got[r].numpy(), np.arange(12, dtype=np.uint16).reshape(1, 3, 4) + 100 * r)
+        pack = torch.arange(9, dtype=torch.int32) * (rank + 1)
+        assert np.array_equal(comm.all_gather(pack).numpy(), np.stack([np.arange(9) * (r + 1) for r in range(world)]))
+        h2 = torch.full((5,), rank + 1, dtype=torch.int64)
+        assert comm.all_reduce(h2, "sum").tolist() == [sum(range(1, world + 1))] * 5
         np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([t]))
     finally:
         dist.destroy_process_group()

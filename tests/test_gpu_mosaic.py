@@ -3,6 +3,8 @@ emulated on one GPU (host/mosaic.py LocalComm): halo over-fetch, CLAHE LUT gathe
 geometry, global Otsu histogram, cross-strip label merge, reduced region tables."""
 from __future__ import annotations
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,7 @@ from yamimageprocessor_b200 import synth
 from yamimageprocessor_b200.host import mosaic
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def dense(backend, frame, p):
@@ -66,3 +69,121 @@ def test_strip_geometry_errors():
     with pytest.raises(ValueError):
         mosaic.strip_rows(1001, 8, 0, 2)
     assert mosaic.input_rows(1024, 1, 2) == (512 - 18, 1024)
+
+
+def test_merge_strips_remap_matches_host_reference(backend, rng):
+    """yam_merge_strips_remap (union + raster-first renumbering on the device) against the NumPy
+    reference sharding.boundary_remaps and against the dense labelling, on masks whose components
+    cross several strip boundaries (incl. U-shapes that join two components of an upper strip)."""
+    import torch
+
+    from yamimageprocessor_b200.host import sharding
+
+    for dens, world, (h, w) in ((0.45, 4, (64, 70)), (0.58, 8, (96, 129)), (0.3, 2, (40, 33)), (0.62, 3, (90, 64))):
+        m = (rng.random((h, w)) < dens).astype(np.uint8) * 255
+        m[:, 5] = 255                                   # a column through every strip
+        n_want, want = O.ccl_label(m)
+        parts, counts, tops, bottoms = [], [], [], []
+        for r in range(world):
+            c0, c1, _, _ = sharding.row_strip(h, r, world)
+            n, lab = O.ccl_label(m[c0:c1])
+            parts.append(lab); counts.append(n); tops.append(lab[0]); bottoms.append(lab[-1])
+        remaps_ref, total_ref = sharding.boundary_remaps(tops, bottoms, counts)
+        stride = 2 * w + 8
+        packed = np.zeros((world, stride), np.int32)
+        for r in range(world):
+            packed[r, :w], packed[r, w:2 * w], packed[r, 2 * w] = tops[r], bottoms[r], counts[r]
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        dev = backend.to_device(packed)
+        got_full = []
+        for r in range(world):
+            remap, total = backend.merge_strips_remap(dev, w, offs, r)
+            remap = backend.to_host(remap)
+            assert int(backend.to_host(total)[0]) == total_ref == n_want
+            assert np.array_equal(remap, remaps_ref[r]), f"remap of strip {r} (world {world})"
+            got_full.append(remap[parts[r]])
+        assert np.array_equal(np.concatenate(got_full), want)
+
+
+def test_mosaic_module_through_pipeline_manager_tiled_handle(backend, tmp_path):
+    """BASELINE config 4's route: a .npy memmap behind a TiledPipelineImage goes through
+    PipelineManager.apply -> _apply_tiled -> the supports_tiled_input step (reference
+    processing/pipeline_manager.py:412-416); nothing is densified on the host, labels equal the
+    dense chain, for 1 and 4 strips per process."""
+    from yamimageprocessor_b200.host.pipeline import PipelineManager
+    from yamimageprocessor_b200.host.tiles import TiledImageRecord, TiledPipelineImage
+    from yamimageprocessor_b200.modules import b200_backend as plugin
+
+    p = mosaic.MosaicParams()
+    frame = synth.nuclei(1024, 768, seed=21)
+    frame[:, 300:303] = 60000
+    np.save(tmp_path / "mosaic.npy", frame)
+    want = dense(backend, frame, p)
+
+    class NoDensify(TiledImageRecord):
+        def to_array(self):
+            raise AssertionError("the tiled handle must not be densified")
+
+    mm = np.load(tmp_path / "mosaic.npy", mmap_mode="r")
+    rec = NoDensify.from_npy(tmp_path / "mosaic.npy", memmap=mm)
+    handle = TiledPipelineImage(rec, tile_size=(256, 256))
+    mod = plugin.MosaicModule()
+    assert mod.supports_tiled_input() and not mod.pipeline_execution_metadata().requires_gpu
+    for strips in (1, 4):
+        step = mod.create_pipeline_step()
+        step.enabled = True
+        step.params["strips"] = strips
+        assert step.supports_tiled_input
+        out = PipelineManager([step]).apply(handle)
+        assert out.dtype == np.int32 and out.shape == frame.shape
+        assert np.array_equal(out, want[3]), f"labels differ ({strips} strips)"
+        res = mod.last_results
+        assert res[0].otsu_threshold == want[1] and res[0].n_components == want[4]
+        assert np.array_equal(np.concatenate([backend.to_host(r.otsu_mask) for r in res]), want[2])
+    # a dense ndarray takes the same step (executor route: DEVICE_STEPS["Mosaic"])
+    from yamimageprocessor_b200.host.executor import B200Executor
+    step = mod.create_pipeline_step(); step.enabled = True
+    assert np.array_equal(B200Executor(backend).execute(step, frame), want[3])
+
+
+def test_mosaic_real_nccl_two_ranks_equal_dense(backend, tmp_path):
+    """The NCCL data path (TorchComm: LUT all-gather, histogram all-reduce, boundary all-gather) with
+    two real ranks on two GPUs (torchrun) against the dense single-GPU run of this process."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    p = mosaic.MosaicParams()
+    size = 2048
+    frame = synth.nuclei(size, size, seed=31)
+    frame[:, 700:704] = 60000
+    np.save(tmp_path / "m.npy", frame)
+    want = dense(backend, frame, p)
+    script = tmp_path / "rank.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from yamimageprocessor_b200.backend import get_backend\n"
+        "from yamimageprocessor_b200.host import mosaic\n"
+        "lr = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(lr)\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', lr))\n"
+        "be = get_backend(lr)\n"
+        f"src = np.load({str(tmp_path / 'm.npy')!r}, mmap_mode='r')\n"
+        "r = mosaic.run_source(be, src, mosaic.MosaicParams(), strips_per_process=1, with_props=True)[0]\n"
+        f"np.savez({str(tmp_path)!r} + f'/out{{dist.get_rank()}}.npz', labels=be.to_host(r.labels), om=be.to_host(r.otsu_mask),\n"
+        "         c=be.to_host(r.clahe), t=r.otsu_threshold, n=r.n_components, props=be.to_host(r.props), rows=np.array(r.rows))\n"
+        "dist.barrier(); dist.destroy_process_group()\n")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    outs = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
+    assert [tuple(o["rows"]) for o in outs] == [(0, size // 2), (size // 2, size)]
+    assert all(int(o["t"]) == want[1] and int(o["n"]) == want[4] for o in outs)
+    assert np.array_equal(np.concatenate([o["c"] for o in outs]), want[0])
+    assert np.array_equal(np.concatenate([o["om"] for o in outs]), want[2])
+    assert np.array_equal(np.concatenate([o["labels"] for o in outs]), want[3])
+    assert all(np.array_equal(o["props"], want[5]) for o in outs)

@@ -451,6 +451,38 @@ class Backend:
         self._call("yam_merge_strip_labels", self._p(edges), self._p(offsets), world, w, total, self._p(root))
         return root
 
+    def merge_strips_remap(self, packed, width: int, offsets: Sequence[int], rank: int):
+        """Cross-strip label merge + raster-first renumbering in one call (yam_merge_strips_remap).
+        ``packed`` int32 [world, stride >= 2*width]: first and last label row of every strip;
+        ``offsets`` host ints [world + 1].  Returns (remap int32[count_rank + 1], total int32[1])."""
+        torch = _torch()
+        packed = self._check(packed, ndim=(2,), dtypes=(torch.int32,), name="packed")
+        world, stride = int(packed.shape[0]), int(packed.shape[1])
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        if offs.size != world + 1:
+            raise ValueError("offsets must have world + 1 entries")
+        nbytes = int(self.lib.yam_merge_strips_workspace_bytes(int(offs[-1])))
+        if nbytes < 0:
+            raise ValueError("too many components for int32 labels")
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        remap = torch.empty((int(offs[rank + 1] - offs[rank]) + 1,), dtype=torch.int32, device=self.device)
+        total = torch.empty((1,), dtype=torch.int32, device=self.device)
+        self._call("yam_merge_strips_remap", self._p(packed), stride, world, int(width),
+                   offs.ctypes.data_as(C.c_void_p), int(rank), self._p(ws), self._p(remap), self._p(total))
+        return remap, total
+
+    def checksum64(self, t, index_base: int = 0, accumulate=None):
+        """Order-independent content checksum (yam_checksum64) of a uint8 / uint16 / int32 CUDA tensor;
+        returns an int64 tensor [1] (bit pattern of the uint64 sum), adding into ``accumulate`` if given."""
+        torch = _torch()
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise TypeError("checksum64 expects a CUDA tensor on this backend's device")
+        t = t.contiguous()
+        out = accumulate if accumulate is not None else torch.zeros((1,), dtype=torch.int64, device=self.device)
+        if t.numel():
+            self._call("yam_checksum64", self._p(t), int(t.numel()), _dtype_code(t), int(index_base), self._p(out))
+        return out
+
     def otsu_from_histogram(self, hist: np.ndarray) -> int:
         """cv2's Otsu recurrence on a host histogram (int64/uint64 counts); host-only helper."""
         h = np.ascontiguousarray(hist, dtype=np.uint64)
@@ -593,9 +625,10 @@ class Backend:
         self._call("yam_ccl_resolve_bits", self._p(bits), n, h, int(width), self._p(workspace), self._p(counts))
         return workspace, counts
 
-    def ccl_emit(self, bits, width: int, workspace, remap=None, rows: Optional[Tuple[int, int]] = None):
+    def ccl_emit(self, bits, width: int, workspace, remap=None, rows: Optional[Tuple[int, int]] = None, out=None):
         """Labels of rows ``[rows[0], rows[1])`` (default: all) of a resolved mask; ``remap`` (int32,
-        entry 0 = 0) maps strip-local to global labels while they are written."""
+        entry 0 = 0) maps strip-local to global labels while they are written.  ``out``: a contiguous
+        int32 CUDA tensor with room for the rows (e.g. a slice of an all-gather send buffer)."""
         torch = _torch()
         bits = self._check(bits, dtypes=(torch.int32,), name="bits")
         n, h, wpr = self._nhw(bits)
@@ -604,7 +637,13 @@ class Backend:
             shape = (h, int(width)) if bits.dim() == 2 else (n, h, int(width))
         else:
             shape = (r1 - r0, int(width))
-        labels = torch.empty(shape, dtype=torch.int32, device=self.device)
+        if out is not None:
+            if out.dtype != torch.int32 or out.device != self.device or not out.is_contiguous() or \
+                    out.numel() < (r1 - r0) * int(width):
+                raise ValueError("ccl_emit: `out` must be a contiguous int32 CUDA tensor holding the rows")
+            labels = out
+        else:
+            labels = torch.empty(shape, dtype=torch.int32, device=self.device)
         rptr = None
         if remap is not None:
             remap = self._check(remap, ndim=(1,), dtypes=(torch.int32,), name="remap")

@@ -1040,9 +1040,161 @@ __global__ void __launch_bounds__(kThreads) flatten_all_kernel(int* __restrict__
     P[i] = x;  // owner-only store: readers see either an ancestor or the root
 }
 
+// ---- one-call merge + renumbering (yam_merge_strips_remap) -----------------------------------------
+struct StripOffsets {
+    long long v[65];  // exclusive prefix of the per-strip component counts, by value (world <= 64)
+};
+
+// P = identity over [0, total]; non-root bitmap cleared
+__global__ void __launch_bounds__(kThreads) merge_init_kernel(int32_t* __restrict__ P, int64_t count,
+                                                              uint32_t* __restrict__ nonroot, int64_t nwords) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) P[i] = (int32_t)i;
+    if (i < nwords) nonroot[i] = 0u;
+}
+
+// thread = (boundary r | r+1, column x) over the packed rows [world][stride]: row 0 = first label row,
+// row 1 = last label row of a strip
+__global__ void __launch_bounds__(kThreads) merge_union_kernel(const int32_t* __restrict__ packed, int64_t stride,
+                                                               StripOffsets offs, int world, int64_t w,
+                                                               int* __restrict__ P) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)(world - 1) * w) return;
+    const int r = (int)(t / w);
+    const int64_t x = t - (int64_t)r * w;
+    const int32_t a = packed[(int64_t)r * stride + w + x];
+    if (a <= 0) return;
+    const int ga = (int)(offs.v[r] + a);
+    const int32_t* top = packed + (int64_t)(r + 1) * stride;
+    const long long ob = offs.v[r + 1];
+    int last = 0;
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+        const int64_t xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const int32_t b = top[xx];
+        if (b > 0 && b != last) {
+            unite(P, ga, (int)(ob + b));
+            last = b;
+        }
+    }
+}
+
+// Only ids that sit on a strip boundary row can have lost their root status: flatten those and mark
+// the non-roots in the bitmap (thread = one pixel of one packed row; duplicates are idempotent).
+__global__ void __launch_bounds__(kThreads) merge_flatten_kernel(const int32_t* __restrict__ packed, int64_t stride,
+                                                                 StripOffsets offs, int world, int64_t w,
+                                                                 int* __restrict__ P, uint32_t* __restrict__ nonroot) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)world * 2 * w) return;
+    const int r = (int)(t / (2 * w));
+    const int64_t x = t - (int64_t)r * 2 * w;
+    const int32_t a = packed[(int64_t)r * stride + x];
+    if (a <= 0) return;
+    if (x > 0 && x != w && packed[(int64_t)r * stride + x - 1] == a) return;  // one thread per run of a label
+    const int g = (int)(offs.v[r] + a);
+    int cur = g, p = __ldcg(P + cur);
+    while (p != cur) {
+        cur = p;
+        p = __ldcg(P + cur);
+    }
+    if (cur != g) {
+        P[g] = cur;  // owner-only store of the final root (readers see an ancestor or the root)
+        atomicOr(nonroot + (g >> 5), 1u << (g & 31));
+    }
+}
+
+// exclusive prefix of the per-word non-root counts (one block; word counts are tiny: total / 32)
+__global__ void __launch_bounds__(1024) merge_scan_kernel(const uint32_t* __restrict__ nonroot, int64_t nwords,
+                                                          uint32_t* __restrict__ prefix, int64_t total,
+                                                          int32_t* __restrict__ total_out) {
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (nwords + 1023) / 1024;
+    const int64_t b0 = min(nwords, (int64_t)t * per), b1 = min(nwords, b0 + per);
+    uint32_t s = 0;
+    for (int64_t i = b0; i < b1; i++) s += __popc(nonroot[i]);
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+        const uint32_t v = t >= o ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (int64_t i = b0; i < b1; i++) {
+        prefix[i] = run;
+        run += __popc(nonroot[i]);
+    }
+    if (t == 1023) total_out[0] = (int32_t)(total - (int64_t)part[1023]);
+}
+
+// remap[l] = raster-first global label of local label l of strip `rank`: the rank of its root among
+// the roots = root id minus the number of non-roots below it
+__global__ void __launch_bounds__(kThreads) merge_remap_kernel(const int* __restrict__ P,
+                                                               const uint32_t* __restrict__ nonroot,
+                                                               const uint32_t* __restrict__ prefix, long long base,
+                                                               int64_t count, int32_t* __restrict__ remap) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > count) return;
+    if (l == 0) {
+        remap[0] = 0;
+        return;
+    }
+    const int rt = P[base + l];
+    const uint32_t below = prefix[rt >> 5] + __popc(nonroot[rt >> 5] & ((1u << (rt & 31)) - 1u));
+    remap[l] = rt - (int)below;
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t yam_merge_strips_workspace_bytes(int64_t total) {
+    if (total < 0 || total >= (1ll << 31) - 1) return -1;
+    const int64_t nwords = (total + 32) / 32;
+    return (int64_t)yam_align_up((size_t)(total + 1) * 4, 256) + 2 * (int64_t)yam_align_up((size_t)nwords * 4, 256);
+}
+
+int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                           const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
+                           int32_t* total_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(packed_dev && offsets_host && workspace && remap_dev && total_dev, "merge_strips_remap: NULL argument");
+    YAM_REQUIRE(world >= 1 && world <= 64 && w > 0 && stride >= 2 * w && rank >= 0 && rank < world,
+                "merge_strips_remap: bad geometry (world %d, w %lld, stride %lld, rank %d)", world, (long long)w,
+                (long long)stride, rank);
+    StripOffsets offs;
+    for (int i = 0; i <= world; i++) {
+        offs.v[i] = offsets_host[i];
+        YAM_REQUIRE(offs.v[i] >= 0 && (i == 0 || offs.v[i] >= offs.v[i - 1]), "merge_strips_remap: offsets must ascend");
+    }
+    YAM_REQUIRE(offs.v[0] == 0, "merge_strips_remap: offsets[0] must be 0");
+    const int64_t total = offs.v[world];
+    YAM_REQUIRE(total < (1ll << 31) - 1, "merge_strips_remap: more than 2^31 components");
+    const int64_t count = total + 1, nwords = (total + 32) / 32;
+    int* P = (int*)workspace;
+    uint32_t* nonroot = (uint32_t*)((char*)workspace + yam_align_up((size_t)count * 4, 256));
+    uint32_t* prefix = (uint32_t*)((char*)nonroot + yam_align_up((size_t)nwords * 4, 256));
+    const auto blocks = [](int64_t items) { return (unsigned)((items + kThreads - 1) / kThreads); };
+    merge_init_kernel<<<blocks(count), kThreads, 0, ctx->stream>>>(P, count, nonroot, nwords);
+    YAM_LAUNCHED(ctx);
+    if (world > 1) {
+        merge_union_kernel<<<blocks((int64_t)(world - 1) * w), kThreads, 0, ctx->stream>>>(packed_dev, stride, offs,
+                                                                                          world, w, P);
+        YAM_LAUNCHED(ctx);
+        merge_flatten_kernel<<<blocks((int64_t)world * 2 * w), kThreads, 0, ctx->stream>>>(packed_dev, stride, offs,
+                                                                                          world, w, P, nonroot);
+        YAM_LAUNCHED(ctx);
+    }
+    merge_scan_kernel<<<1, 1024, 0, ctx->stream>>>(nonroot, nwords, prefix, total, total_dev);
+    YAM_LAUNCHED(ctx);
+    const int64_t mine = offs.v[rank + 1] - offs.v[rank];
+    merge_remap_kernel<<<blocks(mine + 1), kThreads, 0, ctx->stream>>>(P, nonroot, prefix, offs.v[rank], mine, remap_dev);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
 
 int yam_merge_strip_labels(yam_ctx* ctx, const int32_t* edges_dev, const int64_t* offsets_dev, int world, int64_t w,
                            int64_t total, int32_t* root_dev) {

@@ -348,6 +348,28 @@ int yam_threshold_dev(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64
     return YAM_OK;
 }
 
+// ---- order-independent 64-bit content checksum (parity evidence for sharded runs) -------------------
+// sum over elements of mix64((index_base + i) * GOLDEN + value) mod 2^64: the sum does not depend on
+// how the elements are split over launches, strips or ranks, so a sharded run can add its parts up
+// (all-reduce) and compare with the dense run.  mix64 = splitmix64's finalizer.
+__device__ __forceinline__ unsigned long long yam_mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) checksum_kernel(const T* __restrict__ src, int64_t count,
+                                                            unsigned long long base,
+                                                            unsigned long long* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        acc += yam_mix64((base + (unsigned long long)i) * 0x9E3779B97F4A7C15ull + (unsigned long long)(uint32_t)src[i]);
+    acc = yam_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 extern "C" {
 
 int yam_bgr2gray(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype) {
@@ -475,4 +497,20 @@ int yam_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t count, int d
     return YAM_OK;
 }
 
+int yam_checksum64(yam_ctx* ctx, const void* src, int64_t count, int dtype, int64_t index_base, uint64_t* sum_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && sum_dev && count > 0 && index_base >= 0, "checksum64: bad arguments");
+    int64_t bx = (count + kThreads * 8 - 1) / (kThreads * 8);
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (bx > cap) bx = cap;
+    unsigned long long* out = (unsigned long long*)sum_dev;
+    if (dtype == YAM_U8) checksum_kernel<uint8_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint8_t*)src, count, (unsigned long long)index_base, out);
+    else if (dtype == YAM_U16) checksum_kernel<uint16_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint16_t*)src, count, (unsigned long long)index_base, out);
+    else if (dtype == YAM_I32) checksum_kernel<int32_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const int32_t*)src, count, (unsigned long long)index_base, out);
+    else YAM_REQUIRE(false, "checksum64: unsupported dtype %d", dtype);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
 }  // extern "C"
+

@@ -65,13 +65,15 @@ class TorchComm:
         self.rank = dist.get_rank(group)
 
     def all_gather(self, tensor):
+        """[world, *tensor.shape]: one ncclAllGather straight into the result (no per-rank list copies)."""
         import torch
 
         # integer payloads travel as bytes: NCCL does not take every unsigned dtype
-        raw = tensor.contiguous().view(torch.uint8)
-        parts = [torch.empty_like(raw) for _ in range(self.world)]
-        self.dist.all_gather(parts, raw, group=self.group)
-        return [p.view(tensor.dtype).reshape(tensor.shape) for p in parts]
+        t = tensor.contiguous()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(torch.uint8).reshape(-1), t.view(torch.uint8).reshape(-1),
+                                         group=self.group)
+        return out
 
     def all_reduce(self, tensor, op: str = "sum"):
         ops = {"sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX}
@@ -105,18 +107,17 @@ class _BoundLocalComm:
         self.parent, self.rank, self.world = parent, rank, parent.world
 
     def all_gather(self, tensor):
+        import torch
+
         p = self.parent
         p._slots[self.rank] = tensor
         p._barrier.wait()
-        out = [t.clone() for t in p._slots]
+        out = torch.stack(list(p._slots))
         p._barrier.wait()
         return out
 
     def all_reduce(self, tensor, op: str = "sum"):
-        import torch
-
-        parts = self.all_gather(tensor)
-        stacked = torch.stack(parts)
+        stacked = self.all_gather(tensor)
         red = stacked.sum(0) if op == "sum" else (stacked.min(0).values if op == "min" else stacked.max(0).values)
         tensor.copy_(red)
         return tensor
@@ -174,22 +175,19 @@ class _BoundHybridComm:
         if self.li == 0:
             local = torch.stack(p._slots)  # (local, ...)
             if p.dist is not None:
-                raw = local.view(torch.uint8)
-                parts = [torch.empty_like(raw) for _ in range(p.nproc)]
-                p.dist.all_gather(parts, raw)
-                everything = torch.cat([q.view(local.dtype).reshape(local.shape) for q in parts], dim=0)
+                everything = torch.empty((p.nproc * p.local,) + tuple(local.shape[1:]), dtype=local.dtype,
+                                         device=local.device)
+                p.dist.all_gather_into_tensor(everything.view(torch.uint8).reshape(-1), local.view(torch.uint8).reshape(-1))
             else:
                 everything = local
             p._result = everything
         p._barrier.wait()
-        out = [p._result[i] for i in range(self.world)]
+        out = p._result
         p._barrier.wait()
         return out
 
     def all_reduce(self, tensor, op: str = "sum"):
-        import torch
-
-        stacked = torch.stack(self.all_gather(tensor))
+        stacked = self.all_gather(tensor)
         red = stacked.sum(0) if op == "sum" else (stacked.min(0).values if op == "min" else stacked.max(0).values)
         tensor.copy_(red)
         return tensor
@@ -247,7 +245,10 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
 
     # CLAHE: LUTs of the tile rows this rank owns, gathered from every rank
     luts_local = be.clahe_luts(g[c0 - r0: c1 - r0], p.clip_limit, (tiles_x, tiles_y // world))
-    luts = torch.cat(comm.all_gather(luts_local), dim=0) if comm is not None else luts_local
+    if comm is not None:  # [world, tile rows per strip, tiles_x, bins] is the global LUT table, already in order
+        luts = comm.all_gather(luts_local).reshape(tiles_y, tiles_x, -1)
+    else:
+        luts = luts_local
     c = be.clahe_apply(g[a0 - r0: a1 - r0], luts, (tw, th), y_offset=a0)
     c_core = c[c0 - a0: c1 - a0]
     mark("clahe")
@@ -281,37 +282,26 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     # cross-strip merge from boundary rows
     if comm is not None:
         rows_core = c1 - c0
-        edge = torch.cat([be.ccl_emit(bits_core, W, ccl_ws, rows=(0, 1)),
-                          be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core))]).contiguous()
-        edges = comm.all_gather(edge)
-        cnts = comm.all_gather(counts)             # device tensors: no host round trip before the merge
-        # label offsets of the strips: the one value the host needs (array sizes).  It is read back
-        # asynchronously and the Otsu threshold kernel is enqueued behind the copy, so the GPU has
-        # work while the host waits for the offsets and prepares the merge.
-        offs_dev = torch.cat([torch.zeros(1, dtype=torch.int64, device=be.device),
-                              torch.cat(cnts).to(torch.int64).cumsum(0)])
-        offs_host = torch.empty(offs_dev.shape, dtype=torch.int64, pin_memory=True)
-        offs_host.copy_(offs_dev, non_blocking=True)
-        offs_ready = torch.cuda.Event()
-        offs_ready.record()
+        # one all-gather carries each strip's first / last label row and its component count
+        stride = 2 * W + 8
+        pack = torch.empty((stride,), dtype=torch.int32, device=be.device)
+        be.ccl_emit(bits_core, W, ccl_ws, rows=(0, 1), out=pack[:W])
+        be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core), out=pack[W:2 * W])
+        pack[2 * W:2 * W + 1].copy_(counts)
+        packed = comm.all_gather(pack)             # [world, stride]
+        # The host needs the counts only to size the tables.  They are read back asynchronously and the
+        # Otsu threshold kernel is enqueued behind the copy, so the GPU has work while the host waits.
+        cnt_host = torch.empty((comm.world,), dtype=torch.int32, pin_memory=True)
+        cnt_host.copy_(packed[:, 2 * W], non_blocking=True)
+        cnt_ready = torch.cuda.Event()
+        cnt_ready.record()
         otsu_mask = be.threshold(c_core, float(t), 255)
         mark("otsu")
-        offs_ready.synchronize()
-        offs = [int(v) for v in offs_host.tolist()]
-
-        def merge():
-            # all on the device: union of the ids that touch across strip boundaries, then the
-            # raster-first renumbering (rank of every root among the roots)
-            root = be.merge_strip_labels(torch.stack(edges), offs_dev, total=offs[-1])
-            is_root = root == torch.arange(root.numel(), dtype=torch.int32, device=be.device)
-            is_root[0] = False
-            ranks = torch.cumsum(is_root, dim=0, dtype=torch.int32)
-            glob = ranks[root]
-            glob[0] = 0
-            return glob, ranks[-1:]
-
-        glob, total_dev = comm.once(merge)
-        remap = torch.cat([glob[:1], glob[int(offs[rank]) + 1: int(offs[rank + 1]) + 1]]).contiguous()
+        cnt_ready.synchronize()
+        offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
+        # union of the ids that touch across strip boundaries + raster-first renumbering: one library
+        # call, five small kernels, all on the device (yam_merge_strips_remap)
+        remap, total_dev = be.merge_strips_remap(packed, W, offs, rank)
         labels = be.ccl_emit(bits_core, W, ccl_ws, remap=remap)   # global labels, written once
     else:
         otsu_mask = be.threshold(c_core, float(t), 255)
