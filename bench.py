@@ -577,9 +577,14 @@ def run_gpu_mosaic(args):
         h = be.histogram(c)
         return be.threshold(c, 30000.0, 255), h
 
-    def ccl_op():
-        ws, cnt = be.ccl_resolve_bits(bits2, W)
-        return be.ccl_emit(bits2, W, ws)
+    sub_rows = (c1 - c0) // max(1, -(-strip_px // mosaic._CCL_MAX_PX))
+
+    def ccl_op():   # in sub-strips of < 2^31 pixels like run_strip (32-bit pixel indices in the labeller)
+        lab = torch.empty((c1 - c0, W), dtype=torch.int32, device=be.device)
+        for y in range(0, c1 - c0, sub_rows):
+            ws, cnt = be.ccl_resolve_bits(bits2[y:y + sub_rows], W)
+            be.ccl_emit(bits2[y:y + sub_rows], W, ws, out=lab[y:y + sub_rows])
+        return lab
 
     op_rows = [
         ("gaussian_fixed_u16_k11 (sep_fixed_tiled)", 4.0, measure(lambda: be.gaussian(g_core, p.gauss_ksize, 0.0))),

@@ -51,6 +51,21 @@ def test_sharded_mosaic_equals_dense(backend, world):
         assert np.array_equal(backend.to_host(r.props), want_props), "reduced region table differs"
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_mosaic_with_labelling_sub_strips(backend, world):
+    """Strips of >= 2^31 pixels are labelled as merged sub-strips (65536^2 on one or two GPUs); forced
+    here with a tiny ccl_max_px: 1024 rows -> 4 (world 1) / 2 x 4 (world 2) sub-strips."""
+    p = mosaic.MosaicParams(ccl_max_px=768 * 128)
+    frame = synth.nuclei(1024, 768, seed=13)
+    frame[:, 200:204] = 60000
+    frame[100:900, 500:503] = 55000
+    want_c, want_t, want_om, want_lab, want_n, want_props = dense(backend, frame, mosaic.MosaicParams())
+    res = mosaic.run_emulated(backend, frame, world, p, with_props=True)
+    assert all(r.n_components == want_n and r.otsu_threshold == want_t for r in res)
+    assert np.array_equal(np.concatenate([backend.to_host(r.labels) for r in res]), want_lab)
+    assert np.array_equal(backend.to_host(res[0].props), want_props)
+
+
 def test_dense_chain_matches_oracle(backend):
     """anchor: the dense chain the sharded path is compared with equals the CPU oracle"""
     p = mosaic.MosaicParams()

@@ -31,6 +31,9 @@ from ..backend import Backend
 from . import ingest, sharding
 
 
+_CCL_MAX_PX = 1 << 30   # pixels per labelling call (32-bit pixel indices inside yam_ccl_*)
+
+
 @dataclass
 class MosaicParams:
     gauss_ksize: int = 11
@@ -39,6 +42,7 @@ class MosaicParams:
     block_size: int = 11
     C: float = 2.0
     morph_ksize: int = 5
+    ccl_max_px: int = _CCL_MAX_PX  # pixels per labelling call; larger strips are labelled as merged sub-strips
     trace: Any = None              # optional callable(phase_name, rank): profiling hook, called at phase ends
 
 
@@ -269,8 +273,20 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     # cropping whole rows of the packed mask is a view, not a copy)
     bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
     bits_core = bits[c0 - a0: c1 - a0]
-    # labelling in two steps: resolve now, write the label image once the global numbering is known
-    ccl_ws, counts = be.ccl_resolve_bits(bits_core, W)
+    # labelling in two steps: resolve now, write the label image once the global numbering is known.
+    # The labeller indexes pixels with 32 bits, so a strip of 2^31 pixels or more (65536^2 on one or two
+    # GPUs) is resolved as `k_sub` equal sub-strips that the cross-strip merge below stitches exactly like
+    # strips of different ranks.
+    rows_core = c1 - c0
+    k_sub = max(1, -(-(rows_core * W) // int(p.ccl_max_px)))
+    while rows_core % k_sub:
+        k_sub += 1
+    sub_rows = rows_core // k_sub
+    subs = []
+    for i in range(k_sub):
+        b = bits_core[i * sub_rows:(i + 1) * sub_rows]
+        ws_i, cnt_i = be.ccl_resolve_bits(b, W)
+        subs.append((b, ws_i, cnt_i))
 
     def scan():
         hist_ready.synchronize()
@@ -279,19 +295,18 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     t = comm.once(scan) if comm is not None else scan()
     mark("segment")
 
-    # cross-strip merge from boundary rows
-    if comm is not None:
-        rows_core = c1 - c0
-        # one all-gather carries each strip's first / last label row and its component count
+    if comm is not None or k_sub > 1:
+        # one all-gather carries every (sub-)strip's first / last label row and its component count
         stride = 2 * W + 8
-        pack = torch.empty((stride,), dtype=torch.int32, device=be.device)
-        be.ccl_emit(bits_core, W, ccl_ws, rows=(0, 1), out=pack[:W])
-        be.ccl_emit(bits_core, W, ccl_ws, rows=(rows_core - 1, rows_core), out=pack[W:2 * W])
-        pack[2 * W:2 * W + 1].copy_(counts)
-        packed = comm.all_gather(pack)             # [world, stride]
+        pack = torch.empty((k_sub, stride), dtype=torch.int32, device=be.device)
+        for i, (b, ws_i, cnt_i) in enumerate(subs):
+            be.ccl_emit(b, W, ws_i, rows=(0, 1), out=pack[i, :W])
+            be.ccl_emit(b, W, ws_i, rows=(sub_rows - 1, sub_rows), out=pack[i, W:2 * W])
+            pack[i, 2 * W:2 * W + 1].copy_(cnt_i)
+        packed = comm.all_gather(pack).reshape(-1, stride) if comm is not None else pack
         # The host needs the counts only to size the tables.  They are read back asynchronously and the
         # Otsu threshold kernel is enqueued behind the copy, so the GPU has work while the host waits.
-        cnt_host = torch.empty((comm.world,), dtype=torch.int32, pin_memory=True)
+        cnt_host = torch.empty((int(packed.shape[0]),), dtype=torch.int32, pin_memory=True)
         cnt_host.copy_(packed[:, 2 * W], non_blocking=True)
         cnt_ready = torch.cuda.Event()
         cnt_ready.record()
@@ -299,15 +314,18 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         mark("otsu")
         cnt_ready.synchronize()
         offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
-        # union of the ids that touch across strip boundaries + raster-first renumbering: one library
-        # call, five small kernels, all on the device (yam_merge_strips_remap)
-        remap, total_dev = be.merge_strips_remap(packed, W, offs, rank)
-        labels = be.ccl_emit(bits_core, W, ccl_ws, remap=remap)   # global labels, written once
+        # union of the ids that touch across (sub-)strip boundaries + raster-first renumbering: one
+        # library call per sub-strip, small kernels, all on the device (yam_merge_strips_remap);
+        # the label image is written once, already in global numbering
+        labels = torch.empty((rows_core, W), dtype=torch.int32, device=be.device)
+        for i, (b, ws_i, cnt_i) in enumerate(subs):
+            remap, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub + i)
+            be.ccl_emit(b, W, ws_i, remap=remap, out=labels[i * sub_rows:(i + 1) * sub_rows])
     else:
         otsu_mask = be.threshold(c_core, float(t), 255)
         mark("otsu")
-        total_dev = counts
-        labels = be.ccl_emit(bits_core, W, ccl_ws)
+        b, ws_i, total_dev = subs[0]
+        labels = be.ccl_emit(b, W, ws_i)
     total = int(total_dev[0].item())   # the only wait for the labelling: everything above is enqueued
     mark("merge")
 
