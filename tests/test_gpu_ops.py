@@ -513,6 +513,30 @@ def test_adaptive_bits_and_unpack(backend, rng, dt):
                 assert int((raw[:, -1] >> (shape[1] % 32)).max()) == 0
 
 
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_adaptive_bits_tma_kernel(backend, rng, dt):
+    """Shapes a tensor map can describe (16-byte rows, >= 256 x 80) take the TMA-staged kernel
+    (yam_adaptive.cu): bit-exact against the oracle and against the generic tiled kernel, including
+    tiles that hang over every image border, widths that are not multiples of 240 / 32, stacks, and
+    every fused block size."""
+    for shape in ((80, 256), (130, 272), (300, 496), (201, 1104), (96, 2048), (3, 90, 512), (2, 150, 720)):
+        a = blobs(rng, shape[-2:], dt) if len(shape) == 2 else np.stack([blobs(rng, shape[-2:], dt) for _ in range(shape[0])])
+        if dt == U16:
+            a[..., 0:3, :] = 65535      # saturated rows / columns on the replicate border
+            a[..., :, -2:] = 0
+        for block, C in ((11, 2), (5, 2), (15, -1), (3, 1), (7, 3), (11, -7.5), (11, 0)):
+            bits = backend.adaptive_threshold_bits(dev(backend, a), block, C)
+            got = host(backend, backend.bits_unpack(bits, shape[-1]))
+            want = host(backend, backend.adaptive_threshold(dev(backend, a), block, C))
+            assert_same(got, want, f"adaptive bits (TMA) {block},{C} {shape}")
+            if block in (11, 5) and C == 2:
+                ref = O.adaptive_threshold(a, block, C) if a.ndim == 2 else np.stack([O.adaptive_threshold(f, block, C) for f in a])
+                assert_same(got, ref, f"adaptive bits (TMA) vs oracle {block},{C} {shape}")
+            raw = host(backend, bits).view(np.uint32)
+            if shape[-1] % 32:
+                assert int((raw[..., -1] >> (shape[-1] % 32)).max()) == 0
+
+
 @pytest.mark.parametrize("k,it", [(1, 1), (2, 1), (3, 1), (3, 2), (3, 3), (4, 2), (5, 1), (7, 1), (5, 3), (9, 2), (15, 3), (31, 2)])
 def test_bits_morph(backend, rng, k, it):
     for shape in ((64, 64), (33, 71), (130, 257), (70, 1200), (37, 2000)):

@@ -806,6 +806,12 @@ int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_ou
     for (int i = 0; i < block_size; i++) taps.v[i] = (float)kf[i];
     const int idelta = (int)ceil(C);
     const int wpr = (int)((w + 31) / 32);
+    YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "adaptive_threshold_bits: unsupported dtype %d", dtype);
+    {
+        int handled = 0;  // TMA-staged kernel (yam_adaptive.cu) for the shapes a tensor map can describe
+        if (int rc = yam_adaptive_bits_tma(ctx, src, bits_out, n, h, w, dtype, block_size, taps.v, idelta, &handled)) return rc;
+        if (handled) return YAM_OK;
+    }
     if (dtype == YAM_U8)
         return launch_f32<uint8_t, uint8_t, FEPI_ADAPTIVE_BITS>(ctx, (const uint8_t*)src, (uint8_t*)nullptr, n, h, w, taps,
                                                                 block_size, YAM_BORDER_REPLICATE, 255, idelta, bits_out, wpr);

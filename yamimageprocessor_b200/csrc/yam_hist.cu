@@ -1053,11 +1053,12 @@ int clahe_luts16(yam_ctx* ctx, const uint16_t* s_ptr, const ClaheGeom& g, int64_
     const int64_t total_tiles = tiles * nf;
     const int slots = ctx->num_sms;
     const long long area = (long long)g.tw * g.th;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per DEVICE: one flag per device id (a process may own several contexts)
+    static bool attr_set[64] = {};
+    if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
         YAM_CUDA(cudaFuncSetAttribute(clahe_lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
         YAM_CUDA(cudaFuncSetAttribute(clahe_hist16_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
-        attr_set = true;
+        if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
     }
     if (total_tiles * 2 <= slots && area >= (4ll << 20)) {
         // few huge tiles: split every tile over several CTAs
@@ -1092,10 +1093,10 @@ int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, in
         if (bx < 1) bx = 1;
         hist8_kernel<<<dim3((unsigned)bx, 1, (unsigned)n), 256, 0, ctx->stream>>>((const uint8_t*)src, frame_px, hist);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};  // per device, see clahe_luts16
+        if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
             YAM_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
-            attr_set = true;
+            if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
         }
         int64_t parts = ctx->num_sms / n;
         if (parts < 1) parts = 1;

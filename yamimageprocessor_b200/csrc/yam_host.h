@@ -14,3 +14,9 @@ int yam_host_otsu32(const uint32_t* h, int bins);  // same recurrence on 32-bit 
 // 1..4 histograms (stride_bytes apart; 32-bit counts if narrow) advanced in lock step by the calling
 // thread: independent dependency chains fill the pipeline one chain leaves idle
 void yam_host_otsu_group(const void* hists, size_t stride_bytes, int count, int bins, int narrow, int32_t* out);
+
+// TMA fast path of the adaptive threshold -> packed bits (yam_adaptive.cu); *handled = 0 when the shape
+// does not qualify and the caller must use the generic tiled kernel
+struct yam_ctx;
+int yam_adaptive_bits_tma(yam_ctx* ctx, const void* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, int dtype,
+                          int block_size, const float* taps_f, int idelta, int* handled);

@@ -23,7 +23,7 @@ from .steps import DEVICE_STEPS
 
 
 class B200Executor:
-    def __init__(self, backend: Optional[Backend] = None, device: int = 0) -> None:
+    def __init__(self, backend: Optional[Backend] = None, device: Optional[int] = None) -> None:
         self._backend = backend
         self._device = device
         self.calls: list[str] = []  # step names executed, in order (diagnostics / tests)
@@ -31,7 +31,13 @@ class B200Executor:
     @property
     def backend(self) -> Backend:
         if self._backend is None:
-            self._backend = get_backend(self._device)
+            device = self._device
+            if device is None:
+                # one process per GPU: the device this process selected (torch.cuda.set_device(LOCAL_RANK))
+                import torch
+
+                device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            self._backend = get_backend(int(device))
         return self._backend
 
     @staticmethod
