@@ -64,8 +64,7 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
     for (int r = r0 + warp; r < r1; r += nwarps) {
         const int gy = yam_border(r, h, YAM_BORDER_REFLECT101);
         const uint16_t* row = src + (int64_t)gy * w;
-        for (int v = lane; v < nvec; v += 32) {
-            const uint4 q = yam_ld_stream(reinterpret_cast<const uint4*>(row + c0) + v);
+        auto consume = [&](const uint4& q) {
             const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -77,7 +76,21 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
                     bump16(sh, overflow, spill_flag, b, 1u);
                 }
             }
+        };
+        const uint4* vrow = reinterpret_cast<const uint4*>(row + c0);
+        int v = lane;
+        // four 16-byte loads in flight per thread before the first shared-memory atomic: with one CTA of
+        // 1024 threads per SM a single load per thread (16 KiB in flight) left the kernel waiting on HBM
+        // latency (long scoreboard was the top stall in round 1's profile)
+        for (; v + 96 < nvec; v += 128) {
+            const uint4 q0 = yam_ld_stream(vrow + v), q1 = yam_ld_stream(vrow + v + 32);
+            const uint4 q2 = yam_ld_stream(vrow + v + 64), q3 = yam_ld_stream(vrow + v + 96);
+            consume(q0);
+            consume(q1);
+            consume(q2);
+            consume(q3);
         }
+        for (; v < nvec; v += 32) consume(yam_ld_stream(vrow + v));
         for (int c = nvec * 8 + lane; c < cw; c += 32) {
             const int gx = yam_border(c0 + c, w, YAM_BORDER_REFLECT101);
             bump16(sh, overflow, spill_flag, row[gx], 1u);
@@ -994,6 +1007,110 @@ __global__ void __launch_bounds__(256) clahe_apply_quad_kernel(const uint16_t* _
     }
 }
 
+// ---- table-driven apply kernels for 16-bit frames ---------------------------------------------------
+// The x interpolation weight and cell of a column are the same for every row: a one-off table
+// (clahe_xtab_kernel, float xa[w] + uint16 cell[w]) replaces ~12 per-pixel instructions (I2F, FMUL, FADD,
+// floor, F2I, min / max) by coalesced L1-resident loads; LUT values become floats with PRMT + FADD2
+// (no I2F on the quarter-rate conversion pipe) and the blend runs on the packed fp32 pipe.  Each
+// packed half is an IEEE fp32 operation in cv2's order (no FMA), so results are bit-identical.
+__global__ void __launch_bounds__(256) clahe_xtab_kernel(ClaheGeom g, float* __restrict__ xa, uint16_t* __restrict__ cell) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.w) return;
+    const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+    const int fx = (int)floorf(txf);
+    xa[x] = __fsub_rn(txf, (float)fx);
+    cell[x] = (uint16_t)min(max(fx + 1, 0), g.tiles_x);   // tiles (max(cell-1,0), min(cell,tiles_x-1))
+}
+
+// q01 = l11 | l12 << 16, q23 = l21 | l22 << 16 -> blended, rounded 16-bit value
+__device__ __forceinline__ uint32_t clahe_blend16(uint32_t q01, uint32_t q23, float xa, float2 yw) {
+    const float2 nb = make_float2(-8388608.0f, -8388608.0f);
+    const float2 a = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q01, 0x4B000000u, 0x7410)),
+                                            __uint_as_float(__byte_perm(q01, 0x4B000000u, 0x7432))), nb);
+    const float2 b = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q23, 0x4B000000u, 0x7410)),
+                                            __uint_as_float(__byte_perm(q23, 0x4B000000u, 0x7432))), nb);
+    const float2 xw = make_float2(__fsub_rn(1.0f, xa), xa);
+    const float2 pa = __fmul2_rn(a, xw), pb = __fmul2_rn(b, xw);
+    const float2 pr = __fmul2_rn(make_float2(__fadd_rn(pa.x, pa.y), __fadd_rn(pb.x, pb.y)), yw);
+    const float res = __fadd_rn(pr.x, pr.y);
+    // a convex combination of 16-bit values: 0 <= res <= 65535, so saturation cannot trigger and
+    // rint(res) sits in the low mantissa bits of res + 1.5 * 2^23 (round-half-even)
+    return __float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffffu;
+}
+
+// grid (rows, ceil(w / 2048), frames); thread = 8 pixels.  QUAD: one 8-byte gather per pixel from the
+// interleaved cell table; otherwise four 2-byte gathers from the per-tile LUTs (stacks of small frames).
+template <bool QUAD>
+__global__ void __launch_bounds__(256) clahe_apply16_tab_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+                                                               ClaheGeom g, const void* __restrict__ table,
+                                                               const float* __restrict__ xa_tab,
+                                                               const uint16_t* __restrict__ cell_tab) {
+    const int y = blockIdx.x;
+    const int x0 = (blockIdx.y * 256 + threadIdx.x) * 8;
+    if (x0 >= g.w) return;
+    const int64_t frame_px = (int64_t)g.h * g.w;
+    src += (int64_t)blockIdx.z * frame_px;
+    dst += (int64_t)blockIdx.z * frame_px;
+    const float tyf = __fsub_rn(__fmul_rn((float)(y + g.y_off), g.inv_th), 0.5f);
+    const int fy = (int)floorf(tyf);
+    const float ya = __fsub_rn(tyf, (float)fy);
+    const float2 yw = make_float2(__fsub_rn(1.0f, ya), ya);
+    const int cy = min(max(fy + 1, 0), g.tiles_y);
+    const uint4 pix = yam_ld_stream(reinterpret_cast<const uint4*>(src + (int64_t)y * g.w + x0));
+    const float4 xa_lo = __ldg(reinterpret_cast<const float4*>(xa_tab + x0));
+    const float4 xa_hi = __ldg(reinterpret_cast<const float4*>(xa_tab + x0 + 4));
+    const uint4 cells = __ldg(reinterpret_cast<const uint4*>(cell_tab + x0));
+    const float xa[8] = {xa_lo.x, xa_lo.y, xa_lo.z, xa_lo.w, xa_hi.x, xa_hi.y, xa_hi.z, xa_hi.w};
+    const uint32_t pw[4] = {pix.x, pix.y, pix.z, pix.w}, cw[4] = {cells.x, cells.y, cells.z, cells.w};
+    uint32_t q01[8], q23[8];
+    if (QUAD) {
+        const uint2* qrow = reinterpret_cast<const uint2*>(table) + (int64_t)cy * (g.tiles_x + 1) * kBins16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t v = (pw[i >> 1] >> (16 * (i & 1))) & 0xffffu, cx = (cw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            const uint2 q = __ldg(qrow + (int64_t)cx * kBins16 + v);
+            q01[i] = q.x;
+            q23[i] = q.y;
+        }
+    } else {
+        const uint16_t* luts = reinterpret_cast<const uint16_t*>(table) + (int64_t)blockIdx.z * g.tiles_x * g.tiles_y * kBins16;
+        const uint16_t* lrow1 = luts + (int64_t)max(cy - 1, 0) * g.tiles_x * kBins16;
+        const uint16_t* lrow2 = luts + (int64_t)min(cy, g.tiles_y - 1) * g.tiles_x * kBins16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t v = (pw[i >> 1] >> (16 * (i & 1))) & 0xffffu, cx = (cw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            const int64_t o1 = (int64_t)max((int)cx - 1, 0) * kBins16 + v, o2 = (int64_t)min((int)cx, g.tiles_x - 1) * kBins16 + v;
+            q01[i] = (uint32_t)__ldg(lrow1 + o1) | ((uint32_t)__ldg(lrow1 + o2) << 16);
+            q23[i] = (uint32_t)__ldg(lrow2 + o1) | ((uint32_t)__ldg(lrow2 + o2) << 16);
+        }
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        out[i] = clahe_blend16(q01[2 * i], q23[2 * i], xa[2 * i], yw) |
+                 (clahe_blend16(q01[2 * i + 1], q23[2 * i + 1], xa[2 * i + 1], yw) << 16);
+    yam_st_stream(reinterpret_cast<uint4*>(dst + (int64_t)y * g.w + x0), make_uint4(out[0], out[1], out[2], out[3]));
+}
+
+inline bool clahe_tab_ok(const void* src, const void* dst, int64_t w) {
+    return (w % 8) == 0 && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+}
+inline size_t clahe_tab_bytes(int64_t w) { return yam_align_up((size_t)w * 4, 256) + yam_align_up((size_t)w * 2, 256); }
+
+// builds the column tables at `tab` and applies rows x frames; `table` = quad cells (QUAD) or the LUT set
+template <bool QUAD>
+int clahe_apply16_tab(yam_ctx* ctx, const uint16_t* s_ptr, uint16_t* d_ptr, int64_t rows, int64_t frames, const ClaheGeom& g,
+                      const void* table, void* tab) {
+    float* xa = (float*)tab;
+    uint16_t* cell = (uint16_t*)((char*)tab + yam_align_up((size_t)g.w * 4, 256));
+    clahe_xtab_kernel<<<(unsigned)((g.w + 255) / 256), 256, 0, ctx->stream>>>(g, xa, cell);
+    YAM_LAUNCHED(ctx);
+    dim3 grid((unsigned)rows, (unsigned)((g.w + 2047) / 2048), (unsigned)frames);
+    clahe_apply16_tab_kernel<QUAD><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, table, xa, cell);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
 constexpr int64_t kQuadMinPixels = 8ll << 20;  // below this the 40 MB quad build costs more than it saves
 constexpr int kQuadMaxCells = 128;
 
@@ -1003,13 +1120,20 @@ inline bool clahe_use_quad(int64_t pixels, int tiles_x, int tiles_y) {
 inline size_t clahe_quad_bytes(int tiles_x, int tiles_y) {
     return (size_t)(tiles_x + 1) * (tiles_y + 1) * kBins16 * sizeof(ushort4);
 }
+inline size_t clahe_tab_bytes(int64_t w);
 
 // apply `rows` rows of one frame with the quad path: build quad from luts, then gather
 int clahe_apply16_quad(yam_ctx* ctx, const uint16_t* s_ptr, uint16_t* d_ptr, int64_t rows, const ClaheGeom& g,
                        const uint16_t* luts, ushort4* quad) {
+    // scratch layout: [quad cells][column tables]
     const int cells = (g.tiles_x + 1) * (g.tiles_y + 1);
     clahe_quad_build_kernel<<<dim3(kBins16 / 256, (unsigned)cells), 256, 0, ctx->stream>>>(luts, g.tiles_x, g.tiles_y, quad);
     YAM_LAUNCHED(ctx);
+    if (clahe_tab_ok(s_ptr, d_ptr, g.w)) {
+        ClaheGeom gr = g;
+        gr.h = (int)rows;
+        return clahe_apply16_tab<true>(ctx, s_ptr, d_ptr, rows, 1, gr, quad, (char*)quad + clahe_quad_bytes(g.tiles_x, g.tiles_y));
+    }
     clahe_apply_quad_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, quad);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
@@ -1345,8 +1469,9 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
         const size_t ovf_bytes = yam_align_up((size_t)tail_slots * kBins16 * sizeof(uint32_t), 256);
         const size_t luts_bytes = yam_align_up(lut_frame * chunk, 256);
         const size_t quad_bytes = quad_path ? clahe_quad_bytes(tiles_x, tiles_y) : 0;
+        const size_t tab_bytes = clahe_tab_bytes(w);
         void* scratch = nullptr;
-        if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes + quad_bytes, &scratch)) return rc;
+        if (int rc = yam_scratch(ctx, luts_bytes + ovf_bytes + quad_bytes + tab_bytes, &scratch)) return rc;
         uint16_t* luts = (uint16_t*)scratch;
         void* tail = (char*)scratch + luts_bytes;
         ushort4* quad = (ushort4*)((char*)scratch + luts_bytes + ovf_bytes);
@@ -1358,6 +1483,8 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
             if (int rc = clahe_luts16(ctx, s_ptr, g, nf, luts, tail)) return rc;
             if (quad_path) {
                 if (int rc = clahe_apply16_quad(ctx, s_ptr, d_ptr, h, g, luts, quad)) return rc;
+            } else if (clahe_tab_ok(s_ptr, d_ptr, w)) {
+                if (int rc = clahe_apply16_tab<false>(ctx, s_ptr, d_ptr, h, nf, g, luts, (char*)scratch + luts_bytes + ovf_bytes)) return rc;
             } else {
                 dim3 grid((unsigned)h, 1, (unsigned)nf);
                 clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, luts);
@@ -1420,8 +1547,13 @@ int yam_clahe_apply(yam_ctx* ctx, const void* src, void* dst, int64_t rows, int6
     dim3 grid((unsigned)rows, 1, 1);
     if (dtype == YAM_U16 && clahe_use_quad(rows * w, tiles_x, tiles_y)) {
         void* scratch = nullptr;
-        if (int rc = yam_scratch(ctx, clahe_quad_bytes(tiles_x, tiles_y), &scratch)) return rc;
+        if (int rc = yam_scratch(ctx, clahe_quad_bytes(tiles_x, tiles_y) + clahe_tab_bytes(w), &scratch)) return rc;
         return clahe_apply16_quad(ctx, (const uint16_t*)src, (uint16_t*)dst, rows, g, (const uint16_t*)luts_dev, (ushort4*)scratch);
+    }
+    if (dtype == YAM_U16 && clahe_tab_ok(src, dst, w)) {
+        void* scratch = nullptr;
+        if (int rc = yam_scratch(ctx, clahe_tab_bytes(w), &scratch)) return rc;
+        return clahe_apply16_tab<false>(ctx, (const uint16_t*)src, (uint16_t*)dst, rows, 1, g, luts_dev, scratch);
     }
     if (dtype == YAM_U16)
         clahe_apply_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, g, (const uint16_t*)luts_dev);
