@@ -242,6 +242,25 @@ int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stri
                            const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
                            int32_t* total_dev);
 
+/* ---- watershed front half (core/segmentation.py:97-111) and second moments ---------
+ * yam_threshold_inv: cv2.threshold(..., THRESH_BINARY_INV [+ OTSU]) (:100): dst = src > t ? 0 : maxval per frame;
+ *   t = thresh_dev[frame] (device int32, e.g. from yam_otsu_threshold) when thresh_dev != NULL, else `thresh`.
+ * yam_distance_transform: cv2.distanceTransform(mask, DIST_L2, 5) (:104): float32 chamfer distance
+ *   (a = 1, b = 1.4, c = 2.1969) of every non-zero pixel to the nearest zero pixel, computed as the least
+ *   fixed point of the chamfer relaxation; within 1e-5 relative of cv2's sequential two-pass scan (equal
+ *   except for isolated one-ulp differences).  launches_out (optional, host) = relaxation launches used.
+ * yam_watershed_combine: markers = labels + 1; markers[sure_bg == 255 and sure_fg == 0] = 0 (:109-110).
+ * yam_region_moments: per label (1..n_labels) sum r^2, sum c^2, sum r*c as int64 [n_labels][3]: with the
+ *   first-order sums of yam_region_props these give skimage's central moments / inertia tensor
+ *   (orientation, eccentricity; core/extraction.py:81-85). */
+int yam_threshold_inv(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
+                      const int32_t* thresh_dev, double thresh, double maxval);
+int yam_distance_transform(yam_ctx* ctx, const uint8_t* mask, float* dist, int64_t n, int64_t h, int64_t w,
+                           int* launches_out);
+int yam_watershed_combine(yam_ctx* ctx, const int32_t* labels, const uint8_t* sure_bg, const uint8_t* sure_fg,
+                          int32_t* markers, int64_t count);
+int yam_region_moments(yam_ctx* ctx, const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, int64_t* moments_dev);
+
 /* Order-independent 64-bit content checksum: ADDS to *sum_dev (device, caller zeroes it) the sum over
  * i < count of mix64((index_base + i) * 0x9E3779B97F4A7C15 + value_i) mod 2^64 (mix64 = splitmix64's
  * finalizer; values zero-extended from U8 | U16 | I32 bit patterns).  A row strip passes the linear

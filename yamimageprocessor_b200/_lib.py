@@ -44,6 +44,7 @@ _CTYPES = {
     "int": C.c_int,
     "int64_t": C.c_int64,
     "double": C.c_double,
+    "float": C.c_float,
     "void": None,
 }
 
@@ -54,7 +55,8 @@ def _ctype_of(decl: str):
     stars = d.count("*")
     base = d.replace("*", " ").split()
     # drop the parameter name when present
-    known = {"int", "int64_t", "int32_t", "uint8_t", "uint32_t", "uint64_t", "double", "void", "char", "yam_ctx"}
+    known = {"int", "int64_t", "int32_t", "uint8_t", "uint16_t", "uint32_t", "uint64_t", "float", "double", "void", "char",
+             "yam_ctx"}
     tokens = [t for t in base if t in known]
     if not tokens:
         raise ValueError(f"cannot parse C declaration: {decl!r}")

@@ -6,6 +6,8 @@
 // (halo re-reads hit L2).  Arithmetic follows oracle/np_oracle.py bit for bit.
 #include <math.h>
 
+#include <type_traits>
+
 #include "yam_common.cuh"
 #include "yam_host.h"
 #include "yam_median_net.h"
@@ -155,38 +157,74 @@ __global__ void __launch_bounds__(kThreads) sep_fixed_tiled(const T* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cx = 2 * lane;
     const int r0 = warp * RB;
-    Acc acc0[RB], acc1[RB];
+    T* s_out = reinterpret_cast<T*>(s_t + ROWS * TWP);
+    if constexpr (sizeof(T) == 2 && EPI == EPI_SHIFT) {
+        // 16-bit Gaussian: sum of 16-bit taps x 32-bit row sums needs 48 bits.  IMAD.WIDE runs at ~36 / clk / SM
+        // (tools/ubench/imad_wide.cu); fp64 FMA at 63 / clk / SM holds every partial sum exactly (< 2^48 < 2^53),
+        // leaves the integer pipe to the horizontal passes of the other resident blocks, and needs no
+        // conversion instruction: (0x43300000 : t) is the double 2^52 + t, and the rounded result
+        // (acc + 2^31) >> 32 is read from the mantissa of acc + (2^52 + 2^31).
+        double kd[KS];
 #pragma unroll
-    for (int j = 0; j < RB; j++) acc0[j] = acc1[j] = 0;
+        for (int k = 0; k < KS; k++) kd[k] = (double)taps.v[k];
+        double a0[RB], a1[RB];
 #pragma unroll
-    for (int i = 0; i < RB + 2 * R; i++) {
-        const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TWP + cx);
+        for (int j = 0; j < RB; j++) a0[j] = a1[j] = 0.0;
 #pragma unroll
-        for (int j = 0; j < RB; j++) {
-            const int k = i - j;  // tap index for output row j
-            if (k >= 0 && k < KS) {
-                acc0[j] += (Acc)taps.v[k] * tv.x;
-                acc1[j] += (Acc)taps.v[k] * tv.y;
+        for (int i = 0; i < RB + 2 * R; i++) {
+            const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TWP + cx);
+            const double t0 = __dsub_rn(__hiloint2double(0x43300000, (int)tv.x), 4503599627370496.0);
+            const double t1 = __dsub_rn(__hiloint2double(0x43300000, (int)tv.y), 4503599627370496.0);
+#pragma unroll
+            for (int j = 0; j < RB; j++) {
+                const int k = i - j;  // tap index for output row j
+                if (k >= 0 && k < KS) {
+                    a0[j] = __fma_rn(kd[k], t0, a0[j]);
+                    a1[j] = __fma_rn(kd[k], t1, a1[j]);
+                }
             }
         }
-    }
-    T* s_out = reinterpret_cast<T*>(s_t + ROWS * TWP);
 #pragma unroll
-    for (int j = 0; j < RB; j++) {
-        uint32_t o0, o1;
-        if (EPI == EPI_SHIFT) {
-            o0 = (uint32_t)((acc0[j] + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
-            o1 = (uint32_t)((acc1[j] + ((Acc)1 << (2 * bits - 1))) >> (2 * bits));
-        } else {
-            // rint(sum / k^2), k^2 odd: (2 sum + k^2) / (2 k^2)
-            o0 = (uint32_t)((2 * (uint32_t)acc0[j] + box_div) / (2 * box_div));
-            o1 = (uint32_t)((2 * (uint32_t)acc1[j] + box_div) / (2 * box_div));
+        for (int j = 0; j < RB; j++) {
+            const uint32_t o0 = (uint32_t)__double2hiint(__dadd_rn(a0[j], 4503599627370496.0 + 2147483648.0)) & 0xffffu;
+            const uint32_t o1 = (uint32_t)__double2hiint(__dadd_rn(a1[j], 4503599627370496.0 + 2147483648.0)) & 0xffffu;
+            *reinterpret_cast<uint32_t*>(s_out + (r0 + j) * TW + cx) = o0 | (o1 << 16);
         }
-        T* d = s_out + (r0 + j) * TW + cx;
-        if (sizeof(T) == 2)
-            *reinterpret_cast<uint32_t*>(d) = o0 | (o1 << 16);
-        else
-            *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
+    } else {
+        // box sums of 16-bit pixels stay below 2^32 (k <= 31), so only the 16-bit Gaussian needs wide sums
+        typedef typename std::conditional<EPI == EPI_BOX, uint32_t, Acc>::type VAcc;
+        VAcc acc0[RB], acc1[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) acc0[j] = acc1[j] = 0;
+#pragma unroll
+        for (int i = 0; i < RB + 2 * R; i++) {
+            const uint2 tv = *reinterpret_cast<const uint2*>(s_t + (r0 + i) * TWP + cx);
+#pragma unroll
+            for (int j = 0; j < RB; j++) {
+                const int k = i - j;  // tap index for output row j
+                if (k >= 0 && k < KS) {
+                    acc0[j] += (VAcc)taps.v[k] * tv.x;
+                    acc1[j] += (VAcc)taps.v[k] * tv.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+            uint32_t o0, o1;
+            if (EPI == EPI_SHIFT) {
+                o0 = (uint32_t)((acc0[j] + ((VAcc)1 << (2 * bits - 1))) >> (2 * bits));
+                o1 = (uint32_t)((acc1[j] + ((VAcc)1 << (2 * bits - 1))) >> (2 * bits));
+            } else {
+                // rint(sum / k^2), k^2 odd: (2 sum + k^2) / (2 k^2)
+                o0 = (uint32_t)((2 * (uint32_t)acc0[j] + box_div) / (2 * box_div));
+                o1 = (uint32_t)((2 * (uint32_t)acc1[j] + box_div) / (2 * box_div));
+            }
+            T* d = s_out + (r0 + j) * TW + cx;
+            if (sizeof(T) == 2)
+                *reinterpret_cast<uint32_t*>(d) = o0 | (o1 << 16);
+            else
+                *reinterpret_cast<uint16_t*>(d) = (uint16_t)(o0 | (o1 << 8));
+        }
     }
     __syncthreads();
     store_tile<T>(s_out, dst, h, w, x0, y0);

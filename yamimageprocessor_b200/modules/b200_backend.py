@@ -230,6 +230,21 @@ def region_properties_data(image: np.ndarray) -> Dict[str, np.ndarray]:
     return region_table(be, labels, gray if gray.dtype in _intensity_dtypes() else None)
 
 
+def watershed_markers_data(image: np.ndarray, kernel_size: int = 3, opening_iterations: int = 2, dilation_iterations: int = 3,
+                           distance_threshold_factor: float = 0.7) -> Dict[str, np.ndarray]:
+    """GPU counterpart of the marker construction inside Detector.watershed_segmentation
+    (core/segmentation.py:99-110) for a uint8 gray or BGR image: thresh, opening, sure_bg, dist (float32
+    chamfer distance), sure_fg and the int32 markers image (0 unknown, 1 background, k + 1 markers).
+    The flooding itself (cv2.watershed, :111) and the red boundary overlay the step returns (:112-114)
+    are a sequential priority-queue algorithm plus UI drawing and stay with the reference: hand it
+    ``markers`` (``cv2.watershed(image, markers)``) to finish the step from here."""
+    ex = _executor()
+    be = ex.backend
+    gray = be.bgr2gray(be.to_device(np.asarray(image)))
+    out = be.watershed_markers(gray, kernel_size, opening_iterations, dilation_iterations, distance_threshold_factor)
+    return {k: be.to_host(v) for k, v in out.items()}
+
+
 def hu_moments_data(image: np.ndarray) -> Dict[str, float]:
     """GPU counterpart of core/extraction.py:100-105: Otsu -> cv2.moments(mask) -> cv2.HuMoments,
     as ``{"hu_1": ..., "hu_7": ...}`` (the mask and its row power sums are formed on the device)."""
@@ -264,4 +279,4 @@ def _intensity_dtypes():
 
 
 __all__ = [cls.__name__ for cls in MODULE_CLASSES] + ["MODULE_CLASSES", "register_module", "region_properties_data",
-                                                       "hu_moments_data", "histogram_data"]
+                                                       "hu_moments_data", "histogram_data", "watershed_markers_data"]
