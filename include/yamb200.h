@@ -128,7 +128,9 @@ int yam_gaussian(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h,
 /* cv2.blur(src,(k,k)) odd k, BORDER_REFLECT_101 (absent from the reference; north_star op) */
 int yam_box(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
             int ksize);
-/* cv2.medianBlur(src,k) k in {3,5} — modules/preprocessing.py:147. border REPLICATE */
+/* cv2.medianBlur(src,k) — modules/preprocessing.py:147. border REPLICATE; k in {3,5}, uint8 also odd k 7..15
+ * (cv2 accepts ksize > 5 for CV_8U only; range ui/control_metadata.py:210-218) */
+/* (uint8 also takes odd ksize 7..15, like cv2.medianBlur; uint16: 3 or 5) */
 int yam_median(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,
                int dtype, int ksize);
 
@@ -241,6 +243,12 @@ int64_t yam_merge_strips_workspace_bytes(int64_t total);
 int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
                            const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
                            int32_t* total_dev);
+
+/* Interleaved (px, channels) <-> planar (channels, px) copies, channels <= 4: cv2's neighbourhood
+ * filters (GaussianBlur, medianBlur, blur, erode / dilate, modules/preprocessing.py:140-150) treat the
+ * channels of a colour image independently, so colour input runs as a stack of planes. */
+int yam_split_channels(yam_ctx* ctx, const void* src, void* dst, int64_t px, int channels, int dtype);
+int yam_merge_channels(yam_ctx* ctx, const void* src, void* dst, int64_t px, int channels, int dtype);
 
 /* ---- watershed front half (core/segmentation.py:97-111) and second moments ---------
  * yam_threshold_inv: cv2.threshold(..., THRESH_BINARY_INV [+ OTSU]) (:100): dst = src > t ? 0 : maxval per frame;

@@ -585,3 +585,50 @@ def test_errors_are_python_exceptions(backend, rng):
         backend.median(t, 7)              # unsupported, like cv2 on u16
     with pytest.raises(TypeError):
         backend.equalize_hist(t)          # u8 only, like the reference
+
+
+# ---------------------------------------------------------------------------------------------
+# input kinds the reference steps accept (VERDICT r1 missing #5): 8-bit median 7..15, colour input
+@pytest.mark.parametrize("k", [7, 9, 11, 13, 15])
+def test_median_u8_large_windows(backend, rng, k):
+    """cv2.medianBlur takes ksize > 5 for CV_8U (modules/preprocessing.py:147; range 1..15 odd,
+    ui/control_metadata.py:210-218): exact rank filter, BORDER_REPLICATE."""
+    for shape in ((64, 64), (33, 71), (130, 257), (3, 40, 50)):
+        a = rnd(rng, shape, U8)
+        if len(shape) == 2:
+            a[5:20, 10:40] = 200                      # flat areas and ties
+        got = host(backend, backend.median(dev(backend, a), k))
+        want = O.median(a, k) if a.ndim == 2 else np.stack([O.median(f, k) for f in a])
+        assert_same(got, want, f"median u8 k={k} {shape}")
+    with pytest.raises(Exception):
+        backend.median(dev(backend, rnd(rng, (32, 32), U16)), 7)   # cv2 raises for uint16 too
+
+
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_colour_input_runs_per_channel(backend, rng, dt):
+    """NoiseReduction / Sharpen / BoxFilter / morphology on (h, w, 3) input: channels independently, like
+    cv2 (modules/preprocessing.py:140-150 is channel-agnostic); IntensityNormalization takes ONE min / max
+    over all channels (cv2.normalize NORM_MINMAX)."""
+    from yamimageprocessor_b200.host.steps import DEVICE_STEPS
+
+    a = rnd(rng, (45, 70, 3), dt)
+    a[..., 1] //= 2
+    x = dev(backend, a)
+    planes = [np.ascontiguousarray(a[..., c]) for c in range(3)]
+    stackc = lambda fn: np.stack([fn(p) for p in planes], axis=-1)
+    assert_same(host(backend, backend.merge_channels(backend.split_channels(x))), a, "split/merge round trip")
+    cases = [
+        ("NoiseReduction", {"method": "Gaussian", "ksize": 11}, lambda p: O.gaussian_fixed(p, 11, 0.0)),
+        ("NoiseReduction", {"method": "Median", "ksize": 5}, lambda p: O.median(p, 5)),
+        ("BoxFilter", {"ksize": 5}, lambda p: O.box(p, 5)),
+        ("Sharpen", {"strength": 1.5}, lambda p: O.sharpen(p, 1.5)),
+        ("Opening", {"kernel_shape": "Elliptical", "kernel_size": 5, "iterations": 1}, lambda p: O.morph_open(p, "Elliptical", 5, 1)),
+        ("Dilation", {"kernel_shape": "Rectangular", "kernel_size": 3, "iterations": 2}, lambda p: O.dilate(p, "Rectangular", 3, 2)),
+    ]
+    if dt == U8:
+        cases.append(("NoiseReduction", {"method": "Median", "ksize": 9}, lambda p: O.median(p, 9)))
+    for name, params, fn in cases:
+        got = host(backend, DEVICE_STEPS[name](backend, x, params))
+        assert_same(got, stackc(fn), f"{name} {params} colour {np.dtype(dt).name}")
+    got = host(backend, DEVICE_STEPS["IntensityNormalization"](backend, x, {"alpha": 10, "beta": 200}))
+    assert_same(got, O.normalize_minmax(a.reshape(45, 210), 10, 200).reshape(45, 70, 3), "IntensityNormalization colour")

@@ -376,6 +376,72 @@ def test_device_pipeline_cache(backend, mods):
         cache.compute(sid, None, [step("Otsu"), type("S", (), {"name": "K-Means", "enabled": True, "params": {}})()])
 
 
+def test_device_cache_progressive_tiles_and_disk_tier(backend, mods, tmp_path):
+    """SURVEY.md 8(f) N1, second half: PipelineCacheTileUpdate stream (processing/pipeline_cache.py:91-105,
+    416-574) from the device tier -- row-major boxes, tiles cut from the halo-correct dense result, a
+    lazy memmap source that is never densified -- and the reference's on-disk layout."""
+    import json
+
+    from yamimageprocessor_b200.host.device_cache import DevicePipelineCache, PipelineCacheTileUpdate
+    from yamimageprocessor_b200.host.executor import B200Executor
+    from yamimageprocessor_b200.host.tiles import TiledImageRecord, TiledPipelineImage, iter_tile_boxes
+
+    def step(name, **params):
+        s = mods[name].create_pipeline_step()
+        s.enabled = True
+        s.params.update(params)
+        return s
+
+    frame = synth.nuclei(300, 420, seed=33)
+    np.save(tmp_path / "src.npy", frame)
+
+    class NoDensify(TiledImageRecord):
+        def to_array(self):
+            raise AssertionError("the lazy source must not be densified")
+
+    rec = NoDensify.from_npy(tmp_path / "src.npy", memmap=np.load(tmp_path / "src.npy", mmap_mode="r"))
+    handle = TiledPipelineImage(rec, tile_size=(128, 96))
+    cache = DevicePipelineCache(B200Executor(backend), cache_directory=tmp_path / "cache")
+    from yamimageprocessor_b200.host import cache_keys
+
+    sid = cache.register_tiled_source(handle, band_rows=64)
+    assert sid == cache_keys.source_id(frame)            # same digest as the dense register_source
+    steps = [step("NoiseReduction", method="Gaussian", ksize=11), step("Adaptive"), step("Opening", kernel_size=5)]
+    updates = []
+    res = cache.compute(sid, handle, steps, incremental=updates.append)
+    want = O.morph_open(O.adaptive_threshold(O.gaussian_fixed(frame, 11, 0.0), 11, 2), "Rectangular", 5, 1)
+    eq(res.image, want, "progressive compute, final image")
+    boxes = list(iter_tile_boxes(420, 300, (128, 96)))
+    assert [u.box for u in updates] == boxes                       # the reference's row-major order
+    assert all(isinstance(u, PipelineCacheTileUpdate) for u in updates)
+    canvas = np.zeros_like(want)
+    for u in updates:
+        left, top, right, bottom = u.box
+        assert u.tile.shape == (bottom - top, right - left) and u.tile.flags.owndata
+        canvas[top:bottom, left:right] = u.tile
+        assert (u.source_id, u.final_signature, u.step_signature) == (sid, res.final_signature, res.steps[-1].signature)
+        assert (u.step_index, u.total_steps, u.shape, u.dtype, u.tile_size, u.from_cache) == (3, 3, want.shape, want.dtype, (128, 96), False)
+    eq(canvas, want, "tiles assemble to the dense (seam-free) result")
+    # second request: served from HBM, flagged from_cache
+    again = []
+    cache.compute(sid, None, steps, incremental=again.append, tile_size=(128, 96))
+    assert all(u.from_cache for u in again) and len(again) == len(boxes)
+    # disk tier: the reference's file name and npz layout (tile_{i} + JSON metadata of type "tiles")
+    path = tmp_path / "cache" / f"{sid}_{res.final_signature}.npz"
+    assert path.exists()
+    with np.load(path, allow_pickle=False) as z:
+        meta = json.loads(str(z["metadata"]))
+        assert meta["type"] == "tiles" and meta["shape"] == list(want.shape) and meta["boxes"] == [list(b) for b in boxes]
+        assert meta["tile_size"] == [128, 96] and meta["dtype"] == str(want.dtype)
+        eq(z["tile_3"], want[boxes[3][1]:boxes[3][3], boxes[3][0]:boxes[3][2]], "tile_3 on disk")
+    # a new cache object (new process) finds the result on disk; dense requests write .npy
+    fresh = DevicePipelineCache(B200Executor(backend), cache_directory=tmp_path / "cache")
+    eq(fresh.get_cached_image(sid, res.final_signature), want, "reload from the disk tier")
+    dense = fresh.compute(fresh.register_source(frame), frame, steps[:1])
+    assert (tmp_path / "cache" / f"{sid}_{dense.final_signature}.npy").exists()
+    eq(np.load(tmp_path / "cache" / f"{sid}_{dense.final_signature}.npy"), O.gaussian_fixed(frame, 11, 0.0), "dense .npy entry")
+
+
 def test_n3_extraction_tables_on_device(backend, gold_n3):
     from yamimageprocessor_b200.modules import b200_backend as plugin
 

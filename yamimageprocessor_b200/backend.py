@@ -280,6 +280,24 @@ class Backend:
         self._call("yam_median", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(ksize))
         return out
 
+    def split_channels(self, img):
+        """(h, w, c) interleaved -> (c, h, w) planes."""
+        torch = _torch()
+        img = self._check(img, ndim=(3,), dtypes=(torch.uint8, torch.uint16, torch.float32))
+        h, w, c = (int(v) for v in img.shape)
+        out = torch.empty((c, h, w), dtype=img.dtype, device=self.device)
+        self._call("yam_split_channels", self._p(img), self._p(out), h * w, c, _dtype_code(img))
+        return out
+
+    def merge_channels(self, planes):
+        """(c, h, w) planes -> (h, w, c) interleaved."""
+        torch = _torch()
+        planes = self._check(planes, ndim=(3,), dtypes=(torch.uint8, torch.uint16, torch.float32))
+        c, h, w = (int(v) for v in planes.shape)
+        out = torch.empty((h, w, c), dtype=planes.dtype, device=self.device)
+        self._call("yam_merge_channels", self._p(planes), self._p(out), h * w, c, _dtype_code(planes))
+        return out
+
     # ------------------------------------------------------------------ K9
     def adaptive_threshold(self, img, block_size: int = 11, C_: float = 2.0):
         torch = _torch()

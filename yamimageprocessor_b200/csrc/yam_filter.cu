@@ -675,6 +675,53 @@ size_t f32_tiled_smem(int ks) {
     return ((size_t)ROWS * SWP + 8 + (size_t)ROWS * TWP) * 4 + (sizeof(Tout) == 1 ? 0 : (size_t)TH * TW * sizeof(Tout));
 }
 
+// median for 8-bit images and windows of 7x7 .. 15x15 (cv2.medianBlur accepts ksize > 5 for CV_8U only,
+// modules/preprocessing.py:147, range ui/control_metadata.py:210-218): the rank (k*k + 1) / 2 element is
+// found by an 8-step binary search on the value, counting window pixels <= mid with the SIMD video
+// compare (four pixels per instruction).  Thread = one output pixel; the (64 + 2r) x (64 + 2r) byte tile
+// lives in shared memory.  Exact: a rank filter has no arithmetic to round.
+__global__ void __launch_bounds__(kThreads) median_u8_search_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                    int h, int w, int ks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = ks / 2;
+    const int RA = round_up_c(R, 16);
+    const int SW = TW + 2 * RA;
+    const int ROWS = TH + 2 * R;
+    uint8_t* s_in = smem_raw;
+    const int64_t frame = blockIdx.z;
+    src += frame * (int64_t)h * w;
+    dst += frame * (int64_t)h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile<uint8_t, uint8_t>(src, s_in, h, w, x0, y0, R, RA, SW, ROWS, YAM_BORDER_REPLICATE);
+    __syncthreads();
+    const int need = (ks * ks + 1) / 2;
+    for (int item = threadIdx.x; item < TH * TW; item += kThreads) {
+        const int ry = item / TW, cx = item - ry * TW;
+        const int gx = x0 + cx, gy = y0 + ry;
+        if (gx >= w || gy >= h) continue;
+        const uint8_t* win = s_in + ry * SW + (RA - R) + cx;   // top-left pixel of the window
+        int lo = 0, hi = 255;                                   // smallest v with count(window <= v) >= need
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const uint32_t m4 = (uint32_t)mid * 0x01010101u;
+            int count = 0;
+            for (int dy = 0; dy < ks; dy++) {
+                const uint8_t* row = win + dy * SW;
+                int dx = 0;
+                for (; dx + 4 <= ks; dx += 4) {
+                    const uint32_t v = (uint32_t)row[dx] | ((uint32_t)row[dx + 1] << 8) | ((uint32_t)row[dx + 2] << 16) |
+                                       ((uint32_t)row[dx + 3] << 24);
+                    count += __popc(__vcmpleu4(v, m4)) >> 3;     // 0xff per byte that is <= mid
+                }
+                for (; dx < ks; dx++) count += row[dx] <= mid;
+            }
+            if (count >= need) hi = mid;
+            else lo = mid + 1;
+        }
+        dst[(int64_t)gy * w + gx] = (uint8_t)lo;
+    }
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -862,9 +909,16 @@ int yam_median(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, i
     if (int rc = yam_enter(ctx)) return rc;
     if (int rc = check_shape(src, dst, n, h, w, "median")) return rc;
     YAM_REQUIRE(src != dst, "median: in-place operation is not supported");
-    YAM_REQUIRE(ksize == 3 || ksize == 5, "median: ksize must be 3 or 5 (got %d)", ksize);
     YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "median: unsupported dtype %d", dtype);
     dim3 grid = tile_grid(n, h, w);
+    if (dtype == YAM_U8 && ksize >= 7 && ksize <= 15 && (ksize & 1)) {
+        const int R = ksize / 2, RA = round_up_c(R, 16);
+        const size_t smem = (size_t)(TH + 2 * R) * (TW + 2 * RA);
+        median_u8_search_kernel<<<grid, kThreads, smem, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, (int)w, ksize);
+        YAM_LAUNCHED(ctx);
+        return YAM_OK;
+    }
+    YAM_REQUIRE(ksize == 3 || ksize == 5, "median: ksize must be 3 or 5, or 7..15 (odd) for uint8 as in cv2 (got %d)", ksize);
     if (dtype == YAM_U8) {
         if (ksize == 3) median_kernel<uint8_t, 3><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, (int)w);
         else median_kernel<uint8_t, 5><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (int)h, (int)w);

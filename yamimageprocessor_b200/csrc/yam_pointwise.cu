@@ -348,6 +348,26 @@ int yam_threshold_dev(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64
     return YAM_OK;
 }
 
+// ---- interleaved colour <-> planes (neighbourhood filters on BGR input run per channel, like cv2) ----
+template <typename T>
+__global__ void __launch_bounds__(kThreads) split_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t px, int ch) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px * ch; i += stride) {
+        const int64_t p = i / ch;
+        const int c = (int)(i - p * ch);
+        dst[(int64_t)c * px + p] = src[i];          // coalesced read, strided write
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) merge_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t px, int ch) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px * ch; i += stride) {
+        const int64_t p = i / ch;
+        const int c = (int)(i - p * ch);
+        dst[i] = src[(int64_t)c * px + p];          // strided read, coalesced write
+    }
+}
+
 // ---- order-independent 64-bit content checksum (parity evidence for sharded runs) -------------------
 // sum over elements of mix64((index_base + i) * GOLDEN + value) mod 2^64: the sum does not depend on
 // how the elements are split over launches, strips or ranks, so a sharded run can add its parts up
@@ -512,5 +532,34 @@ int yam_checksum64(yam_ctx* ctx, const void* src, int64_t count, int dtype, int6
     return YAM_OK;
 }
 
+int yam_split_channels(yam_ctx* ctx, const void* src, void* dst, int64_t px, int channels, int dtype) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && src != dst && px > 0 && channels >= 1 && channels <= 4, "split_channels: bad arguments");
+    int64_t bx = (px * channels + kThreads * 4 - 1) / (kThreads * 4);
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (bx > cap) bx = cap;
+    if (dtype == YAM_U8) split_channels_kernel<uint8_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, px, channels);
+    else if (dtype == YAM_U16) split_channels_kernel<uint16_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, px, channels);
+    else if (dtype == YAM_F32) split_channels_kernel<float><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const float*)src, (float*)dst, px, channels);
+    else YAM_REQUIRE(false, "split_channels: unsupported dtype %d", dtype);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
+int yam_merge_channels(yam_ctx* ctx, const void* src, void* dst, int64_t px, int channels, int dtype) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(src && dst && src != dst && px > 0 && channels >= 1 && channels <= 4, "merge_channels: bad arguments");
+    int64_t bx = (px * channels + kThreads * 4 - 1) / (kThreads * 4);
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (bx > cap) bx = cap;
+    if (dtype == YAM_U8) merge_channels_kernel<uint8_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, px, channels);
+    else if (dtype == YAM_U16) merge_channels_kernel<uint16_t><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, px, channels);
+    else if (dtype == YAM_F32) merge_channels_kernel<float><<<(unsigned)bx, kThreads, 0, ctx->stream>>>((const float*)src, (float*)dst, px, channels);
+    else YAM_REQUIRE(false, "merge_channels: unsupported dtype %d", dtype);
+    YAM_LAUNCHED(ctx);
+    return YAM_OK;
+}
+
 }  // extern "C"
+
 

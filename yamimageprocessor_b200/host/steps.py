@@ -44,6 +44,14 @@ def _plane_only(t, name: str):
     return t
 
 
+def _per_channel(be: Backend, t, fn):
+    """cv2's neighbourhood filters treat the channels of an interleaved colour image independently
+    (modules/preprocessing.py:140-150 is channel-agnostic): run ``fn`` on the (c, h, w) plane stack."""
+    if not _is_colour(t):
+        return fn(t)
+    return be.merge_channels(fn(be.split_channels(t)))
+
+
 def grayscale(be: Backend, t, p: Mapping[str, Any]):
     return _gray(be, t)
 
@@ -65,17 +73,21 @@ def gamma(be: Backend, t, p):
 
 
 def intensity_normalization(be: Backend, t, p):
-    return be.normalize_minmax(_plane_only(t, "IntensityNormalization"), float(p.get("alpha", 0)), float(p.get("beta", 255)))
+    if _is_colour(t):
+        # cv2.normalize(NORM_MINMAX) on a multi-channel image takes ONE min / max over all channels
+        # (cv::norm / minMaxLoc on the reshaped matrix): the interleaved frame is one (h, w*c) plane
+        h, w, c = (int(v) for v in t.shape)
+        return be.normalize_minmax(t.reshape(h, w * c), float(p.get("alpha", 0)), float(p.get("beta", 255))).reshape(h, w, c)
+    return be.normalize_minmax(t, float(p.get("alpha", 0)), float(p.get("beta", 255)))
 
 
 def noise_reduction(be: Backend, t, p):
     method = str(p.get("method", "Gaussian"))
     ksize = int(p.get("ksize", 5))
-    t = _plane_only(t, "NoiseReduction")
     if method == "Gaussian":
-        return be.gaussian(t, ksize, 0.0)
+        return _per_channel(be, t, lambda x: be.gaussian(x, ksize, 0.0))
     if method == "Median":
-        return be.median(t, ksize)
+        return _per_channel(be, t, lambda x: be.median(x, ksize))
     if method == "Bilateral":
         raise UnsupportedOnDevice("NoiseReduction(method='Bilateral') is outside the GPU hot path")
     return t  # unknown method: identity, like modules/preprocessing.py:150
@@ -87,7 +99,7 @@ def clahe(be: Backend, t, p):
 
 
 def box_filter(be: Backend, t, p):
-    return be.box(_plane_only(t, "BoxFilter"), int(p.get("ksize", 3)))
+    return _per_channel(be, t, lambda x: be.box(x, int(p.get("ksize", 3))))
 
 
 def histogram_equalization(be: Backend, t, p):
@@ -107,7 +119,7 @@ def adaptive(be: Backend, t, p):
 
 
 def sharpen(be: Backend, t, p):
-    return be.sharpen(_plane_only(t, "Sharpen"), float(p.get("strength", 1.0)))
+    return _per_channel(be, t, lambda x: be.sharpen(x, float(p.get("strength", 1.0))))
 
 
 def select_channel(be: Backend, t, p):
@@ -132,13 +144,13 @@ def border_removal(be: Backend, t, p):
 
 def _morph(op: int) -> Callable:
     def run(be: Backend, t, p):
-        return be.morph(
-            _plane_only(t, "morphology"),
+        return _per_channel(be, t, lambda x: be.morph(
+            x,
             op,
             str(p.get("kernel_shape", "Rectangular")),
             int(p.get("kernel_size", 3)),
             int(p.get("iterations", 1)),
-        )
+        ))
 
     return run
 
