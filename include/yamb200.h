@@ -235,14 +235,15 @@ int yam_merge_strip_labels(yam_ctx* ctx, const int32_t* edges_dev, const int64_t
  * (w values) followed by its last label row (w values) -- what an all-gather of every rank's two
  * boundary rows delivers; anything after 2w in a row (e.g. the strip's count) is ignored.
  * offsets_host[world + 1] (HOST memory) is the exclusive prefix of the per-strip component counts.
- * Writes remap_dev[0 .. count_rank] for strip `rank`: remap[l] = global label of local label l
+ * Writes, for each of the strips rank .. rank + rank_count - 1 (the strips this process owns), a table
+ * of count_r + 1 entries back to back into remap_dev: remap[l] = global label of local label l
  * (remap[0] = 0; labels number merged components by their first pixel in raster order, the same
  * numbering a dense run produces), and total_dev[0] = number of merged components.  `workspace`:
  * yam_merge_strips_workspace_bytes(offsets_host[world]) bytes of 256-byte aligned device memory. */
 int64_t yam_merge_strips_workspace_bytes(int64_t total);
 int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
-                           const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
-                           int32_t* total_dev);
+                           const int64_t* offsets_host, int rank, int rank_count, void* workspace,
+                           int32_t* remap_dev, int32_t* total_dev);
 
 /* Interleaved (px, channels) <-> planar (channels, px) copies, channels <= 4: cv2's neighbourhood
  * filters (GaussianBlur, medianBlur, blur, erode / dilate, modules/preprocessing.py:140-150) treat the

@@ -632,3 +632,23 @@ def test_colour_input_runs_per_channel(backend, rng, dt):
         assert_same(got, stackc(fn), f"{name} {params} colour {np.dtype(dt).name}")
     got = host(backend, DEVICE_STEPS["IntensityNormalization"](backend, x, {"alpha": 10, "beta": 200}))
     assert_same(got, O.normalize_minmax(a.reshape(45, 210), 10, 200).reshape(45, 70, 3), "IntensityNormalization colour")
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15])
+def test_gaussian_u16_tma_kernel(backend, rng, k):
+    """uint16 frames with 16-byte rows, >= 256 x 96, take the TMA-staged persistent kernel
+    (yam_gauss_tma.cu): bit-exact against the oracle (cv2's fixed-point Gaussian), including tiles that
+    hang over every border (REFLECT_101 mirror), widths that are not multiples of 240, and stacks."""
+    for shape in ((96, 256), (130, 272), (300, 496), (100, 1104), (2, 181, 720)):
+        a = rnd(rng, shape, U16)
+        a[..., :3, :] = 65535
+        a[..., :, -4:] = 65535          # saturated borders: the 48-bit sums reach their maximum
+        got = host(backend, backend.gaussian(dev(backend, a), k, 0.0))
+        want = O.gaussian_fixed(a, k, 0.0) if a.ndim == 2 else np.stack([O.gaussian_fixed(f, k, 0.0) for f in a])
+        assert_same(got, want, f"gaussian u16 (TMA) k={k} {shape}")
+    # replicate border (the adaptive-threshold convention) through the same kernel
+    a = rnd(rng, (128, 512), U16)
+    from yamimageprocessor_b200._lib import BORDER_REPLICATE
+    got = host(backend, backend.gaussian(dev(backend, a), k, 0.0, BORDER_REPLICATE))
+    legacy = host(backend, backend.gaussian(dev(backend, a[:, :250].copy()), k, 0.0, BORDER_REPLICATE))   # narrow: generic kernel
+    assert_same(got[:, :200], legacy[:, :200], f"gaussian u16 replicate border k={k}")

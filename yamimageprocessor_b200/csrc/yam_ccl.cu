@@ -1104,30 +1104,41 @@ __global__ void __launch_bounds__(kThreads) merge_flatten_kernel(const int32_t* 
     }
 }
 
-// exclusive prefix of the per-word non-root counts (one block; word counts are tiny: total / 32)
+// exclusive prefix of the per-word non-root counts.  One block of 32 warps; warp w owns a contiguous
+// segment, lanes stride through it (coalesced): pass 1 sums the segments, pass 2 writes the prefix with
+// a shuffle scan per 32-word group and a running carry.
 __global__ void __launch_bounds__(1024) merge_scan_kernel(const uint32_t* __restrict__ nonroot, int64_t nwords,
                                                           uint32_t* __restrict__ prefix, int64_t total,
                                                           int32_t* __restrict__ total_out) {
-    __shared__ uint32_t part[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (nwords + 1023) / 1024;
-    const int64_t b0 = min(nwords, (int64_t)t * per), b1 = min(nwords, b0 + per);
+    __shared__ uint32_t seg_sum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t seg = ((nwords + 31) / 32 + 31) / 32 * 32;          // words per warp, a multiple of 32
+    const int64_t b0 = min(nwords, (int64_t)warp * seg), b1 = min(nwords, b0 + seg);
     uint32_t s = 0;
-    for (int64_t i = b0; i < b1; i++) s += __popc(nonroot[i]);
-    part[t] = s;
+    for (int64_t i = b0 + lane; i < b1; i += 32) s += __popc(nonroot[i]);
+    s = yam_warp_sum(s);
+    if (lane == 0) seg_sum[warp] = s;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-        const uint32_t v = t >= o ? part[t - o] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+    uint32_t carry = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const uint32_t v = seg_sum[i];
+        if (i < warp) carry += v;
+        all += v;
     }
-    uint32_t run = part[t] - s;
-    for (int64_t i = b0; i < b1; i++) {
-        prefix[i] = run;
-        run += __popc(nonroot[i]);
+    for (int64_t g = b0; g < b1; g += 32) {
+        const int64_t i = g + lane;
+        const uint32_t c = i < b1 ? __popc(nonroot[i]) : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (i < b1) prefix[i] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (t == 1023) total_out[0] = (int32_t)(total - (int64_t)part[1023]);
+    if (threadIdx.x == 0) total_out[0] = (int32_t)(total - (int64_t)all);
 }
 
 // remap[l] = raster-first global label of local label l of strip `rank`: the rank of its root among
@@ -1158,13 +1169,13 @@ int64_t yam_merge_strips_workspace_bytes(int64_t total) {
 }
 
 int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
-                           const int64_t* offsets_host, int rank, void* workspace, int32_t* remap_dev,
+                           const int64_t* offsets_host, int rank, int rank_count, void* workspace, int32_t* remap_dev,
                            int32_t* total_dev) {
     if (int rc = yam_enter(ctx)) return rc;
     YAM_REQUIRE(packed_dev && offsets_host && workspace && remap_dev && total_dev, "merge_strips_remap: NULL argument");
-    YAM_REQUIRE(world >= 1 && world <= 64 && w > 0 && stride >= 2 * w && rank >= 0 && rank < world,
-                "merge_strips_remap: bad geometry (world %d, w %lld, stride %lld, rank %d)", world, (long long)w,
-                (long long)stride, rank);
+    YAM_REQUIRE(world >= 1 && world <= 64 && w > 0 && stride >= 2 * w && rank >= 0 && rank_count >= 1 && rank + rank_count <= world,
+                "merge_strips_remap: bad geometry (world %d, w %lld, stride %lld, strips %d..+%d)", world, (long long)w,
+                (long long)stride, rank, rank_count);
     StripOffsets offs;
     for (int i = 0; i <= world; i++) {
         offs.v[i] = offsets_host[i];
@@ -1190,9 +1201,14 @@ int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stri
     }
     merge_scan_kernel<<<1, 1024, 0, ctx->stream>>>(nonroot, nwords, prefix, total, total_dev);
     YAM_LAUNCHED(ctx);
-    const int64_t mine = offs.v[rank + 1] - offs.v[rank];
-    merge_remap_kernel<<<blocks(mine + 1), kThreads, 0, ctx->stream>>>(P, nonroot, prefix, offs.v[rank], mine, remap_dev);
-    YAM_LAUNCHED(ctx);
+    // tables of strips rank .. rank + rank_count - 1, back to back (count_i + 1 entries each)
+    int64_t at = 0;
+    for (int r = rank; r < rank + rank_count; r++) {
+        const int64_t mine = offs.v[r + 1] - offs.v[r];
+        merge_remap_kernel<<<blocks(mine + 1), kThreads, 0, ctx->stream>>>(P, nonroot, prefix, offs.v[r], mine, remap_dev + at);
+        YAM_LAUNCHED(ctx);
+        at += mine + 1;
+    }
     return YAM_OK;
 }
 

@@ -837,6 +837,11 @@ int yam_gaussian(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h,
         }
         if (dtype == YAM_U8)
             return launch_fixed<uint8_t, EPI_SHIFT>(ctx, (const uint8_t*)src, (uint8_t*)dst, n, h, w, taps, ksize, border, 0);
+        {
+            int handled = 0;  // TMA-staged persistent kernel (yam_gauss_tma.cu) for the shapes a tensor map can describe
+            if (int rc = yam_gauss16_tma(ctx, src, dst, n, h, w, ksize, taps.v, border, &handled)) return rc;
+            if (handled) return YAM_OK;
+        }
         return launch_fixed<uint16_t, EPI_SHIFT>(ctx, (const uint16_t*)src, (uint16_t*)dst, n, h, w, taps, ksize, border, 0);
     }
     YAM_REQUIRE(dtype == YAM_F32, "gaussian: unsupported dtype %d", dtype);

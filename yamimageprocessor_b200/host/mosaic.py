@@ -315,12 +315,14 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         cnt_ready.synchronize()
         offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
         # union of the ids that touch across (sub-)strip boundaries + raster-first renumbering: one
-        # library call per sub-strip, small kernels, all on the device (yam_merge_strips_remap);
+        # library call, small kernels, all on the device (yam_merge_strips_remap);
         # the label image is written once, already in global numbering
         labels = torch.empty((rows_core, W), dtype=torch.int32, device=be.device)
+        remaps, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub, k_sub)
+        if k_sub == 1:
+            remaps = [remaps]
         for i, (b, ws_i, cnt_i) in enumerate(subs):
-            remap, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub + i)
-            be.ccl_emit(b, W, ws_i, remap=remap, out=labels[i * sub_rows:(i + 1) * sub_rows])
+            be.ccl_emit(b, W, ws_i, remap=remaps[i], out=labels[i * sub_rows:(i + 1) * sub_rows])
     else:
         otsu_mask = be.threshold(c_core, float(t), 255)
         mark("otsu")
