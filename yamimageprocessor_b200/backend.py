@@ -498,6 +498,73 @@ class Backend:
             at += n
         return views, total
 
+    # ------------------------------------------------------------------ watershed front half
+    def threshold_inv(self, img, thresh: float = 0.0, maxval: float = 255.0, t_dev=None):
+        """cv2.threshold(..., THRESH_BINARY_INV): dst = src > t ? 0 : maxval; ``t_dev`` (int32[n] on the
+        device, e.g. from ``otsu_threshold``) takes precedence over ``thresh``."""
+        torch = _torch()
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        n, h, w = self._nhw(img)
+        out = torch.empty_like(img)
+        self._call("yam_threshold_inv", self._p(img), self._p(out), n, h, w, _dtype_code(img),
+                   self._p(t_dev) if t_dev is not None else None, float(thresh), float(maxval))
+        return out
+
+    def distance_transform(self, mask):
+        """cv2.distanceTransform(mask, DIST_L2, 5): float32 chamfer distance to the nearest zero pixel."""
+        torch = _torch()
+        mask = self._check(mask, dtypes=(torch.uint8,), name="mask")
+        n, h, w = self._nhw(mask)
+        dist = torch.empty(mask.shape, dtype=torch.float32, device=self.device)
+        launches = C.c_int(0)
+        self._call("yam_distance_transform", self._p(mask), self._p(dist), n, h, w, C.cast(C.byref(launches), C.c_void_p))
+        self.last_distance_launches = int(launches.value)
+        return dist
+
+    def watershed_markers(self, gray, kernel_size: int = 3, opening_iterations: int = 2, dilation_iterations: int = 3,
+                          distance_threshold_factor: float = 0.7):
+        """The marker construction of ``Detector.watershed_segmentation`` (core/segmentation.py:97-111) for one
+        uint8 frame, every stage on the device.  Returns a dict of CUDA tensors: ``thresh`` (what the reference
+        step returns), ``opening``, ``sure_bg``, ``dist``, ``sure_fg``, ``markers`` (int32: 0 unknown,
+        1 background, k + 1 for marker k in raster-first order) and ``n_markers`` (int32[1])."""
+        torch = _torch()
+        gray = self._check(gray, ndim=(2,), dtypes=(torch.uint8,), name="gray")
+        t, _ = self.otsu_threshold(gray, want_image=False)
+        thresh = self.threshold_inv(gray, t_dev=t)
+        opening = self.morph_open(thresh, "Rectangular", kernel_size, opening_iterations)
+        sure_bg = self.dilate(opening, "Rectangular", kernel_size, dilation_iterations)
+        dist = self.distance_transform(opening)
+        dmax = float(self.minmax(dist)[0, 1])
+        # cv2.threshold on float32 compares against the threshold cast to float32
+        fg_f = self.threshold(dist, float(np.float32(distance_threshold_factor * np.float64(np.float32(dmax)))), 255.0)
+        sure_fg = self.convert_scale_abs(fg_f, 1.0, 0.0)         # np.uint8(sure_fg)
+        labels, counts = self.ccl_label(sure_fg)
+        markers = torch.empty_like(labels)
+        self._call("yam_watershed_combine", self._p(labels), self._p(sure_bg), self._p(sure_fg), self._p(markers), int(labels.numel()))
+        return {"thresh": thresh, "opening": opening, "sure_bg": sure_bg, "dist": dist, "sure_fg": sure_fg,
+                "markers": markers, "n_markers": counts}
+
+    def region_moments(self, labels, n_labels: int):
+        """int64 [n_labels, 3] on device: per label sum r^2, sum c^2, sum r*c (second-order raw moments)."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(2,), dtypes=(torch.int32,), name="labels")
+        out = torch.zeros((int(n_labels), 3), dtype=torch.int64, device=self.device)
+        if n_labels > 0:
+            self._call("yam_region_moments", self._p(labels), int(labels.shape[0]), int(labels.shape[1]), int(n_labels), self._p(out))
+        return out
+
+    def checksum64(self, t, index_base: int = 0, accumulate=None):
+        """Order-independent content checksum (yam_checksum64) of a uint8 / uint16 / int32 CUDA tensor;
+        returns an int64 tensor [1] (bit pattern of the uint64 sum), adding into ``accumulate`` if given."""
+        torch = _torch()
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise TypeError("checksum64 expects a CUDA tensor on this backend's device")
+        t = t.contiguous()
+        out = accumulate if accumulate is not None else torch.zeros((1,), dtype=torch.int64, device=self.device)
+        if t.numel():
+            self._call("yam_checksum64", self._p(t), int(t.numel()), _dtype_code(t), int(index_base), self._p(out))
+        return out
+
     def otsu_from_histogram(self, hist: np.ndarray) -> int:
         """cv2's Otsu recurrence on a host histogram (int64/uint64 counts); host-only helper."""
         h = np.ascontiguousarray(hist, dtype=np.uint64)
