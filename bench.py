@@ -324,8 +324,12 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
     def run_batch(inp):
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
-        t, otsu_mask = be.otsu_threshold(c, 255)
+        # the fp64 Otsu recurrence is sequential per frame and runs on host worker threads: the histograms
+        # are read back asynchronously, the segmentation (which does not depend on the thresholds) is
+        # enqueued, and only then does the host scan -- the GPU works through the queue meanwhile
+        pending = be.otsu_begin(c)
         labels, counts = be.segment_fused(c, 11, 2, 5, 1)
+        t, otsu_mask = be.otsu_finish(pending, 255)
         tables, offsets = be.region_props_stack(labels, c, counts)
         return otsu_mask, labels, tables
 
@@ -846,6 +850,9 @@ def run_gpu(args):
                 "algorithmic_bytes_per_px": cfg["bpp"],
                 "l2": "256 MiB flush write between timed steps (not timed)",
                 "seed": "1000 + i for 32 distinct frames, cycled over the job" if strong else "1000 + rank*frames + i",
+                "otsu_scan": ("device (staged fp64 scan kernels)" if be.lib.yam_otsu_prefers_device(C5_BATCH if strong else nfr)
+                              else f"host worker threads ({be.host_threads}), fp64 recurrence of 65536 dependent steps per frame")
+                             if args.workload in ("c1", "c5") else None,
                 "multi_gpu": ("contiguous frame blocks per rank, no data-path collective" if strong
                               else "replicas only: every rank runs its own frame (SURVEY.md 8e)"),
             },
