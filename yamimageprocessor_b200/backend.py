@@ -83,6 +83,7 @@ class Backend:
         self._ctx = handle
         self._pinned: Dict[Tuple[str, int], object] = {}
         self._lock = threading.RLock()
+        self._last_stream = None
 
     # ------------------------------------------------------------------ plumbing
     def close(self) -> None:
@@ -99,7 +100,16 @@ class Backend:
     def _call(self, name: str, *args) -> None:
         torch = _torch()
         with self._lock:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cur = torch.cuda.current_stream(self.device)
+            stream = cur.cuda_stream
+            # The context's scratch arena and staging buffers are shared by every caller of this Backend and
+            # are ordered by the stream the work is enqueued on.  Callers normally stay on one stream; when
+            # the current stream CHANGES, the previous stream is drained first so that two streams can never
+            # have kernels in flight on the same scratch (rare, so the common path pays nothing).
+            prev = self._last_stream
+            if prev is not None and prev.cuda_stream != stream:
+                prev.synchronize()
+            self._last_stream = cur
             _lib.check("yam_ctx_set_stream", self.lib.yam_ctx_set_stream(self._ctx, C.c_void_p(stream)))
             _lib.check(name, getattr(self.lib, name)(self._ctx, *args))
 

@@ -243,7 +243,16 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     r0, r1 = max(0, a0 - hg), min(H, a1 + hg)                  # rows of input needed
 
     # rows are streamed from the (memmap) source through a pinned ring, gather overlapping the DMA
+    import os
+    import time
+
+    _t0 = time.perf_counter()
     x = device_source if device_source is not None else ingest.upload_rows(be, source, r0, r1)
+    if os.environ.get("YAM_E2E_TRACE") and device_source is None:
+        import sys
+
+        torch.cuda.synchronize()
+        sys.stderr.write(f"[e2e] rank {rank}: upload_rows {(r1 - r0) * W * 2 / 1e9:.2f} GB in {1e3 * (time.perf_counter() - _t0):.1f} ms\n")
     g = be.gaussian(x, p.gauss_ksize, 0.0)                     # exact on [a0, a1): artificial edges are hg rows away
     mark("gaussian")
 

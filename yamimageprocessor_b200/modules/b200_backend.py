@@ -165,7 +165,13 @@ class MosaicModule(_GpuModule):
         be = _executor().backend
         if isinstance(image, np.ndarray) and image.ndim != 2:
             raise ValueError("Mosaic expects a single-channel (H, W) image or tiled handle")
+        import os
+        import time
+
+        trace = os.environ.get("YAM_E2E_TRACE")
+        t0 = time.perf_counter()
         results = mosaic.run_source(be, image, mp, strips_per_process=int(p["strips"]))
+        t1 = time.perf_counter()
         self.last_results = results              # Otsu threshold / mask / CLAHE rows stay on the device for callers
         # Labels come back like every other step result (Backend.to_host): a fresh array backed by the
         # page-locked host pool, so the device -> host copy is one DMA per strip at PCIe speed with no
@@ -179,7 +185,13 @@ class MosaicModule(_GpuModule):
             n = int(r.labels.shape[0])
             torch.from_numpy(out[y:y + n]).copy_(r.labels, non_blocking=True)
             y += n
+        t2 = time.perf_counter()
         torch.cuda.current_stream(be.device).synchronize()
+        if trace:
+            import sys
+
+            sys.stderr.write(f"[e2e] upload+compute {1e3 * (t1 - t0):.1f} ms, pinned alloc + enqueue {1e3 * (t2 - t1):.1f} ms, "
+                             f"download wait {1e3 * (time.perf_counter() - t2):.1f} ms\n")
         return out
 
 
