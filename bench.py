@@ -258,7 +258,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             return [
                 ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
                 ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-                ("otsu_threshold_u16 (hist + exact fp64 scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+                ("otsu_threshold_u16 (hist + certified scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ]
         return x, run, ops
 
@@ -324,9 +324,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
     def run_batch(inp):
         g = be.gaussian(inp, 11, 0.0)
         c = be.clahe(g, 2.0, (8, 8))
-        # the fp64 Otsu recurrence is sequential per frame and runs on host worker threads: the histograms
-        # are read back asynchronously, the segmentation (which does not depend on the thresholds) is
-        # enqueued, and only then does the host scan -- the GPU works through the queue meanwhile
+        # histogram + certified parallel Otsu scan on the device (thresholds never leave HBM)
         pending = be.otsu_begin(c)
         labels, counts = be.segment_fused(c, 11, 2, 5, 1)
         t, otsu_mask = be.otsu_finish(pending, 255)
@@ -350,7 +348,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
         return [
             ("gaussian_fixed_u16_k11", 4.0, lambda: be.gaussian(inp, 11, 0.0)),
             ("clahe_u16 (lut + apply)", 6.0, lambda: be.clahe(g, 2.0, (8, 8))),
-            ("otsu_threshold_u16 (hist + exact fp64 scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
+            ("otsu_threshold_u16 (hist + certified scan + threshold)", 6.0, lambda: be.otsu_threshold(c, 255)),
             ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(c, 11, 2)),
             ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
             ("ccl_label_bits (scan, tile, border, rank, frame_offsets, final_warp)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
@@ -579,7 +577,12 @@ def run_gpu_mosaic(args):
 
     def otsu_op():
         h = be.histogram(c)
-        return be.threshold(c, 30000.0, 255), h
+        return be.threshold_frames(c, be.otsu_from_histogram_device(h), 255), h
+
+    _, cert = be.otsu_from_histogram_device(be.histogram(c), want_certified=True)
+    otsu_where = ("device: certified parallel scan (one 8-CTA cluster; " +
+                  ("certificate decided this histogram, no sequential chain)" if int(cert[0].item())
+                   else "NOT certified for this histogram: exact fp64 chain kernels ran)"))
 
     sub_rows = (c1 - c0) // max(1, -(-strip_px // mosaic._CCL_MAX_PX))
 
@@ -594,7 +597,7 @@ def run_gpu_mosaic(args):
         ("gaussian_fixed_u16_k11 (sep_fixed_tiled)", 4.0, measure(lambda: be.gaussian(g_core, p.gauss_ksize, 0.0))),
         ("clahe_u16 (tile LUTs + apply)", 6.0, measure(lambda: be.clahe_apply(
             g_core, be.clahe_luts(g_core, p.clip_limit, (p.tile_grid[0], p.tile_grid[1] // world)), (tw, th), 0))),
-        ("otsu_u16 (histogram + threshold; the fp64 scan overlaps the segmentation kernels)", 6.0, measure(otsu_op)),
+        ("otsu_u16 (histogram + certified scan + threshold)", 6.0, measure(otsu_op)),
         ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125,
          measure(lambda: be.adaptive_threshold_bits(c, p.block_size, p.C))),
         ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, measure(lambda: be.bits_morph(bits, W, 4, p.morph_ksize, 1))),
@@ -672,7 +675,7 @@ def run_gpu_mosaic(args):
                        "algorithmic_bytes_per_px": cfg["bpp"],
                        "l2": "every strip (>= 1 GiB at 65536^2) exceeds the 126 MB L2; no flush needed",
                        "seed": "source frames 100..103, pattern (7*ty + 3*tx) % 4",
-                       "otsu_scan": "host worker thread, overlapped with the segmentation kernels (fp64 recurrence of 65536 dependent steps)"},
+                       "otsu_scan": otsu_where},
             "check": check,
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic(dom[0], strip_px),
@@ -750,6 +753,15 @@ def run_gpu(args):
     for _ in range(max(3, args.warmup)):
         run(inp)
     barrier()
+
+    otsu_where = None
+    if args.workload in ("c1", "c5"):     # where the Otsu scan runs for this workload's histograms (untimed probe)
+        probe = inp[:C5_BATCH] if strong else inp
+        _, cert = be.otsu_from_histogram_device(be.histogram(be.clahe(be.gaussian(probe, 11, 0.0), 2.0, (8, 8))), want_certified=True)
+        ncert, nall = int(cert.sum().item()), int(cert.numel())
+        otsu_where = (f"device: certified parallel scan, one 8-CTA cluster per frame; {ncert} of {nall} frames decided by the "
+                      "certificate, the rest by the exact fp64 chain kernels; no host scan, nothing read back")
+        barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -850,9 +862,7 @@ def run_gpu(args):
                 "algorithmic_bytes_per_px": cfg["bpp"],
                 "l2": "256 MiB flush write between timed steps (not timed)",
                 "seed": "1000 + i for 32 distinct frames, cycled over the job" if strong else "1000 + rank*frames + i",
-                "otsu_scan": ("device (staged fp64 scan kernels)" if be.lib.yam_otsu_prefers_device(C5_BATCH if strong else nfr)
-                              else f"host worker threads ({be.host_threads}), fp64 recurrence of 65536 dependent steps per frame")
-                             if args.workload in ("c1", "c5") else None,
+                "otsu_scan": otsu_where if args.workload in ("c1", "c5") else None,
                 "multi_gpu": ("contiguous frame blocks per rank, no data-path collective" if strong
                               else "replicas only: every rank runs its own frame (SURVEY.md 8e)"),
             },

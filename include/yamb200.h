@@ -73,10 +73,8 @@ int yam_ctx_synchronize(yam_ctx* ctx);
 /* counts kernel launches issued through this context since the last reset (bench "gpu_launches") */
 int64_t yam_ctx_launch_count(yam_ctx* ctx, int reset);
 
-/* Host worker threads this process may use for the sequential fp64 Otsu scans (default: all
- * hardware threads, at most 32).  One process per GPU: pass cores / local_world_size so that 8
- * ranks on one box do not oversubscribe; the staged device scan takes over when the host share
- * would be slower (see yam_otsu_threshold).  Returns the value now in effect. */
+/* Host worker threads the host-only helper yam_otsu_from_hists may use (default: all hardware
+ * threads, at most 32).  The device operators do not use host threads.  Returns the value in effect. */
 int yam_set_host_threads(int threads);
 /* raw device memory + copies for hosts that do not bring their own allocator */
 int yam_malloc(yam_ctx* ctx, int64_t bytes, void** out);
@@ -95,9 +93,6 @@ int yam_structuring_element(int shape, int ksize, uint8_t* out);
 int yam_otsu_from_hist(const uint64_t* hist, int bins, int* out_threshold);
 /* the same for n histograms (hists[n][bins], host memory) on the host worker pool */
 int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out_thresholds);
-/* 1 if yam_otsu_threshold would scan a stack of n 16-bit frames on the device (cost model over
- * this process's host threads), else 0 */
-int yam_otsu_prefers_device(int64_t n);
 
 /* ---- K1 colour -> gray: cv2.cvtColor(BGR2GRAY) --------------------------------------------
  * replaces modules/preprocessing.py:54, core/preprocessing.py:56, core/segmentation.py:48,
@@ -171,8 +166,17 @@ int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w
 /* Otsu threshold per frame from src (cv2.threshold(...THRESH_OTSU) — core/segmentation.py:147,
  * core/extraction.py:59,72): thresholds to thresh_dev[n] (int32, device) and thresh_host[n]
  * (optional), then dst = src > t ? maxval : 0 in the source dtype if dst != NULL. */
-/* dst = src > thresh_dev[frame] ? maxval : 0 per frame (thresholds int32 on the device): the second
- * half of an Otsu threshold whose scan ran elsewhere (overlapped host scan, all-reduced histogram) */
+/* The scan runs on the device and nothing is read back: histogram -> certified parallel scan (one
+ * 8-CTA cluster per frame proves the arg-max from exact integer prefix sums and a forward error bound of
+ * cv2's fp64 recurrence) -> exact sequential chain kernels only for frames that could not be certified.
+ * yam_otsu_from_hist_dev: the scan alone, for histograms that are already on the device (all-reduced
+ * across ranks: core/segmentation.py:147 on a mosaic); hist_dev[n][bins] uint64, bins = 256 | 65536.
+ * certified_dev (optional, int32[n]): 1 where the certificate decided the frame, 0 where the chain ran.
+ * yam_otsu_set_force_chain(1): every frame goes through the exact chain (tests, comparisons); returns the old value.
+ * yam_threshold_frames: dst = src > thresh_dev[frame] ? maxval : 0 per frame (thresholds int32 on the device). */
+int yam_otsu_from_hist_dev(yam_ctx* ctx, const uint64_t* hist_dev, int bins, int64_t n, int32_t* thresh_dev,
+                           int32_t* certified_dev);
+int yam_otsu_set_force_chain(int on);
 int yam_threshold_frames(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
                          const int32_t* thresh_dev, double maxval);
 int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w,

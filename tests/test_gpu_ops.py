@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
+from yamimageprocessor_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -246,20 +247,15 @@ def test_otsu(backend, rng, dt):
 
 
 def test_otsu_stack_device_scan(backend, rng):
-    a = np.stack([blobs(rng, (48, 64), U16) for _ in range(9)])  # n >= 8 -> device scan kernel
+    a = np.stack([blobs(rng, (48, 64), U16) for _ in range(9)])
     t, out = backend.otsu_threshold(dev(backend, a), 255)
     want_t = [O.otsu_value(p) for p in a]
     assert host(backend, t).tolist() == want_t
     assert_same(host(backend, out), np.stack([O.threshold_binary(p, tt, 255) for p, tt in zip(a, want_t)]), "otsu stack")
 
 
-def test_otsu_stack_staged_scan_distributions(backend, rng):
-    """>= 8 frames: the staged device scan (q1 chain, reciprocals, corrected-quotient mu1 chain,
-    parallel sigma with bit-for-bit verification) must return the reference thresholds for every
-    kind of histogram: dense, sparse plateaus (12-bit data), constant, two-level, near-empty tails."""
-    frames = []
-    shape = (96, 128)
-    frames += [blobs(rng, shape, U16), rnd(rng, shape, U16)]
+def _otsu_distribution_frames(rng, shape=(96, 128), total=70):
+    frames = [blobs(rng, shape, U16), rnd(rng, shape, U16)]
     frames.append((rnd(rng, shape, U16) >> 4).astype(U16) << 4)                 # plateaus: every 16th bin
     frames.append((rng.integers(0, 4096, shape)).astype(U16))                    # 12-bit camera data
     frames.append(np.full(shape, 777, U16))                                      # constant: no valid split
@@ -267,33 +263,90 @@ def test_otsu_stack_staged_scan_distributions(backend, rng):
     tail = np.full(shape, 30000, U16); tail[0, :3] = 65535; tail[1, :2] = 0; frames.append(tail)  # q1 ~ eps tails
     frames.append(np.clip(rng.normal(20000, 300, shape), 0, 65535).astype(U16))  # narrow dense peak
     frames.append(np.zeros(shape, U16))
-    frames += [blobs(rng, shape, U16) for _ in range(70 - len(frames))]          # crosses the 64-frame chunk
-    a = np.stack(frames)
+    frames += [blobs(rng, shape, U16) for _ in range(total - len(frames))]
+    return np.stack(frames)
+
+
+def test_otsu_scan_distributions_certified_and_chain(backend, rng):
+    """The device scan (certified parallel arg-max, exact chain kernels for what it cannot certify) returns
+    the reference thresholds for every kind of histogram -- dense, sparse plateaus (12-bit data), constant,
+    two-level, near-empty tails -- and so does the exact chain alone (force_chain)."""
+    a = _otsu_distribution_frames(rng)
     want_t = [O.otsu_value(p) for p in a]
-    backend.lib.yam_set_host_threads(1)  # one host thread: the cost model picks the staged device scan
-    try:
-        t, out = backend.otsu_threshold(dev(backend, a), 255)
-        assert host(backend, t).tolist() == want_t
-        got = host(backend, out)
-    finally:
-        backend.lib.yam_set_host_threads(backend.host_threads)
+    t, out = backend.otsu_threshold(dev(backend, a), 255)
+    assert host(backend, t).tolist() == want_t
+    got = host(backend, out)
     for i in (0, 2, 4, 6, 8, 69):
-        assert_same(got[i], O.threshold_binary(a[i], want_t[i], 255), f"otsu staged frame {i}")
-    # plenty of host threads: the same stack through the pooled host scans
-    backend.lib.yam_set_host_threads(32)
+        assert_same(got[i], O.threshold_binary(a[i], want_t[i], 255), f"otsu frame {i}")
+    old = backend.lib.yam_otsu_set_force_chain(1)
     try:
-        t, _ = backend.otsu_threshold(dev(backend, a), 255)
-        assert host(backend, t).tolist() == want_t
+        t2, _ = backend.otsu_threshold(dev(backend, a), 255)
+        assert host(backend, t2).tolist() == want_t
     finally:
-        backend.lib.yam_set_host_threads(backend.host_threads)
-    # the same frames one by one go through the host scan: both paths agree
+        backend.lib.yam_otsu_set_force_chain(old)
+    # the same frames one by one
     for i in (2, 3, 6):
         t1, _ = backend.otsu_threshold(dev(backend, a[i]), 255)
         assert int(host(backend, t1)[0]) == want_t[i]
 
 
+def test_otsu_certificate_matches_model(backend, rng):
+    """Which frames the certificate decides: equal to the NumPy model of the kernel (tests/otsu_certify_model.py);
+    microscopy-like frames are certified (no sequential scan), sparse / flat histograms fall back to the chain."""
+    import torch
+    from otsu_certify_model import certify
+
+    frames = [synth.nuclei(512, 512, seed=s) for s in (1, 2)]
+    frames += [np.clip(rng.normal(9000, 2500, (512, 512)), 0, 65535).astype(U16)]                 # one broad mode
+    frames += [((rnd(rng, (512, 512), U16) >> 4) << 4).astype(U16)]                              # plateaus -> ties
+    two = np.full((512, 512), 1000, U16); two[::2] = 50000; frames.append(two)                    # two spikes
+    frames.append(np.zeros((512, 512), U16))                                                      # one bin
+    a = np.stack(frames)
+    hist = backend.histogram(dev(backend, a))
+    t, cert = backend.otsu_from_histogram_device(hist, want_certified=True)
+    t, cert = t.cpu().tolist(), cert.cpu().tolist()
+    hh = hist.cpu().numpy()
+    for i in range(len(a)):
+        assert t[i] == O.otsu_value(a[i]), f"frame {i}"
+        m_cert, m_t, _, _ = certify(hh[i])
+        assert bool(cert[i]) == bool(m_cert), f"frame {i}: kernel certified={cert[i]}, model={m_cert}"
+        if m_cert:
+            assert m_t == t[i]
+    assert cert[0] == 1 and cert[1] == 1 and cert[2] == 1     # realistic frames: no sequential scan
+    assert cert[3] == 0 and cert[4] == 0                      # exact ties between empty bins: chain
+    # pixel counts that are not powers of two (the q1 chain rounds: error-band skip decisions)
+    for shape in ((500, 300), (333, 777), (1000, 1000)):
+        img = np.clip(rng.normal(30000, 9000, shape) + 12000 * (rng.random(shape) < 0.2), 0, 65535).astype(U16)
+        h1 = backend.histogram(dev(backend, img))
+        t1, c1 = backend.otsu_from_histogram_device(h1, want_certified=True)
+        m_cert, m_t, _, _ = certify(h1.cpu().numpy()[0])
+        assert int(t1.cpu()[0]) == O.otsu_value(img) and bool(c1.cpu()[0]) == bool(m_cert), shape
+
+
+def test_otsu_from_histogram_device_large_counts(backend, rng):
+    """All-reduced mosaic histograms: counts beyond 2^32 per bin and N = 2^36 pixels."""
+    import torch
+
+    x = np.arange(65536, dtype=np.float64)
+    h = (1.5e7 * np.exp(-0.5 * ((x - 9000) / 900.0) ** 2) + 1.5e6 * np.exp(-0.5 * ((x - 30000) / 4000.0) ** 2)).astype(np.int64)
+    h[9000] += 1 << 33
+    h[12345] += (1 << 36) - int(h.sum())
+    assert h.min() >= 0 and int(h.sum()) == 1 << 36 and int(h.max()) > 1 << 32
+    want = O.otsu_from_hist(h)
+    hd = torch.from_numpy(h).to(backend.device)
+    t, cert = backend.otsu_from_histogram_device(hd, want_certified=True)
+    assert int(t.cpu()[0]) == want
+    old = backend.lib.yam_otsu_set_force_chain(1)
+    try:
+        assert int(backend.otsu_from_histogram_device(hd).cpu()[0]) == want
+    finally:
+        backend.lib.yam_otsu_set_force_chain(old)
+    h8 = rng.integers(0, 5000, 256).astype(np.int64)          # 256 bins: one device thread per frame
+    assert int(backend.otsu_from_histogram_device(torch.from_numpy(h8).to(backend.device)).cpu()[0]) == O.otsu_from_hist(h8)
+
+
 def test_otsu_begin_finish(backend, rng):
-    """The two-step Otsu (scan overlapped with other work) equals the one-shot operator."""
+    """The two-step Otsu equals the one-shot operator."""
     for a in (blobs(rng, (130, 257), U16), np.stack([blobs(rng, (48, 64), U16) for _ in range(5)]),
               blobs(rng, (64, 80), U8), np.stack([blobs(rng, (48, 64), U16) for _ in range(12)])):
         x = dev(backend, a)

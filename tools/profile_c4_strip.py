@@ -1,0 +1,23 @@
+"""One launch of every c4 operator on one 8192-row x 65536-px strip (for `ncu --set full`; no timing here)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from yamimageprocessor_b200 import synth
+from yamimageprocessor_b200.backend import get_backend
+
+be = get_backend(0)
+rows, W = int(os.environ.get("ROWS", 8192)), int(os.environ.get("COLS", 65536))
+tile = synth.nuclei(4096, 4096, seed=100)
+x = be.to_device(np.tile(tile, (rows // 4096, W // 4096)))
+g = be.gaussian(x, 11, 0.0)
+luts = be.clahe_luts(g, 2.0, (8, 1))
+c = be.clahe_apply(g, luts, (W // 8, rows), 0)
+hist = be.histogram(c)
+m = be.threshold(c, 30000.0, 255)
+bits = be.adaptive_threshold_bits(c, 11, 2)
+bits2 = be.bits_morph(bits, W, 4, 5, 1)
+ws, cnt = be.ccl_resolve_bits(bits2, W)
+lab = be.ccl_emit(bits2, W, ws)
+torch.cuda.synchronize()
+print("done", int(cnt.item()) if hasattr(cnt, "item") else cnt)

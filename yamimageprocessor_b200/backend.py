@@ -371,44 +371,43 @@ class Backend:
         return t, out
 
     def otsu_begin(self, img):
-        """First half of ``otsu_threshold`` for schedules that have other GPU work to enqueue before
-        the thresholds are needed (the fp64 Otsu recurrence is sequential; on the host it can overlap
-        that work).  Returns a handle for ``otsu_finish``."""
+        """First half of ``otsu_threshold`` (histogram + scan, thresholds stay on the device).  The whole
+        operator is asynchronous since the scan moved to the device, so this simply enqueues it; the
+        two-step form is kept for schedules written against it.  Returns a handle for ``otsu_finish``."""
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8, torch.uint16))
-        n, h, w = self._nhw(img)
-        if img.dtype == torch.uint8 or self.lib.yam_otsu_prefers_device(n):
-            # 256-bin and staged device scans are asynchronous already: run the whole operator now
-            t, _ = self.otsu_threshold(img, want_image=False)
-            return {"img": img, "t": t}
-        hist = self.histogram(img)
-        host = torch.empty(hist.shape, dtype=hist.dtype, pin_memory=True)
-        host.copy_(hist, non_blocking=True)
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
-        return {"img": img, "hist_host": host, "ready": ready}
+        t, _ = self.otsu_threshold(img, want_image=False)
+        return {"img": img, "t": t}
 
     def otsu_finish(self, handle, maxval: float = 255.0, want_image: bool = True):
         """Second half: (thresholds int32[n] on device, thresholded image or None)."""
+        t = handle["t"]
+        return t, (self.threshold_frames(handle["img"], t, maxval) if want_image else None)
+
+    def threshold_frames(self, img, t_dev, maxval: float = 255.0):
+        """dst = src > t_dev[frame] ? maxval : 0 per frame, thresholds int32[n] on the device."""
         torch = _torch()
-        img = handle["img"]
+        img = self._check(img, dtypes=(torch.uint8, torch.uint16))
         n, h, w = self._nhw(img)
-        t = handle.get("t")
-        if t is None:
-            handle["ready"].synchronize()
-            hists = handle["hist_host"].numpy()
-            t_pinned = torch.empty((n,), dtype=torch.int32, pin_memory=True)
-            t_host = t_pinned.numpy()
-            _lib.check("yam_otsu_from_hists", self.lib.yam_otsu_from_hists(
-                hists.ctypes.data_as(C.c_void_p), int(hists.shape[-1]), n, t_host.ctypes.data_as(C.c_void_p)))
-            t = t_pinned.to(self.device, non_blocking=True)   # no stream drain: the GPU keeps its queue
-            t._yam_host_ref = t_pinned  # type: ignore[attr-defined]
-        out = None
-        if want_image:
-            out = torch.empty_like(img)
-            self._call("yam_threshold_frames", self._p(img), self._p(out), n, h, w, _dtype_code(img), self._p(t),
-                       float(maxval))
-        return t, out
+        out = torch.empty_like(img)
+        self._call("yam_threshold_frames", self._p(img), self._p(out), n, h, w, _dtype_code(img), self._p(t_dev),
+                   float(maxval))
+        return out
+
+    def otsu_from_histogram_device(self, hist, want_certified: bool = False):
+        """Otsu thresholds (int32[n], device) of histograms that are already on the device: int64 / uint64
+        counts, shape (bins,) or (n, bins), bins = 256 | 65536 (e.g. an all-reduced mosaic histogram).
+        ``want_certified``: also return int32[n] = 1 where the parallel certificate decided the frame."""
+        torch = _torch()
+        if not isinstance(hist, torch.Tensor) or hist.device != self.device or hist.dtype not in (torch.int64, torch.uint64):
+            raise TypeError("otsu_from_histogram_device expects an int64 CUDA tensor on this backend's device")
+        hist = hist.contiguous()
+        bins = int(hist.shape[-1])
+        n = int(hist.numel() // bins)
+        t = torch.empty((n,), dtype=torch.int32, device=self.device)
+        cert = torch.empty((n,), dtype=torch.int32, device=self.device) if want_certified else None
+        self._call("yam_otsu_from_hist_dev", self._p(hist), bins, n, self._p(t), self._p(cert) if cert is not None else None)
+        return (t, cert) if want_certified else t
 
     def equalize_hist(self, img):
         torch = _torch()

@@ -13,6 +13,7 @@
 // Otsu's fp64 recurrence over the 65536 bins is sequential per frame: single frames are scanned on
 // a host thread (0.47 ms), stacks on a pool of host threads (up to 4 frames in lock step per
 // thread) or, when this rank has few host threads, by the staged device scan below.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include <atomic>
@@ -208,7 +209,9 @@ __global__ void otsu_scan_kernel(const unsigned long long* __restrict__ hist, in
 // result is the reference's by construction, whatever the corrected quotient did.
 struct OtsuMeta {
     double scale, mu;
-    int first, last;  // occupied bin range; first < 0: empty frame
+    int first, last;  // occupied bin range the chain has to cover; first < 0: empty frame
+    int certified;    // 1: otsu_certify_kernel proved the threshold, the chain / sigma kernels skip this frame
+    int pad;
 };
 constexpr double kOtsuEps = 1.1920928955078125e-07;  // FLT_EPSILON
 
@@ -253,6 +256,8 @@ __global__ void __launch_bounds__(1024) otsu_prep_kernel(const unsigned long lon
             m.last = last;
             m.scale = last < 0 ? 0.0 : __ddiv_rn(1.0, (double)tot);
             m.mu = __dmul_rn((double)mom, m.scale);
+            m.certified = 0;
+            m.pad = 0;
             meta[blockIdx.x] = m;
         }
     }
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
     __shared__ double s_pn[kOtsuTile], s_qn[kOtsuTile];                     // next tile: p in, q1 out
     __shared__ double s_q[kOtsuTile], s_r[kOtsuTile], s_ip[kOtsuTile], s_m[kOtsuTile];  // current tile
     const OtsuMeta m = meta[blockIdx.x];
-    if (m.first < 0) return;
+    if (m.first < 0 || m.certified) return;
     const int64_t base = (int64_t)blockIdx.x * bins;
     const unsigned long long* h = hist + base;
     const int lane = threadIdx.x;
@@ -401,6 +406,7 @@ __global__ void __launch_bounds__(1024) otsu_sigma_kernel(const unsigned long lo
     __shared__ int s_idx[32];
     __shared__ int s_fail;
     const OtsuMeta m = meta[blockIdx.x];
+    if (m.certified) return;  // out[] already holds the proven threshold
     if (m.first < 0) {
         if (threadIdx.x == 0) out[blockIdx.x] = 0;
         return;
@@ -471,6 +477,357 @@ __global__ void __launch_bounds__(1024) otsu_sigma_kernel(const unsigned long lo
             out[blockIdx.x] = best_i;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Certified parallel Otsu.  The reference's recurrence (above) is sequential, but its RESULT is an
+// argmax, and the value it maximises is known in closed form from exact integer prefix sums:
+//     C_i = sum_{j<=i} h_j,  S'_i = sum_{f<=j<=i} j h_j      (f = first bin the recurrence evaluates; the
+//     first moments of the bins it skips in front are dropped by its `mu1 *= q1; continue`)
+//     sigma_i = q1 q2 (mu1 - mu2)^2,  q1 = C_i/N, q2 = 1 - q1, mu1 = S'_i/C_i, mu2 = (S_T - S'_i)/(N - C_i).
+// A forward error analysis of the recurrence bounds how far its fp64 value can be from that:
+//     q1^ = q1 (1 + th),  |th| <= (i - first + 3) u        (one rounding per addition; exact when N = 2^k)
+//     (mu1 q1)^ = (S'_i/N)(1 + th), |th| <= (3 (i - f) + 5) u   (three roundings per bin, all terms >= 0)
+// and the remaining operations (mu2's cancellation, q2, the difference, the products) propagate as
+// interval bounds e_num, e_q2, e_mu2, e_d below (u = 2^-53, every bound inflated by 1 % and a few u to
+// cover second-order terms and the rounding of the bound's own evaluation).  Each bin gets
+// sigma_lo <= sigma^ <= sigma_up.  If one bin's sigma_lo exceeds every other bin's sigma_up, that bin IS
+// the reference's threshold, whatever the roundings were: the frame is "certified" and the sequential
+// scan is skipped.  Otherwise (ties between empty bins, flat maxima, > 2^53 moments, a skip decision
+// inside its error band) the exact chain kernels run, and only up to the last bin that could still
+// win (kmax).  Either way the threshold is the reference's; tests/test_gpu_ops.py sweeps both outcomes
+// and tests/test_otsu_certify.py holds the NumPy model of this kernel against the sequential scan.
+// One 8-CTA cluster per frame: 8 bins per thread, prefix sums and reductions exchanged through
+// distributed shared memory.
+namespace cg = cooperative_groups;
+constexpr int kCertCluster = 8, kCertThreads = 1024, kCertPer = 8;
+static_assert(kCertCluster * kCertThreads * kCertPer == kBins16, "one thread per 8 bins");
+constexpr double kU = 1.1102230246251565e-16;  // 2^-53
+constexpr double kInfl = 1.01;
+
+struct CertShared {
+    unsigned long long cnt, mom;   // totals of this CTA's bins
+    int first, last;               // occupied bins of this CTA (INT_MAX / -1 when none)
+    int f, amb;                    // first bin certainly evaluated, first ambiguous bin (INT_MAX when none)
+    unsigned long long s_excl_f;   // first moment of all bins before f (valid in the CTA that owns f)
+    double best_lo;
+    int best_i;
+    int ncand, kmax;
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ T cert_block_reduce(T v, T* s_tmp, Op op, T identity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();               // s_tmp may still be read from the previous reduction
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    v = lane < (kCertThreads >> 5) ? s_tmp[lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;                      // every thread holds the block result
+}
+
+__global__ void __cluster_dims__(kCertCluster, 1, 1) __launch_bounds__(kCertThreads, 1)
+otsu_certify_kernel(const unsigned long long* __restrict__ hist, OtsuMeta* __restrict__ meta, int32_t* __restrict__ out,
+                    int32_t* __restrict__ certified_out, int force_chain) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ CertShared sh;
+    __shared__ unsigned long long s_w0[32], s_w1[32];
+    __shared__ double s_d[32];
+    __shared__ int s_i[32];
+    const int frame = blockIdx.y, rank = (int)cluster.block_rank(), tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned long long* h = hist + (int64_t)frame * kBins16;
+    const int bin0 = (rank * kCertThreads + tid) * kCertPer;
+
+    // ---- exact prefix sums of counts and first moments
+    unsigned long long c[kCertPer];
+    {
+        const ulonglong2* hv = reinterpret_cast<const ulonglong2*>(h + bin0);
+#pragma unroll
+        for (int k = 0; k < kCertPer / 2; k++) {
+            const ulonglong2 v = hv[k];
+            c[2 * k] = v.x;
+            c[2 * k + 1] = v.y;
+        }
+    }
+    unsigned long long tc = 0, tm = 0;
+    int nzf = 0x7fffffff, nzl = -1;
+#pragma unroll
+    for (int k = 0; k < kCertPer; k++) {
+        tc += c[k];
+        tm += c[k] * (unsigned long long)(bin0 + k);
+        if (c[k]) {
+            nzf = min(nzf, bin0 + k);
+            nzl = bin0 + k;
+        }
+    }
+    unsigned long long ic = tc, im = tm;  // inclusive scan over the CTA's threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, im, o);
+        if (lane >= o) {
+            ic += a;
+            im += b;
+        }
+    }
+    if (lane == 31) {
+        s_w0[warp] = ic;
+        s_w1[warp] = im;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long a = s_w0[lane], b = s_w1[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) {
+                a += x;
+                b += y;
+            }
+        }
+        s_w0[lane] = a;
+        s_w1[lane] = b;
+    }
+    __syncthreads();
+    unsigned long long ec = ic - tc + (warp ? s_w0[warp - 1] : 0ull);  // exclusive, within the CTA
+    unsigned long long em = im - tm + (warp ? s_w1[warp - 1] : 0ull);
+    const int cta_first = cert_block_reduce<int>(nzf, s_i, [](int a, int b) { return min(a, b); }, 0x7fffffff);
+    const int cta_last = cert_block_reduce<int>(nzl, s_i, [](int a, int b) { return max(a, b); }, -1);
+    if (tid == 0) {
+        sh.cnt = s_w0[31];
+        sh.mom = s_w1[31];
+        sh.first = cta_first;
+        sh.last = cta_last;
+    }
+    cluster.sync();                                                     // (1) CTA totals visible
+    unsigned long long N = 0, ST = 0;
+    int first = 0x7fffffff, last = -1;
+#pragma unroll
+    for (int r = 0; r < kCertCluster; r++) {
+        const CertShared* p = cluster.map_shared_rank(&sh, r);
+        const unsigned long long rc = p->cnt, rm = p->mom;
+        if (r < rank) {
+            ec += rc;
+            em += rm;
+        }
+        N += rc;
+        ST += rm;
+        first = min(first, p->first);
+        last = max(last, p->last);
+    }
+    OtsuMeta m;
+    m.first = last < 0 ? -1 : first;
+    m.last = last;
+    m.scale = last < 0 ? 0.0 : __ddiv_rn(1.0, (double)N);
+    m.mu = __dmul_rn((double)ST, m.scale);
+    m.certified = 0;
+    m.pad = 0;
+    const bool leader = rank == 0 && tid == 0;
+    if (last < 0 || ST >= (1ull << 53) || force_chain) {   // empty frame: t = 0;  moments beyond 2^53: exact chain
+        if (leader) {
+            m.certified = last < 0 ? 1 : 0;
+            meta[frame] = m;
+            if (last < 0) out[frame] = 0;
+            if (certified_out) certified_out[frame] = m.certified;
+        }
+        cluster.sync();
+        return;
+    }
+
+    // ---- which bins does the recurrence evaluate?  skip <=> q1^ < eps or q1^ > 1 - eps
+    const bool pow2 = (N & (N - 1)) == 0;
+    const double Nf = (double)N, slop = 4.0 * kU;
+    unsigned nonc_mask = 0, amb_mask = 0;
+    double q1v[kCertPer];
+    {
+        unsigned long long C = ec;
+#pragma unroll
+        for (int k = 0; k < kCertPer; k++) {
+            C += c[k];
+            const int i = bin0 + k;
+            const double q1 = (double)C / Nf;
+            q1v[k] = q1;
+            const double rq = pow2 ? 0.0 : ((double)max(i - first + 1, 0) + 2.0) * kU * kInfl;
+            bool sf, st, nonc;
+            if (pow2) {                          // the q1 chain is exact (multiples of 1/N): so are the decisions
+                sf = q1 < kOtsuEps;
+                st = q1 > 1.0 - kOtsuEps;
+                nonc = !(sf || st);
+            } else {
+                sf = q1 * (1.0 + rq + slop) < kOtsuEps;
+                st = q1 * (1.0 - rq - slop) > 1.0 - kOtsuEps;
+                nonc = q1 * (1.0 - rq - slop) >= kOtsuEps * (1.0 + slop) && q1 * (1.0 + rq + slop) <= (1.0 - kOtsuEps) * (1.0 - slop);
+            }
+            const bool live = i >= first;
+            if (nonc && live) nonc_mask |= 1u << k;
+            if (!(sf || st || nonc) && live) amb_mask |= 1u << k;
+        }
+    }
+    const int my_f = nonc_mask ? bin0 + __ffs(nonc_mask) - 1 : 0x7fffffff;
+    const int my_amb = amb_mask ? bin0 + __ffs(amb_mask) - 1 : 0x7fffffff;
+    const int cta_f = cert_block_reduce<int>(my_f, s_i, [](int a, int b) { return min(a, b); }, 0x7fffffff);
+    const int cta_amb = cert_block_reduce<int>(my_amb, s_i, [](int a, int b) { return min(a, b); }, 0x7fffffff);
+    if (my_f == cta_f && my_f != 0x7fffffff) {   // the thread that owns the CTA's first evaluated bin
+        unsigned long long sx = em;
+        for (int k = 0; k < my_f - bin0; k++) sx += c[k] * (unsigned long long)(bin0 + k);
+        sh.s_excl_f = sx;
+    }
+    if (tid == 0) {
+        sh.f = cta_f;
+        sh.amb = cta_amb;
+    }
+    cluster.sync();                                                     // (2) f, ambiguity, S before f
+    int f = 0x7fffffff, amb0 = 0x7fffffff;
+    unsigned long long S0 = 0;
+#pragma unroll
+    for (int r = 0; r < kCertCluster; r++) {
+        const CertShared* p = cluster.map_shared_rank(&sh, r);
+        const int rf = p->f;
+        if (rf < f) {
+            f = rf;
+            S0 = p->s_excl_f;
+        }
+        amb0 = min(amb0, p->amb);
+    }
+    if (f == 0x7fffffff || amb0 < f) {
+        // nothing certainly evaluated: the reference returns 0 unless an ambiguous bin might count;
+        // an ambiguous bin in front of f leaves f itself unknown -> exact chain
+        if (leader) {
+            m.certified = (f == 0x7fffffff && amb0 == 0x7fffffff) ? 1 : 0;
+            meta[frame] = m;
+            if (m.certified) out[frame] = 0;
+            if (certified_out) certified_out[frame] = m.certified;
+        }
+        cluster.sync();
+        return;
+    }
+
+    // ---- interval for the recurrence's sigma at every bin it may evaluate
+    double up[kCertPer];
+    double my_lo = 0.0;
+    int my_i = 0x7fffffff;
+    {
+        const double mu_star = (double)ST / Nf;
+        unsigned long long C = ec, S = em;
+#pragma unroll
+        for (int k = 0; k < kCertPer; k++) {
+            C += c[k];
+            S += c[k] * (unsigned long long)(bin0 + k);
+            const int i = bin0 + k;
+            const bool nonc = (nonc_mask >> k) & 1u, cand = (nonc || ((amb_mask >> k) & 1u)) && i >= f && i <= last;
+            up[k] = -1.0;
+            if (!cand) continue;
+            const double q1 = q1v[k], q2 = (double)(N - C) / Nf;
+            const double rq = pow2 ? 0.0 : ((double)max(i - first + 1, 0) + 2.0) * kU * kInfl;
+            const double rT = (3.0 * (double)(i - f) + 5.0) * kU * kInfl;
+            const unsigned long long Sp = S - S0, rest = ST - Sp;
+            const double B = (double)Sp / Nf, mu1 = (double)Sp / (double)C;
+            const double num = (double)rest / Nf, mu2 = (double)rest / (double)(N - C);
+            const double e_m1 = mu1 * ((rT + rq) * kInfl + 2.0 * kU);
+            const double e_num = (mu_star * 3.0 * kU + B * (rT + kU) + kU * (num + mu_star)) * kInfl + 4.0 * kU * mu_star;
+            const double e_q2 = (q1 * rq + kU * q2) * kInfl + 2.0 * kU * q2;
+            const double den = q2 - e_q2;
+            const double e_mu2 = den > 0.0 ? (num + e_num) / den * (1.0 + 4.0 * kU) - mu2 * (1.0 - 4.0 * kU) : INFINITY;
+            const double d = fabs(mu1 - mu2);
+            const double e_d = (e_m1 + e_mu2) * (1.0 + 4.0 * kU) + 4.0 * kU * (fabs(mu1) + fabs(mu2));
+            double u_ = q1 * (1.0 + rq) * (q2 + e_q2) * (d + e_d) * (d + e_d) * (1.0 + 16.0 * kU);
+            double l_ = q1 * (1.0 - rq) * fmax(q2 - e_q2, 0.0) * fmax(d - e_d, 0.0) * fmax(d - e_d, 0.0) * (1.0 - 16.0 * kU);
+            if (u_ != u_) u_ = INFINITY;
+            if (l_ != l_ || !nonc) l_ = 0.0;
+            up[k] = u_;
+            if (l_ > my_lo) {            // ascending i: strict '>' keeps the first maximum
+                my_lo = l_;
+                my_i = i;
+            }
+        }
+    }
+    // (lo, index) arg-max: larger lo wins, equal lo -> smaller index
+    {
+        double b = my_lo;
+        int bi = my_i;
+        auto better = [](double ob, int oi, double b, int bi) { return ob > b || (ob == b && oi < bi); };
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ob, oi, b, bi)) {
+                b = ob;
+                bi = oi;
+            }
+        }
+        __syncthreads();
+        if (lane == 0) {
+            s_d[warp] = b;
+            s_i[warp] = bi;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            b = s_d[lane];
+            bi = s_i[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(ob, oi, b, bi)) {
+                    b = ob;
+                    bi = oi;
+                }
+            }
+            if (lane == 0) {
+                sh.best_lo = b;
+                sh.best_i = bi;
+            }
+        }
+    }
+    cluster.sync();                                                     // (3) per-CTA best lower bounds
+    double Lmax = 0.0;
+    int istar = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < kCertCluster; r++) {
+        const CertShared* p = cluster.map_shared_rank(&sh, r);
+        const double ob = p->best_lo;
+        const int oi = p->best_i;
+        if (ob > Lmax || (ob == Lmax && oi < istar)) {
+            Lmax = ob;
+            istar = oi;
+        }
+    }
+    int ncand = 0, kmax = -1;
+    if (Lmax > 0.0) {
+#pragma unroll
+        for (int k = 0; k < kCertPer; k++)
+            if (up[k] >= Lmax && bin0 + k != istar) {
+                ncand++;
+                kmax = bin0 + k;
+            }
+    }
+    const int cta_n = cert_block_reduce<int>(ncand, s_i, [](int a, int b) { return a + b; }, 0);
+    const int cta_k = cert_block_reduce<int>(kmax, s_i, [](int a, int b) { return max(a, b); }, -1);
+    if (tid == 0) {
+        sh.ncand = cta_n;
+        sh.kmax = cta_k;
+    }
+    cluster.sync();                                                     // (4) competitor counts
+    if (leader) {
+        int n = 0, km = -1;
+        for (int r = 0; r < kCertCluster; r++) {
+            const CertShared* p = cluster.map_shared_rank(&sh, r);
+            n += p->ncand;
+            km = max(km, p->kmax);
+        }
+        if (Lmax > 0.0 && n == 0) {
+            m.certified = 1;
+            out[frame] = istar;
+        } else if (Lmax > 0.0) {
+            m.last = max(km, istar);     // no bin beyond the last competitor can win: the chain stops there
+        }
+        meta[frame] = m;
+        if (certified_out) certified_out[frame] = m.certified;
+    }
+    cluster.sync();                                                     // (5) peers' shared memory read
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1241,25 +1598,12 @@ int yam_set_host_threads(int threads) {
     return host_threads();
 }
 
-// cost model shared by yam_otsu_threshold and yam_otsu_prefers_device (measured on B200 boxes):
-// 0.45 ms per frame and host thread + 12 us read-back per frame on the host, 2.75 ms per launch
-// group of <= kStageChunk frames on the device
-static constexpr int64_t kDeviceScanFrames = 8, kStageChunk = 256;
-static bool otsu_scan_on_device(int64_t n) {
-    const int64_t ht = host_threads();
-    const double host_ms = (double)((n + ht - 1) / ht) * 0.45 + (double)n * 0.012;
-    const double dev_ms = (double)((n + kStageChunk - 1) / kStageChunk) * 2.75;
-    return n >= kDeviceScanFrames && dev_ms < host_ms;
-}
-
 // frames one pool task scans in lock step: 1 while there are idle threads, up to 4 beyond that
 static int64_t otsu_group_size(int64_t frames) {
     const int64_t ht = host_threads();
     int64_t g = (frames + ht - 1) / ht;
     return g < 1 ? 1 : (g > 4 ? 4 : g);
 }
-
-int yam_otsu_prefers_device(int64_t n) { return otsu_scan_on_device(n) ? 1 : 0; }
 
 int yam_otsu_from_hists(const uint64_t* hists, int bins, int64_t n, int32_t* out_thresholds) {
     YAM_REQUIRE(hists && out_thresholds && bins > 0 && n > 0, "yam_otsu_from_hists: bad arguments");
@@ -1295,6 +1639,58 @@ int yam_histogram(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w
     return hist_into(ctx, src, n, h, w, dtype, (unsigned long long*)hist_dev);
 }
 
+// Thresholds of n histograms that already sit in device memory, enqueued on ctx->stream with no host
+// synchronisation: 65536 bins -> certified parallel scan, exact chain kernels for the frames it could
+// not certify (they exit at once for the others); 256 bins -> one device thread per frame.
+// `stage` = otsu_stage_bytes(n) bytes of scratch.
+static constexpr int64_t kStageChunk = 256;
+static size_t otsu_stage_bytes(int64_t n, int bins) {
+    if (bins != kBins16) return 0;
+    const int64_t nf_max = n < kStageChunk ? n : kStageChunk;
+    return 2 * yam_align_up(sizeof(double) * bins * nf_max, 256) + yam_align_up(sizeof(OtsuMeta) * nf_max, 256) + 256;
+}
+static std::atomic<int> g_otsu_force_chain{0};
+static int otsu_scan_device(yam_ctx* ctx, const unsigned long long* hist, int bins, int64_t n, int32_t* t_dev, void* stage,
+                            int32_t* certified_dev = nullptr) {
+    if (bins != kBins16) {
+        if (certified_dev) YAM_CUDA(cudaMemsetAsync(certified_dev, 0, sizeof(int32_t) * n, ctx->stream));
+        otsu_scan_kernel<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(hist, bins, n, t_dev);
+        YAM_LAUNCHED(ctx);
+        return YAM_OK;
+    }
+    const int64_t nf_max = n < kStageChunk ? n : kStageChunk;
+    const size_t arr_bytes = yam_align_up(sizeof(double) * bins * nf_max, 256);
+    char* sp = (char*)stage;
+    double* q1arr = (double*)sp; sp += arr_bytes;
+    double* mu1arr = (double*)sp; sp += arr_bytes;
+    OtsuMeta* meta = (OtsuMeta*)sp; sp += yam_align_up(sizeof(OtsuMeta) * nf_max, 256);
+    int* redo = (int*)sp;
+    YAM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
+    for (int64_t f0 = 0; f0 < n; f0 += kStageChunk) {
+        const unsigned nf = (unsigned)((n - f0) < kStageChunk ? (n - f0) : kStageChunk);
+        const unsigned long long* hc = hist + f0 * bins;
+        otsu_certify_kernel<<<dim3(kCertCluster, nf), kCertThreads, 0, ctx->stream>>>(hc, meta, t_dev + f0, certified_dev ? certified_dev + f0 : nullptr,
+                                                                                      g_otsu_force_chain.load());
+        YAM_LAUNCHED(ctx);
+        otsu_chain_kernel<<<nf, 32, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr);
+        YAM_LAUNCHED(ctx);
+        otsu_sigma_kernel<<<nf, 1024, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr, t_dev + f0, redo);
+        YAM_LAUNCHED(ctx);
+    }
+    return YAM_OK;
+}
+
+int yam_otsu_set_force_chain(int on) { return g_otsu_force_chain.exchange(on ? 1 : 0); }
+
+int yam_otsu_from_hist_dev(yam_ctx* ctx, const uint64_t* hist_dev, int bins, int64_t n, int32_t* thresh_dev,
+                           int32_t* certified_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(hist_dev && thresh_dev && n > 0 && n <= 65535 && (bins == 256 || bins == kBins16), "otsu_from_hist_dev: bad arguments");
+    void* stage = nullptr;
+    if (int rc = yam_scratch(ctx, otsu_stage_bytes(n, bins) + 256, &stage)) return rc;
+    return otsu_scan_device(ctx, (const unsigned long long*)hist_dev, bins, n, thresh_dev, stage, certified_dev);
+}
+
 int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int dtype,
                        double maxval, int32_t* thresh_dev, int32_t* thresh_host) {
     if (int rc = yam_enter(ctx)) return rc;
@@ -1303,118 +1699,19 @@ int yam_otsu_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, int6
     YAM_REQUIRE(h < (1 << 30) && w < (1 << 30), "otsu: image side too large");
     const int bins = dtype == YAM_U8 ? 256 : kBins16;
     const size_t hist_bytes = sizeof(unsigned long long) * bins * n;
-    // 16-bit stacks: staged scan on the device (~2.75 ms for any number of frames up to kStageChunk, no
-    // read-back, nothing for the host cores to fight over when 8 ranks share a box) when that beats
-    // this process's share of the host cores.
-    // Fewer frames: the fp64 recurrence is sequential per frame, 65536 dependent divisions take
-    // ~0.4 ms on a CPU core, so the histograms are read back and scanned on host threads.
-    // 256-bin histograms are scanned by one device thread per frame.
-    const bool staged_scan = (dtype == YAM_U16) && otsu_scan_on_device(n);
-    const bool host_scan = (dtype == YAM_U16) && !staged_scan;
-    const int64_t nf_max = n < kStageChunk ? n : kStageChunk;
-    const size_t arr_bytes = yam_align_up(sizeof(double) * bins * nf_max, 256);
-    const size_t hist_block = yam_align_up(yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256) +
-                                               sizeof(uint32_t) * bins * n, 256);
-    const size_t stage_block = staged_scan ? 2 * arr_bytes + yam_align_up(sizeof(OtsuMeta) * nf_max, 256) + 256 : 0;
+    // histogram -> scan -> threshold, all on the stream: nothing is read back and the host does not wait
+    // (the round-1/2 schedule read the histograms back and ran the sequential fp64 recurrence on host threads)
+    const size_t hist_block = yam_align_up(yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256), 256);
     void* scratch = nullptr;
-    if (int rc = yam_scratch(ctx, hist_block + stage_block, &scratch)) return rc;
+    if (int rc = yam_scratch(ctx, hist_block + otsu_stage_bytes(n, bins) + 256, &scratch)) return rc;
     unsigned long long* hist = (unsigned long long*)scratch;
     int32_t* t_dev = thresh_dev ? thresh_dev : (int32_t*)((char*)scratch + yam_align_up(hist_bytes, 256));
     if (int rc = hist_into(ctx, src, n, h, w, dtype, hist)) return rc;
-    if (staged_scan) {
-        const int64_t chunk = kStageChunk;
-        char* sp = (char*)scratch + hist_block;
-        double* q1arr = (double*)sp; sp += arr_bytes;
-        double* mu1arr = (double*)sp; sp += arr_bytes;
-        OtsuMeta* meta = (OtsuMeta*)sp; sp += yam_align_up(sizeof(OtsuMeta) * nf_max, 256);
-        int* redo = (int*)sp;
-        YAM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
-        for (int64_t f0 = 0; f0 < n; f0 += chunk) {
-            const unsigned nf = (unsigned)((n - f0) < chunk ? (n - f0) : chunk);
-            const unsigned long long* hc = hist + f0 * bins;
-            otsu_prep_kernel<<<nf, 1024, 0, ctx->stream>>>(hc, bins, meta);
-            YAM_LAUNCHED(ctx);
-            otsu_chain_kernel<<<nf, 32, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr);
-            YAM_LAUNCHED(ctx);
-            otsu_sigma_kernel<<<nf, 1024, 0, ctx->stream>>>(hc, bins, meta, q1arr, mu1arr, t_dev + f0, redo);
-            YAM_LAUNCHED(ctx);
-        }
-    } else if (host_scan) {
-        // Read-back in chunks of <= 64 frames through a pinned buffer, 8 frames per copy; each copy is
-        // followed by an event, and the frames of a copy are handed to the worker pool as soon as
-        // its event fires, so the scans overlap the remaining copies.
-        const int64_t chunk = 64, sub = 8;
-        const bool narrow = (h * w) < (1ll << 32);
-        const size_t count_bytes = narrow ? sizeof(uint32_t) : sizeof(unsigned long long);
-        const int64_t first = n < chunk ? n : chunk;
-        void* pinned = nullptr;
-        if (int rc = yam_pinned(ctx, (size_t)first * (count_bytes * bins + sizeof(int32_t)), &pinned)) return rc;
-        int32_t* t_stage = (int32_t*)((char*)pinned + (size_t)first * count_bytes * bins);
-        uint32_t* narrow_dev = nullptr;
-        if (narrow) {
-            // the 32-bit copy lives behind the thresholds in the scratch block requested above
-            narrow_dev = (uint32_t*)((char*)scratch + yam_align_up(hist_bytes, 256) + yam_align_up(sizeof(int32_t) * n, 256));
-            const int64_t cells = (int64_t)bins * n;
-            hist_narrow_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(hist, narrow_dev, cells);
-            YAM_LAUNCHED(ctx);
-        }
-        cudaEvent_t ev[8];
-        int nev = 0;
-        for (int64_t f0 = 0; f0 < n; f0 += chunk) {
-            const int64_t nf = (n - f0) < chunk ? (n - f0) : chunk;
-            const int subs = (int)((nf + sub - 1) / sub);
-            for (int k = 0; k < subs; k++) {
-                const int64_t s0 = k * sub, sn = (nf - s0) < sub ? (nf - s0) : sub;
-                const char* srcp = narrow ? (const char*)(narrow_dev + (f0 + s0) * bins) : (const char*)(hist + (f0 + s0) * bins);
-                YAM_CUDA(cudaMemcpyAsync((char*)pinned + (size_t)s0 * count_bytes * bins, srcp, (size_t)sn * count_bytes * bins,
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-                if (k >= nev) {
-                    YAM_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-                    nev = k + 1;
-                }
-                YAM_CUDA(cudaEventRecord(ev[k], ctx->stream));
-            }
-            ScanPool& pool = ScanPool::instance();
-            cudaError_t ev_err = cudaSuccess;
-            for (int k = 0; k < subs; k++) {
-                const int64_t s0 = k * sub, sn = (nf - s0) < sub ? (nf - s0) : sub;
-                if (ev_err == cudaSuccess) ev_err = cudaEventSynchronize(ev[k]);
-                if (ev_err != cudaSuccess) break;
-                // frames per task: enough tasks for every host thread, then up to 4 frames in lock step
-                const int64_t group = otsu_group_size(nf);
-                for (int64_t f = s0; f < s0 + sn; f += group) {
-                    const int cnt = (int)((s0 + sn - f) < group ? (s0 + sn - f) : group);
-                    const char* hp = (const char*)pinned + (size_t)f * count_bytes * bins;
-                    int32_t* outp = t_stage + f;
-                    const size_t stride = count_bytes * bins;
-                    if (nf == 1) {
-                        yam_host_otsu_group(hp, stride, 1, bins, narrow ? 1 : 0, outp);
-                    } else {
-                        pool.submit([hp, outp, bins, narrow, cnt, stride] {
-                            yam_host_otsu_group(hp, stride, cnt, bins, narrow ? 1 : 0, outp);
-                        });
-                    }
-                }
-            }
-            pool.wait_all();
-            if (ev_err != cudaSuccess) {
-                for (int k = 0; k < nev; k++) cudaEventDestroy(ev[k]);
-                yam_set_error("otsu: histogram read-back failed: %s", cudaGetErrorString(ev_err));
-                return YAM_ECUDA;
-            }
-            YAM_CUDA(cudaMemcpyAsync(t_dev + f0, t_stage, sizeof(int32_t) * nf, cudaMemcpyHostToDevice, ctx->stream));
-            if (thresh_host) memcpy(thresh_host + f0, t_stage, sizeof(int32_t) * nf);
-            if (f0 + chunk < n) YAM_CUDA(cudaStreamSynchronize(ctx->stream));  // the pinned buffer is reused
-        }
-        for (int k = 0; k < nev; k++) cudaEventDestroy(ev[k]);
-    } else {
-        otsu_scan_kernel<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(hist, bins, n, t_dev);
-        YAM_LAUNCHED(ctx);
-    }
+    if (int rc = otsu_scan_device(ctx, hist, bins, n, t_dev, (char*)scratch + hist_block)) return rc;
     if (dst) {
         if (int rc = yam_threshold_dev(ctx, src, dst, n, h * w, dtype, t_dev, maxval)) return rc;
     }
-    if (thresh_host && !host_scan) {  // staged and 8-bit scans leave the thresholds on the device
+    if (thresh_host) {
         YAM_CUDA(cudaMemcpyAsync(thresh_host, t_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
         YAM_CUDA(cudaStreamSynchronize(ctx->stream));
     }

@@ -266,16 +266,12 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     c_core = c[c0 - a0: c1 - a0]
     mark("clahe")
 
-    # Otsu on the global histogram.  The fp64 scan runs on the host (sequential recurrence); it is
-    # overlapped with the segmentation kernels, which do not depend on it: the (all-reduced)
-    # histogram is read back asynchronously, the segmentation is enqueued, THEN the host scans.
+    # Otsu on the global histogram: all-reduce, then the certified parallel scan on the device (every rank
+    # scans the same histogram and gets the same threshold); nothing is read back, the host does not wait.
     hist = be.histogram(c_core)[0]
     if comm is not None:
         comm.all_reduce(hist, "sum")
-    hist_host = torch.empty(hist.shape, dtype=hist.dtype, pin_memory=True)
-    hist_host.copy_(hist, non_blocking=True)
-    hist_ready = torch.cuda.Event()
-    hist_ready.record()
+    t_dev = be.otsu_from_histogram_device(hist)
 
     # segmentation on the extended rows, cropped to the core
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
@@ -297,11 +293,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         ws_i, cnt_i = be.ccl_resolve_bits(b, W)
         subs.append((b, ws_i, cnt_i))
 
-    def scan():
-        hist_ready.synchronize()
-        return be.otsu_from_histogram(hist_host.numpy())
-
-    t = comm.once(scan) if comm is not None else scan()
     mark("segment")
 
     if comm is not None or k_sub > 1:
@@ -314,12 +305,12 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
             pack[i, 2 * W:2 * W + 1].copy_(cnt_i)
         packed = comm.all_gather(pack).reshape(-1, stride) if comm is not None else pack
         # The host needs the counts only to size the tables.  They are read back asynchronously and the
-        # Otsu threshold kernel is enqueued behind the copy, so the GPU has work while the host waits.
+        # Otsu mask kernel is enqueued behind the copy, so the GPU has work while the host waits.
         cnt_host = torch.empty((int(packed.shape[0]),), dtype=torch.int32, pin_memory=True)
         cnt_host.copy_(packed[:, 2 * W], non_blocking=True)
         cnt_ready = torch.cuda.Event()
         cnt_ready.record()
-        otsu_mask = be.threshold(c_core, float(t), 255)
+        otsu_mask = be.threshold_frames(c_core, t_dev, 255)
         mark("otsu")
         cnt_ready.synchronize()
         offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
@@ -333,11 +324,12 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         for i, (b, ws_i, cnt_i) in enumerate(subs):
             be.ccl_emit(b, W, ws_i, remap=remaps[i], out=labels[i * sub_rows:(i + 1) * sub_rows])
     else:
-        otsu_mask = be.threshold(c_core, float(t), 255)
+        otsu_mask = be.threshold_frames(c_core, t_dev, 255)
         mark("otsu")
         b, ws_i, total_dev = subs[0]
         labels = be.ccl_emit(b, W, ws_i)
     total = int(total_dev[0].item())   # the only wait for the labelling: everything above is enqueued
+    t = int(t_dev[0].item())
     mark("merge")
 
     props = None
