@@ -68,8 +68,9 @@ def certify(h):
     pow2 = (N & (N - 1)) == 0
     Nf = float(N)
     slop = 4 * U
-    q1 = Cc.astype(np.float64) / Nf
-    q2 = (N - Cc).astype(np.float64) / Nf
+    invN = 1.0 / Nf          # x / N as x * (1 / N), like the kernel (exact for N = 2^k, else inside the slack)
+    q1 = Cc.astype(np.float64) * invN
+    q2 = (N - Cc).astype(np.float64) * invN
     rq = np.zeros(n) if pow2 else (np.maximum(idx - first + 1, 0).astype(np.float64) + 2.0) * U * INFL
     if pow2:   # the q1 chain is exact (multiples of 1/N), so are the skip decisions
         skip_front = q1 < EPS
@@ -93,10 +94,10 @@ def certify(h):
     rT = (3.0 * np.maximum(idx - f, 0).astype(np.float64) + 5.0) * U * INFL
     cand = (nonc | amb) & (idx >= f) & (idx <= last)
     with np.errstate(all="ignore"):
-        mu_star = ST / Nf
-        B = Sp_i.astype(np.float64) / Nf
+        mu_star = ST * invN
+        B = Sp_i.astype(np.float64) * invN
         mu1 = Sp_i.astype(np.float64) / Cc.astype(np.float64)
-        num = rest_i.astype(np.float64) / Nf
+        num = rest_i.astype(np.float64) * invN
         mu2 = rest_i.astype(np.float64) / (N - Cc).astype(np.float64)
         e_m1 = mu1 * ((rT + rq) * INFL + 2 * U)
         e_num = (mu_star * 3 * U + B * (rT + U) + U * (num + mu_star)) * INFL + 4 * U * mu_star
@@ -122,7 +123,7 @@ def certify(h):
     # (common mode), and sigma reacts to them almost identically at neighbouring bins
     if comp.any():
         ks = np.nonzero(comp)[0]
-        keep = ~differential_excludes(ks, istar, q1, q2, mu1, mu2, Sp_i.astype(np.float64) / Nf, ST / Nf, rq, rT, nonc, pow2)
+        keep = ~differential_excludes(ks, istar, q1, q2, mu1, mu2, B, mu_star, rq, rT, nonc, pow2)
         comp[ks[~keep]] = False
     nc = int(comp.sum())
     kmax = max(istar, int(np.nonzero(comp)[0][-1])) if nc else istar

@@ -323,6 +323,22 @@ def test_otsu_certificate_matches_model(backend, rng):
         assert int(t1.cpu()[0]) == O.otsu_value(img) and bool(c1.cpu()[0]) == bool(m_cert), shape
 
 
+def test_otsu_certificate_on_bench_frames(backend):
+    """The c5 bench frames after Gaussian + CLAHE: every one is certified (frame 1007 only through the
+    differential test: its runner-up is the neighbouring bin, 5e-10 below), thresholds = the recurrence's."""
+    from otsu_certify_model import certify
+
+    a = np.stack([synth.nuclei(2048, 2048, seed=1000 + i) for i in range(4, 12)])
+    c = backend.clahe(backend.gaussian(dev(backend, a), 11, 0.0), 2.0, (8, 8))
+    hist = backend.histogram(c)
+    t, cert = backend.otsu_from_histogram_device(hist, want_certified=True)
+    hh = hist.cpu().numpy()
+    for i in range(len(a)):
+        m_cert, m_t, _, _ = certify(hh[i])
+        assert m_cert and int(cert[i].item()) == 1, f"frame {1004 + i}"
+        assert int(t[i].item()) == m_t == O.otsu_from_hist(hh[i])
+
+
 def test_otsu_from_histogram_device_large_counts(backend, rng):
     """All-reduced mosaic histograms: counts beyond 2^32 per bin and N = 2^36 pixels."""
     import torch
@@ -392,6 +408,27 @@ def test_clahe_huge_tiles_multi_cta(backend, rng):
     for clip, grid in ((2.0, (1, 2)), (0.0, (2, 1))):
         got = host(backend, backend.clahe(dev(backend, a), clip, grid))
         assert_same(got, O.clahe(a, clip, grid), f"clahe huge tiles {clip} {grid}")
+
+
+def test_clahe_stack_chunks_and_cell_table_path(backend):
+    """Stacks of large frames: LUTs of a chunk of frames in one launch; frames of >= 8 Mpx then interleave
+    their 81-cell table one by one and gather from it -- same output as frame-by-frame, and as the oracle."""
+    import cv2
+
+    big = np.stack([synth.nuclei(2048, 4096, seed=2000 + i) for i in range(3)])       # 8 Mpx frames: cell-table path
+    gb = backend.gaussian(dev(backend, big), 11, 0.0)
+    gotb = host(backend, backend.clahe(gb, 2.0, (8, 8)))
+    gbh = host(backend, gb)
+    for i in range(3):
+        assert_same(gotb[i], cv2.createCLAHE(2.0, (8, 8)).apply(gbh[i]), f"clahe big stack frame {i} vs cv2")
+    a = np.stack([synth.nuclei(2048, 2048, seed=1000 + i) for i in range(10)])        # crosses the 8-frame chunk
+    g = backend.gaussian(dev(backend, a), 11, 0.0)
+    got = host(backend, backend.clahe(g, 2.0, (8, 8)))
+    gh = host(backend, g)
+    for i in (0, 7, 8, 9):
+        assert_same(got[i], host(backend, backend.clahe(dev(backend, gh[i]), 2.0, (8, 8))), f"clahe stack frame {i} vs single")
+    assert_same(got[9], O.clahe(gh[9], 2.0, (8, 8)), "clahe stack frame 9 vs oracle")
+    assert_same(got[3], cv2.createCLAHE(2.0, (8, 8)).apply(gh[3]), "clahe stack frame 3 vs cv2")
 
 
 # --------------------------------------------------------------------------- K10 / K11

@@ -17,7 +17,15 @@ hist = be.histogram(c)
 m = be.threshold(c, 30000.0, 255)
 bits = be.adaptive_threshold_bits(c, 11, 2)
 bits2 = be.bits_morph(bits, W, 4, 5, 1)
-ws, cnt = be.ccl_resolve_bits(bits2, W)
-lab = be.ccl_emit(bits2, W, ws)
+# the labeller indexes pixels with 32 bits: strips of 2^31 px or more go through in sub-strips (as host/mosaic.py does)
+sub = rows
+while sub * W >= (1 << 31) or rows % sub:
+    sub //= 2
+lab = torch.empty((rows, W), dtype=torch.int32, device=be.device)
+total = 0
+for y in range(0, rows, sub):
+    ws, cnt = be.ccl_resolve_bits(bits2[y:y + sub], W)
+    be.ccl_emit(bits2[y:y + sub], W, ws, out=lab[y:y + sub])
+    total += int(cnt.item()) if hasattr(cnt, "item") else int(cnt)
 torch.cuda.synchronize()
-print("done", int(cnt.item()) if hasattr(cnt, "item") else cnt)
+print("done", total)

@@ -16,6 +16,8 @@ struct yam_ctx {
     cudaStream_t own_stream;  // created with the context
     void* scratch;            // grow-only device scratch
     size_t scratch_bytes;
+    void* scratch2;           // second arena: helpers called by operators that already hold `scratch`
+    size_t scratch2_bytes;
     void* pinned;             // small pinned host buffer for scalar/histogram read-back
     size_t pinned_bytes;
     int64_t launches;
@@ -55,6 +57,8 @@ void yam_set_error(const char* fmt, ...);
 
 // Device scratch: returns a pointer valid until the next yam_scratch call on this context.
 int yam_scratch(yam_ctx* ctx, size_t bytes, void** out);
+// Second arena with the same rule (histogram slabs under operators whose own buffers live in the first).
+int yam_scratch2(yam_ctx* ctx, size_t bytes, void** out);
 int yam_pinned(yam_ctx* ctx, size_t bytes, void** out);
 int yam_enter(yam_ctx* ctx);  // cudaSetDevice + sanity
 

@@ -74,6 +74,7 @@ int yam_ctx_destroy(yam_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -161,6 +162,24 @@ int yam_scratch(yam_ctx* ctx, size_t bytes, void** out) {
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;
+    return YAM_OK;
+}
+
+int yam_scratch2(yam_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch2_bytes) {
+        YAM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch2) YAM_CUDA(cudaFree(ctx->scratch2));
+        ctx->scratch2 = nullptr;
+        ctx->scratch2_bytes = 0;
+        size_t want = yam_align_up(bytes + bytes / 4, (size_t)1 << 20);
+        cudaError_t e = cudaMalloc(&ctx->scratch2, want);
+        if (e != cudaSuccess) {
+            yam_set_error("scratch2 cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return YAM_ENOMEM;
+        }
+        ctx->scratch2_bytes = want;
+    }
+    *out = ctx->scratch2;
     return YAM_OK;
 }
 

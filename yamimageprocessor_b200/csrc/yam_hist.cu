@@ -5,14 +5,15 @@
 // 128 KiB, two bins per 32-bit word, shared-memory atomics).  A counter that reaches 0x8000 is
 // "spilled": 0x8000 is subtracted from it and added to a global overflow histogram, so a half
 // never carries into its neighbour and counts stay exact for any region size.
-//   * Otsu / plain histogram: P CTAs per frame (row slabs), non-zero bins flushed with RED to a
-//     global u64 histogram.
+//   * Otsu / plain histogram: P CTAs per frame (row slabs); every CTA stores its packed histogram to a
+//     scratch slab and a second small kernel adds the slabs per bin (no flush atomics).
 //   * CLAHE: ONE CTA per CLAHE tile does histogram -> clip -> redistribute -> prefix sum -> LUT
 //     entirely on chip and writes only the 128 KiB LUT (no histogram ever reaches HBM).
 // 8-bit histograms use per-warp privatised 256-bin shared histograms.
-// Otsu's fp64 recurrence over the 65536 bins is sequential per frame: single frames are scanned on
-// a host thread (0.47 ms), stacks on a pool of host threads (up to 4 frames in lock step per
-// thread) or, when this rank has few host threads, by the staged device scan below.
+// Otsu's fp64 recurrence over the 65536 bins is sequential per frame, but its result is an arg-max:
+// otsu_certify_kernel proves it in parallel from exact integer prefix sums and an error bound of the
+// recurrence; frames it cannot certify go through the exact staged chain kernels.  Nothing is read
+// back and no host thread takes part (the host scan functions below serve the host-only C-ABI helpers).
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -32,6 +33,7 @@ int yam_threshold_dev(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64
 
 namespace {
 
+namespace cg = cooperative_groups;
 constexpr int kHistThreads = 1024;
 constexpr int kBins16 = 65536;
 constexpr int kWords16 = kBins16 / 2;
@@ -101,8 +103,44 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
 
 // ---------------------------------------------------------------------------------------------
 // plain histogram (Otsu): grid (parts, 1, frames)
-__global__ void __launch_bounds__(kHistThreads, 1) hist16_kernel(const uint16_t* __restrict__ src, int h, int w,
-                                                                 unsigned long long* __restrict__ hist) {
+// Flush without atomics: every CTA stores its packed private histogram (128 KiB, coalesced 16-byte
+// stores, zeros included) to a scratch slab and hist16_reduce_kernel adds the slabs per bin.  The
+// flush by RED (one per non-empty bin and CTA: ~30 000 x 148 for a 4096^2 frame) was 61 % of the
+// plain kernel's 43 us there (ncu source view: the warps sit on the scoreboard behind REDG.64).
+__device__ __forceinline__ void store_packed16(const uint32_t* __restrict__ sh, uint32_t* __restrict__ slab) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(sh);
+    uint4* d4 = reinterpret_cast<uint4*>(slab);
+    for (int i = threadIdx.x; i < kWords16 / 4; i += kHistThreads) d4[i] = s4[i];
+}
+
+// grid (kWords16 / 256, slots): thread = one packed word (two bins) of one slot, summed over `nparts` slabs
+// and ADDED to the counts already in `out` (the spill path of the private histograms adds there directly)
+template <typename CntT>
+__global__ void __launch_bounds__(256) hist16_reduce_kernel(const uint32_t* __restrict__ slabs, int nparts,
+                                                            CntT* __restrict__ out) {
+    const int wi = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t* p = slabs + (int64_t)blockIdx.y * nparts * kWords16 + wi;
+    uint32_t c0 = 0, c1 = 0;     // nparts x 0x7fff < 2^32
+    int q = 0;
+    for (; q + 4 <= nparts; q += 4) {
+        const uint32_t a = __ldcg(p + (int64_t)q * kWords16), b = __ldcg(p + (int64_t)(q + 1) * kWords16);
+        const uint32_t c = __ldcg(p + (int64_t)(q + 2) * kWords16), d = __ldcg(p + (int64_t)(q + 3) * kWords16);
+        c0 += (a & 0xffffu) + (b & 0xffffu) + (c & 0xffffu) + (d & 0xffffu);
+        c1 += (a >> 16) + (b >> 16) + (c >> 16) + (d >> 16);
+    }
+    for (; q < nparts; q++) {
+        const uint32_t a = __ldcg(p + (int64_t)q * kWords16);
+        c0 += a & 0xffffu;
+        c1 += a >> 16;
+    }
+    CntT* o = out + (int64_t)blockIdx.y * kBins16 + 2 * wi;
+    o[0] += (CntT)c0;
+    o[1] += (CntT)c1;
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1) hist16_slab_kernel(const uint16_t* __restrict__ src, int h, int w,
+                                                                      unsigned long long* __restrict__ hist,
+                                                                      uint32_t* __restrict__ slabs) {
     extern __shared__ __align__(16) uint32_t sh[];
     src += (int64_t)blockIdx.z * h * w;
     unsigned long long* out = hist + (int64_t)blockIdx.z * kBins16;
@@ -110,14 +148,10 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist16_kernel(const uint16_t*
     __syncthreads();
     const int parts = gridDim.x;
     const int rows_per = (h + parts - 1) / parts;
-    const int r0 = blockIdx.x * rows_per, r1 = min(h, r0 + rows_per);
+    const int r0 = min(h, (int)blockIdx.x * rows_per), r1 = min(h, r0 + rows_per);
     accumulate16<unsigned long long>(sh, out, nullptr, src, h, w, 0, w, r0, r1);
     __syncthreads();
-    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) {
-        const uint32_t wv = sh[i];
-        if (wv & 0xffffu) atomicAdd(&out[2 * i], (unsigned long long)(wv & 0xffffu));
-        if (wv >> 16) atomicAdd(&out[2 * i + 1], (unsigned long long)(wv >> 16));
-    }
+    store_packed16(sh, slabs + ((int64_t)blockIdx.z * parts + blockIdx.x) * kWords16);
 }
 
 // 8-bit histogram: grid (blocks, 1, frames); per-warp private histograms
@@ -198,7 +232,7 @@ __global__ void otsu_scan_kernel(const unsigned long long* __restrict__ hist, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Staged Otsu scan for stacks of 16-bit histograms.  The recurrence
+// Exact staged Otsu scan (the fall-back behind otsu_certify_kernel, which fills OtsuMeta).  The recurrence
 //     mu1 <- (mu1 * q1_prev + i * p_i) / q1_i,   q1_i = q1_prev + p_i
 // has two sequential chains.  q1 does not depend on mu1, so it runs one tile ahead (one DADD per
 // bin), the reciprocals 1/q1_i of a finished tile are computed by all lanes in parallel, and the mu1
@@ -214,54 +248,6 @@ struct OtsuMeta {
     int pad;
 };
 constexpr double kOtsuEps = 1.1920928955078125e-07;  // FLT_EPSILON
-
-__global__ void __launch_bounds__(1024) otsu_prep_kernel(const unsigned long long* __restrict__ hist, int bins,
-                                                         OtsuMeta* __restrict__ meta) {
-    __shared__ unsigned long long s_tot[32], s_mom[32];
-    __shared__ int s_first[32], s_last[32];
-    const unsigned long long* h = hist + (int64_t)blockIdx.x * bins;
-    unsigned long long tot = 0, mom = 0;
-    int first = 0x7fffffff, last = -1;
-    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
-        const unsigned long long c = h[i];
-        if (c) {
-            tot += c;
-            mom += c * (unsigned long long)i;  // integer-valued: exact in any order (as in the double sum)
-            first = min(first, i);
-            last = max(last, i);
-        }
-    }
-    tot = yam_warp_sum(tot);
-    mom = yam_warp_sum(mom);
-    first = yam_warp_min(first);
-    last = yam_warp_max(last);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        s_tot[warp] = tot; s_mom[warp] = mom; s_first[warp] = first; s_last[warp] = last;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = blockDim.x >> 5;
-        tot = lane < nw ? s_tot[lane] : 0ull;
-        mom = lane < nw ? s_mom[lane] : 0ull;
-        first = lane < nw ? s_first[lane] : 0x7fffffff;
-        last = lane < nw ? s_last[lane] : -1;
-        tot = yam_warp_sum(tot);
-        mom = yam_warp_sum(mom);
-        first = yam_warp_min(first);
-        last = yam_warp_max(last);
-        if (lane == 0) {
-            OtsuMeta m;
-            m.first = last < 0 ? -1 : first;
-            m.last = last;
-            m.scale = last < 0 ? 0.0 : __ddiv_rn(1.0, (double)tot);
-            m.mu = __dmul_rn((double)mom, m.scale);
-            m.certified = 0;
-            m.pad = 0;
-            meta[blockIdx.x] = m;
-        }
-    }
-}
 
 // Both chains in one warp per frame.  Per tile of kOtsuTile bins: all lanes stage p_i = h_i * scale
 // of the NEXT tile, the reciprocals 1/q1_i and i * p_i of the CURRENT tile in shared memory (coalesced
@@ -499,7 +485,6 @@ __global__ void __launch_bounds__(1024) otsu_sigma_kernel(const unsigned long lo
 // and tests/test_otsu_certify.py holds the NumPy model of this kernel against the sequential scan.
 // One 8-CTA cluster per frame: 8 bins per thread, prefix sums and reductions exchanged through
 // distributed shared memory.
-namespace cg = cooperative_groups;
 constexpr int kCertCluster = 8, kCertThreads = 1024, kCertPer = 8;
 static_assert(kCertCluster * kCertThreads * kCertPer == kBins16, "one thread per 8 bins");
 constexpr double kU = 1.1102230246251565e-16;  // 2^-53
@@ -513,7 +498,56 @@ struct CertShared {
     double best_lo;
     int best_i;
     int ncand, kmax;
+    double star[7];                // q1, q2, mu1, mu2, T, rq, rT of the winning bin (valid in the CTA that owns it)
 };
+
+// closed-form ("star") quantities of one bin from the exact prefix sums, and the accumulated-error radii
+struct BinStar {
+    double q1, q2, mu1, mu2, T, rq, rT;
+};
+// (x / N is computed as x * (1 / N): exact when N is a power of two, else 1.5 u instead of 0.5 u, inside the slack)
+__device__ __forceinline__ BinStar bin_star(unsigned long long C, unsigned long long Sp, unsigned long long N,
+                                            unsigned long long ST, double invN, int i, int first, int f, bool pow2) {
+    BinStar b;
+    const unsigned long long rest = ST - Sp;
+    b.q1 = (double)C * invN;
+    b.q2 = (double)(N - C) * invN;
+    b.rq = pow2 ? 0.0 : ((double)max(i - first + 1, 0) + 2.0) * kU * kInfl;
+    b.rT = (3.0 * (double)max(i - f, 0) + 5.0) * kU * kInfl;
+    b.T = (double)Sp * invN;
+    b.mu1 = (double)Sp / (double)C;
+    b.mu2 = (double)rest / (double)(N - C);
+    return b;
+}
+
+// Second chance for a bin k whose sigma interval overlaps the winner's (bin i): the accumulated errors of
+// the two chains at k and at i are the SAME numbers up to the |k - i| steps between them, and
+// F = A^2 / (q (1 - q)), A = T - M q, reacts to them almost identically at neighbouring bins.  With
+// q^_k = q_k + Eq + lq, T^_k = T_k + Et + lt (Eq, Et: the errors at i; lq, lt: the few roundings between
+// the bins), ln F_i - ln F_k moves with (Eq, Et, the rounding of mu) only through the DIFFERENCE of the
+// log-derivatives at the two bins.  True: k provably loses.  (tests/otsu_certify_model.py
+// differential_excludes is the same arithmetic.)
+__device__ __forceinline__ bool cert_differential_excludes(const BinStar& bi, const BinStar& bk, int dist, double M, bool pow2) {
+    const double D = (double)dist;
+    const double di = bi.mu1 - bi.mu2, dk = bk.mu1 - bk.mu2;
+    const double Ai = bi.q1 * bi.q2 * di, Ak = bk.q1 * bk.q2 * dk;
+    const double si = bi.q1 * bi.q2 * di * di, sk = bk.q1 * bk.q2 * dk * dk;
+    const double dT = 2.0 * fabs(1.0 / Ai - 1.0 / Ak);
+    const double dq = fabs(-2.0 * M * (1.0 / Ai - 1.0 / Ak) - (1.0 / bi.q1 - 1.0 / bk.q1) + (1.0 / bi.q2 - 1.0 / bk.q2));
+    const double dM = 2.0 * fabs(bi.q1 / Ai - bk.q1 / Ak);
+    const double common = 1.5 * (dT * bi.T * bi.rT + dq * bi.q1 * bi.rq + dM * M * 3.0 * kU);
+    const double lq = pow2 ? 0.0 : bk.q1 * (D + 3.0) * kU * kInfl;
+    const double lt = bk.T * (3.0 * D + 5.0) * kU * kInfl;
+    const double local = 1.5 * ((2.0 / fabs(Ak)) * lt + (fabs(2.0 * M / Ak) + 1.0 / bk.q1 + 1.0 / bk.q2) * lq);
+    auto eps = [&](const BinStar& b, double d) {
+        const double kappa = (fabs(b.T / (M - b.T)) + 4.0) * kU;
+        return 7.0 * kU + 2.0 * fabs(b.mu2 / d) * kappa;
+    };
+    auto star_err = [&](const BinStar& b, double d) { return 16.0 * kU * (1.0 + (fabs(b.mu1) + fabs(b.mu2)) / fabs(d)); };
+    const double gap = (si - sk) / si;
+    const double need = (common + local + eps(bi, di) + eps(bk, dk) + star_err(bi, di) + star_err(bk, dk)) * kInfl + 8.0 * kU;
+    return gap > need && need < INFINITY;   // NaN compares false
+}
 
 template <typename T, typename Op>
 __device__ __forceinline__ T cert_block_reduce(T v, T* s_tmp, Op op, T identity) {
@@ -639,17 +673,15 @@ otsu_certify_kernel(const unsigned long long* __restrict__ hist, OtsuMeta* __res
 
     // ---- which bins does the recurrence evaluate?  skip <=> q1^ < eps or q1^ > 1 - eps
     const bool pow2 = (N & (N - 1)) == 0;
-    const double Nf = (double)N, slop = 4.0 * kU;
+    const double Nf = (double)N, invN = 1.0 / Nf, slop = 4.0 * kU;
     unsigned nonc_mask = 0, amb_mask = 0;
-    double q1v[kCertPer];
     {
         unsigned long long C = ec;
 #pragma unroll
         for (int k = 0; k < kCertPer; k++) {
             C += c[k];
             const int i = bin0 + k;
-            const double q1 = (double)C / Nf;
-            q1v[k] = q1;
+            const double q1 = (double)C * invN;
             const double rq = pow2 ? 0.0 : ((double)max(i - first + 1, 0) + 2.0) * kU * kInfl;
             bool sf, st, nonc;
             if (pow2) {                          // the q1 chain is exact (multiples of 1/N): so are the decisions
@@ -710,7 +742,7 @@ otsu_certify_kernel(const unsigned long long* __restrict__ hist, OtsuMeta* __res
     double my_lo = 0.0;
     int my_i = 0x7fffffff;
     {
-        const double mu_star = (double)ST / Nf;
+        const double mu_star = (double)ST * invN;
         unsigned long long C = ec, S = em;
 #pragma unroll
         for (int k = 0; k < kCertPer; k++) {
@@ -720,12 +752,9 @@ otsu_certify_kernel(const unsigned long long* __restrict__ hist, OtsuMeta* __res
             const bool nonc = (nonc_mask >> k) & 1u, cand = (nonc || ((amb_mask >> k) & 1u)) && i >= f && i <= last;
             up[k] = -1.0;
             if (!cand) continue;
-            const double q1 = q1v[k], q2 = (double)(N - C) / Nf;
-            const double rq = pow2 ? 0.0 : ((double)max(i - first + 1, 0) + 2.0) * kU * kInfl;
-            const double rT = (3.0 * (double)(i - f) + 5.0) * kU * kInfl;
-            const unsigned long long Sp = S - S0, rest = ST - Sp;
-            const double B = (double)Sp / Nf, mu1 = (double)Sp / (double)C;
-            const double num = (double)rest / Nf, mu2 = (double)rest / (double)(N - C);
+            const BinStar b = bin_star(C, S - S0, N, ST, invN, i, first, f, pow2);
+            const double q1 = b.q1, q2 = b.q2, rq = b.rq, rT = b.rT, B = b.T, mu1 = b.mu1, mu2 = b.mu2;
+            const double num = (double)(ST - (S - S0)) * invN;
             const double e_m1 = mu1 * ((rT + rq) * kInfl + 2.0 * kU);
             const double e_num = (mu_star * 3.0 * kU + B * (rT + kU) + kU * (num + mu_star)) * kInfl + 4.0 * kU * mu_star;
             const double e_q2 = (q1 * rq + kU * q2) * kInfl + 2.0 * kU * q2;
@@ -795,14 +824,45 @@ otsu_certify_kernel(const unsigned long long* __restrict__ hist, OtsuMeta* __res
             istar = oi;
         }
     }
+    // the owner of the winning bin publishes its closed-form values for the differential test
+    if (Lmax > 0.0 && istar >= bin0 && istar < bin0 + kCertPer) {
+        unsigned long long C = ec, S = em;
+        for (int k = 0; k <= istar - bin0; k++) {
+            C += c[k];
+            S += c[k] * (unsigned long long)(bin0 + k);
+        }
+        const BinStar b = bin_star(C, S - S0, N, ST, invN, istar, first, f, pow2);
+        sh.star[0] = b.q1; sh.star[1] = b.q2; sh.star[2] = b.mu1; sh.star[3] = b.mu2;
+        sh.star[4] = b.T; sh.star[5] = b.rq; sh.star[6] = b.rT;
+    }
+    cluster.sync();                                                     // (3b) winner's values visible
     int ncand = 0, kmax = -1;
     if (Lmax > 0.0) {
+        bool any = false;
 #pragma unroll
-        for (int k = 0; k < kCertPer; k++)
-            if (up[k] >= Lmax && bin0 + k != istar) {
-                ncand++;
-                kmax = bin0 + k;
+        for (int k = 0; k < kCertPer; k++) any |= up[k] >= Lmax && bin0 + k != istar;
+        if (any) {   // rare: a sigma interval of this thread overlaps the winner's
+            const double* ps = cluster.map_shared_rank(&sh, istar / (kCertThreads * kCertPer))->star;
+            BinStar bi;
+            bi.q1 = ps[0]; bi.q2 = ps[1]; bi.mu1 = ps[2]; bi.mu2 = ps[3]; bi.T = ps[4]; bi.rq = ps[5]; bi.rT = ps[6];
+            const double M = (double)ST * invN;
+            unsigned long long C = ec, S = em;
+            for (int k = 0; k < kCertPer; k++) {
+                C += c[k];
+                S += c[k] * (unsigned long long)(bin0 + k);
+                const int i = bin0 + k;
+                if (!(up[k] >= Lmax) || i == istar) continue;
+                bool excluded = false;
+                if ((nonc_mask >> k) & 1u) {
+                    const BinStar bk = bin_star(C, S - S0, N, ST, invN, i, first, f, pow2);
+                    excluded = cert_differential_excludes(bi, bk, abs(i - istar), M, pow2);
+                }
+                if (!excluded) {
+                    ncand++;
+                    kmax = i;
+                }
             }
+        }
     }
     const int cta_n = cert_block_reduce<int>(ncand, s_i, [](int a, int b) { return a + b; }, 0);
     const int cta_k = cert_block_reduce<int>(kmax, s_i, [](int a, int b) { return max(a, b); }, -1);
@@ -1059,7 +1119,8 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint
 // bins into the tile's 32-bit global histogram (zeroed by the caller); a second kernel builds the LUT.
 __global__ void __launch_bounds__(kHistThreads, 1) clahe_hist16_parts_kernel(const uint16_t* __restrict__ src_all,
                                                                              ClaheGeom g,
-                                                                             uint32_t* __restrict__ ghist) {
+                                                                             uint32_t* __restrict__ ghist,
+                                                                             uint32_t* __restrict__ slabs) {
     extern __shared__ __align__(16) uint32_t sh[];
     const int tiles_per_frame = g.tiles_x * g.tiles_y;
     const int slot = blockIdx.y;
@@ -1075,11 +1136,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_hist16_parts_kernel(con
     const int r1 = min((tyi + 1) * g.th, r0 + rows_per);
     accumulate16<uint32_t>(sh, gh, nullptr, src, g.h, g.w, txi * g.tw, (txi + 1) * g.tw, r0, r1);
     __syncthreads();
-    for (int i = threadIdx.x; i < kWords16; i += kHistThreads) {
-        const uint32_t wv = sh[i];
-        if (wv & 0xffffu) atomicAdd(&gh[2 * i], wv & 0xffffu);
-        if (wv >> 16) atomicAdd(&gh[2 * i + 1], wv >> 16);
-    }
+    store_packed16(sh, slabs + ((int64_t)slot * parts + blockIdx.x) * kWords16);   // hist16_reduce_kernel adds the slabs
 }
 
 __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut_from_hist_kernel(const uint32_t* __restrict__ ghist,
@@ -1287,29 +1344,31 @@ private:
 };
 
 // 64-bit device histograms -> 32-bit counts for the host scan (halves the read-back)
-__global__ void __launch_bounds__(256) hist_narrow_kernel(const unsigned long long* __restrict__ in,
-                                                          uint32_t* __restrict__ out, int64_t count) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = (uint32_t)in[i];
-}
-
-// Interleaved LUTs for the apply pass on large 16-bit frames: quad[cell][v] holds the four LUT
-// values a pixel of interpolation cell (cy, cx) needs, so the apply kernel issues ONE 8-byte gather
-// per pixel instead of four 2-byte gathers (the gathers, not HBM, bound the plain apply kernel).
-// cell (cy, cx), cy in [0, tiles_y], cx in [0, tiles_x]: tiles (max(cy-1,0) | min(cy,ty-1)) x (max(cx-1,0) | min(cx,tx-1))
+// thread = 8 consecutive values: four 16-byte LUT loads, four 16-byte stores (two interleaved entries each)
 __global__ void __launch_bounds__(256) clahe_quad_build_kernel(const uint16_t* __restrict__ luts, int tiles_x, int tiles_y,
                                                               ushort4* __restrict__ quad) {
     const int cell = blockIdx.y;
     const int cy = cell / (tiles_x + 1), cx = cell - cy * (tiles_x + 1);
     const int ty1 = max(cy - 1, 0), ty2 = min(cy, tiles_y - 1);
     const int tx1 = max(cx - 1, 0), tx2 = min(cx, tiles_x - 1);
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    ushort4 q;
-    q.x = luts[((int64_t)ty1 * tiles_x + tx1) * kBins16 + v];
-    q.y = luts[((int64_t)ty1 * tiles_x + tx2) * kBins16 + v];
-    q.z = luts[((int64_t)ty2 * tiles_x + tx1) * kBins16 + v];
-    q.w = luts[((int64_t)ty2 * tiles_x + tx2) * kBins16 + v];
-    quad[(int64_t)cell * kBins16 + v] = q;
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(luts + ((int64_t)ty1 * tiles_x + tx1) * kBins16 + v));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(luts + ((int64_t)ty1 * tiles_x + tx2) * kBins16 + v));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(luts + ((int64_t)ty2 * tiles_x + tx1) * kBins16 + v));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(luts + ((int64_t)ty2 * tiles_x + tx2) * kBins16 + v));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    uint4* out = reinterpret_cast<uint4*>(quad + (int64_t)cell * kBins16 + v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // entries v + 2k and v + 2k + 1: (l11 | l12 << 16, l21 | l22 << 16) each
+        uint4 o;
+        o.x = __byte_perm(aw[k], bw[k], 0x5410);
+        o.y = __byte_perm(cw[k], dw[k], 0x5410);
+        o.z = __byte_perm(aw[k], bw[k], 0x7632);
+        o.w = __byte_perm(cw[k], dw[k], 0x7632);
+        out[k] = o;
+    }
 }
 
 __global__ void __launch_bounds__(256) clahe_apply_quad_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
@@ -1454,21 +1513,24 @@ inline bool clahe_tab_ok(const void* src, const void* dst, int64_t w) {
 }
 inline size_t clahe_tab_bytes(int64_t w) { return yam_align_up((size_t)w * 4, 256) + yam_align_up((size_t)w * 2, 256); }
 
-// builds the column tables at `tab` and applies rows x frames; `table` = quad cells (QUAD) or the LUT set
+// builds the column tables at `tab` (unless the caller already did: build_tab = false) and applies
+// rows x frames; `table` = quad cells (QUAD) or the LUT set
 template <bool QUAD>
 int clahe_apply16_tab(yam_ctx* ctx, const uint16_t* s_ptr, uint16_t* d_ptr, int64_t rows, int64_t frames, const ClaheGeom& g,
-                      const void* table, void* tab) {
+                      const void* table, void* tab, bool build_tab = true) {
     float* xa = (float*)tab;
     uint16_t* cell = (uint16_t*)((char*)tab + yam_align_up((size_t)g.w * 4, 256));
-    clahe_xtab_kernel<<<(unsigned)((g.w + 255) / 256), 256, 0, ctx->stream>>>(g, xa, cell);
-    YAM_LAUNCHED(ctx);
+    if (build_tab) {
+        clahe_xtab_kernel<<<(unsigned)((g.w + 255) / 256), 256, 0, ctx->stream>>>(g, xa, cell);
+        YAM_LAUNCHED(ctx);
+    }
     dim3 grid((unsigned)rows, (unsigned)((g.w + 2047) / 2048), (unsigned)frames);
     clahe_apply16_tab_kernel<QUAD><<<grid, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, table, xa, cell);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
 }
 
-constexpr int64_t kQuadMinPixels = 8ll << 20;  // below this the 40 MB quad build costs more than it saves
+constexpr int64_t kQuadMinPixels = 8ll << 20;  // below this the 40 MB cell-table build costs more than it saves (measured again in round 2: 32 x 2048^2 frames 1.45 ms with four 2-byte gathers, 1.63 ms through per-frame cell tables)
 constexpr int kQuadMaxCells = 128;
 
 inline bool clahe_use_quad(int64_t pixels, int tiles_x, int tiles_y) {
@@ -1481,15 +1543,15 @@ inline size_t clahe_tab_bytes(int64_t w);
 
 // apply `rows` rows of one frame with the quad path: build quad from luts, then gather
 int clahe_apply16_quad(yam_ctx* ctx, const uint16_t* s_ptr, uint16_t* d_ptr, int64_t rows, const ClaheGeom& g,
-                       const uint16_t* luts, ushort4* quad) {
+                       const uint16_t* luts, ushort4* quad, bool build_tab = true) {
     // scratch layout: [quad cells][column tables]
     const int cells = (g.tiles_x + 1) * (g.tiles_y + 1);
-    clahe_quad_build_kernel<<<dim3(kBins16 / 256, (unsigned)cells), 256, 0, ctx->stream>>>(luts, g.tiles_x, g.tiles_y, quad);
+    clahe_quad_build_kernel<<<dim3(kBins16 / (8 * 256), (unsigned)cells), 256, 0, ctx->stream>>>(luts, g.tiles_x, g.tiles_y, quad);
     YAM_LAUNCHED(ctx);
     if (clahe_tab_ok(s_ptr, d_ptr, g.w)) {
         ClaheGeom gr = g;
         gr.h = (int)rows;
-        return clahe_apply16_tab<true>(ctx, s_ptr, d_ptr, rows, 1, gr, quad, (char*)quad + clahe_quad_bytes(g.tiles_x, g.tiles_y));
+        return clahe_apply16_tab<true>(ctx, s_ptr, d_ptr, rows, 1, gr, quad, (char*)quad + clahe_quad_bytes(g.tiles_x, g.tiles_y), build_tab);
     }
     clahe_apply_quad_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(s_ptr, d_ptr, g, quad);
     YAM_LAUNCHED(ctx);
@@ -1546,8 +1608,13 @@ int clahe_luts16(yam_ctx* ctx, const uint16_t* s_ptr, const ClaheGeom& g, int64_
         int64_t parts = (2 * (int64_t)slots + total_tiles - 1) / total_tiles;
         if (parts > g.th) parts = g.th;
         YAM_CUDA(cudaMemsetAsync(scratch_tail, 0, (size_t)total_tiles * kBins16 * sizeof(uint32_t), ctx->stream));
+        void* slabs = nullptr;
+        if (int rc = yam_scratch2(ctx, (size_t)total_tiles * parts * kSmem16, &slabs)) return rc;
         clahe_hist16_parts_kernel<<<dim3((unsigned)parts, (unsigned)total_tiles), kHistThreads, kSmem16, ctx->stream>>>(
-            s_ptr, g, (uint32_t*)scratch_tail);
+            s_ptr, g, (uint32_t*)scratch_tail, (uint32_t*)slabs);
+        YAM_LAUNCHED(ctx);
+        hist16_reduce_kernel<uint32_t><<<dim3(kWords16 / 256, (unsigned)total_tiles), 256, 0, ctx->stream>>>(
+            (const uint32_t*)slabs, (int)parts, (uint32_t*)scratch_tail);
         YAM_LAUNCHED(ctx);
         clahe_lut_from_hist_kernel<<<(unsigned)total_tiles, kHistThreads, 0, ctx->stream>>>((const uint32_t*)scratch_tail, g, luts);
         YAM_LAUNCHED(ctx);
@@ -1576,14 +1643,19 @@ int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, in
     } else {
         static bool attr_set[64] = {};  // per device, see clahe_luts16
         if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
-            YAM_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
+            YAM_CUDA(cudaFuncSetAttribute(hist16_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
             if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
         }
         int64_t parts = ctx->num_sms / n;
         if (parts < 1) parts = 1;
         if (parts > h) parts = h;
-        hist16_kernel<<<dim3((unsigned)parts, 1, (unsigned)n), kHistThreads, kSmem16, ctx->stream>>>(
-            (const uint16_t*)src, (int)h, (int)w, hist);
+        void* slabs = nullptr;
+        if (int rc = yam_scratch2(ctx, (size_t)n * parts * kSmem16, &slabs)) return rc;
+        hist16_slab_kernel<<<dim3((unsigned)parts, 1, (unsigned)n), kHistThreads, kSmem16, ctx->stream>>>(
+            (const uint16_t*)src, (int)h, (int)w, hist, (uint32_t*)slabs);
+        YAM_LAUNCHED(ctx);
+        hist16_reduce_kernel<unsigned long long><<<dim3(kWords16 / 256, (unsigned)n), 256, 0, ctx->stream>>>(
+            (const uint32_t*)slabs, (int)parts, hist);
     }
     YAM_LAUNCHED(ctx);
     return YAM_OK;
@@ -1760,8 +1832,9 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
         int64_t chunk = (int64_t)((64u << 20) / lut_frame);
         if (chunk < 1) chunk = 1;
         if (chunk > n) chunk = n;
+        // quad path: the LUTs of a chunk are built together (enough tiles to fill the SMs), then every frame
+        // interleaves its cell table and gathers from it while it is still in L2
         const bool quad_path = clahe_use_quad(h * w, tiles_x, tiles_y);
-        if (quad_path) chunk = 1;
         const int64_t tail_slots = (tiles * chunk > ctx->num_sms) ? tiles * chunk : ctx->num_sms;
         const size_t ovf_bytes = yam_align_up((size_t)tail_slots * kBins16 * sizeof(uint32_t), 256);
         const size_t luts_bytes = yam_align_up(lut_frame * chunk, 256);
@@ -1779,7 +1852,10 @@ int yam_clahe(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, in
             uint16_t* d_ptr = (uint16_t*)dst + f0 * frame_px;
             if (int rc = clahe_luts16(ctx, s_ptr, g, nf, luts, tail)) return rc;
             if (quad_path) {
-                if (int rc = clahe_apply16_quad(ctx, s_ptr, d_ptr, h, g, luts, quad)) return rc;
+                for (int64_t f = 0; f < nf; f++)
+                    if (int rc = clahe_apply16_quad(ctx, s_ptr + f * frame_px, d_ptr + f * frame_px, h, g, luts + f * tiles * kBins16,
+                                                    quad, f0 + f == 0))
+                        return rc;
             } else if (clahe_tab_ok(s_ptr, d_ptr, w)) {
                 if (int rc = clahe_apply16_tab<false>(ctx, s_ptr, d_ptr, h, nf, g, luts, (char*)scratch + luts_bytes + ovf_bytes)) return rc;
             } else {
