@@ -66,7 +66,7 @@ def _peaks():
 def _traffic(op_name: str, px: int):
     """Measured DRAM bytes per launch of an operator (ncu --set full; profiles/r0*_traffic_*.json);
     None when no capture exists for this operator at this pixel count."""
-    for name in ("r02_traffic_c4.json", "r02_traffic_c2.json", "r01_traffic_c2.json"):
+    for name in ("r02_traffic_c4.json", "r02_traffic_c4_n1.json", "r02_traffic_c2.json", "r01_traffic_c2.json"):
         try:
             d = json.loads((ROOT / "profiles" / name).read_text())
         except Exception:

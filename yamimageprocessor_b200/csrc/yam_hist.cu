@@ -67,16 +67,33 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
     for (int r = r0 + warp; r < r1; r += nwarps) {
         const int gy = yam_border(r, h, YAM_BORDER_REFLECT101);
         const uint16_t* row = src + (int64_t)gy * w;
+        // Eight pixels per call: all eight shared-memory atomics are issued back to back (independent), the
+        // returned words are checked together afterwards (one predicate per call instead of a dependent
+        // atomic -> compare -> branch chain per pixel).  A counter spills when THIS increment took its half
+        // to 0x8000 (bit 15 of the half goes 0 -> 1); between that atomic and the subtraction in the rare
+        // path at most threads x 8 further increments can land, far below the 0x8000 of head room, so a
+        // half never carries into its neighbour.
         auto consume = [&](const uint4& q) {
             const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+            uint32_t old[8];
+            uint32_t flips = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t a = wd[i] & 0xffffu, b = wd[i] >> 16;
-                if (a == b) {
-                    bump16(sh, overflow, spill_flag, a, 2u);
-                } else {
-                    bump16(sh, overflow, spill_flag, a, 1u);
-                    bump16(sh, overflow, spill_flag, b, 1u);
+            for (int i = 0; i < 8; i++) {
+                const uint32_t v = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu);
+                const uint32_t inc = 1u + (v & 1u) * 0xffffu;             // 1 or 0x10000
+                old[i] = atomicAdd(&sh[v >> 1], inc);
+                flips |= ~old[i] & (old[i] + inc) & (inc << 15);
+            }
+            if (flips) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t v = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu);
+                    const uint32_t inc = 1u + (v & 1u) * 0xffffu;
+                    if (~old[i] & (old[i] + inc) & (inc << 15)) {
+                        atomicSub(&sh[v >> 1], inc << 15);
+                        atomicAdd(&overflow[v], (CntT)0x8000u);
+                        if (spill_flag) *spill_flag = 1;
+                    }
                 }
             }
         };
