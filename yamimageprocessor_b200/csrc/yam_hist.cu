@@ -99,12 +99,23 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
         };
         const uint4* vrow = reinterpret_cast<const uint4*>(row + c0);
         int v = lane;
-        // four 16-byte loads in flight per thread before the first shared-memory atomic: with one CTA of
-        // 1024 threads per SM a single load per thread (16 KiB in flight) left the kernel waiting on HBM
-        // latency (long scoreboard was the top stall in round 1's profile)
-        for (; v + 96 < nvec; v += 128) {
-            const uint4 q0 = yam_ld_stream(vrow + v), q1 = yam_ld_stream(vrow + v + 32);
-            const uint4 q2 = yam_ld_stream(vrow + v + 64), q3 = yam_ld_stream(vrow + v + 96);
+        // four 16-byte loads in flight per thread AT ALL TIMES: every consumed vector is replaced by the
+        // load of the vector four steps ahead before the next one is consumed (with one CTA of 1024 threads
+        // per SM a single load per thread, 16 KiB in flight, left the kernel waiting on HBM latency)
+        if (v + 96 < nvec) {
+            uint4 q0 = yam_ld_stream(vrow + v), q1 = yam_ld_stream(vrow + v + 32);
+            uint4 q2 = yam_ld_stream(vrow + v + 64), q3 = yam_ld_stream(vrow + v + 96);
+            v += 128;
+            for (; v + 96 < nvec; v += 128) {
+                consume(q0);
+                q0 = yam_ld_stream(vrow + v);
+                consume(q1);
+                q1 = yam_ld_stream(vrow + v + 32);
+                consume(q2);
+                q2 = yam_ld_stream(vrow + v + 64);
+                consume(q3);
+                q3 = yam_ld_stream(vrow + v + 96);
+            }
             consume(q0);
             consume(q1);
             consume(q2);
