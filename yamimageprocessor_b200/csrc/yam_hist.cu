@@ -1677,13 +1677,22 @@ int hist_into(yam_ctx* ctx, const void* src, int64_t n, int64_t h, int64_t w, in
         int64_t parts = ctx->num_sms / n;
         if (parts < 1) parts = 1;
         if (parts > h) parts = h;
+        // frames go through in groups so the slab scratch stays bounded (<= 296 slabs of 128 KiB)
+        int64_t group = (2 * (int64_t)ctx->num_sms) / parts;
+        if (group < 1) group = 1;
+        if (group > n) group = n;
         void* slabs = nullptr;
-        if (int rc = yam_scratch2(ctx, (size_t)n * parts * kSmem16, &slabs)) return rc;
-        hist16_slab_kernel<<<dim3((unsigned)parts, 1, (unsigned)n), kHistThreads, kSmem16, ctx->stream>>>(
-            (const uint16_t*)src, (int)h, (int)w, hist, (uint32_t*)slabs);
-        YAM_LAUNCHED(ctx);
-        hist16_reduce_kernel<unsigned long long><<<dim3(kWords16 / 256, (unsigned)n), 256, 0, ctx->stream>>>(
-            (const uint32_t*)slabs, (int)parts, hist);
+        if (int rc = yam_scratch2(ctx, (size_t)group * parts * kSmem16, &slabs)) return rc;
+        const int64_t frame_px = h * w;
+        for (int64_t f0 = 0; f0 < n; f0 += group) {
+            const int64_t nf = (n - f0) < group ? (n - f0) : group;
+            hist16_slab_kernel<<<dim3((unsigned)parts, 1, (unsigned)nf), kHistThreads, kSmem16, ctx->stream>>>(
+                (const uint16_t*)src + f0 * frame_px, (int)h, (int)w, hist + f0 * kBins16, (uint32_t*)slabs);
+            YAM_LAUNCHED(ctx);
+            hist16_reduce_kernel<unsigned long long><<<dim3(kWords16 / 256, (unsigned)nf), 256, 0, ctx->stream>>>(
+                (const uint32_t*)slabs, (int)parts, hist + f0 * kBins16);
+            if (f0 + group < n) YAM_LAUNCHED(ctx);
+        }
     }
     YAM_LAUNCHED(ctx);
     return YAM_OK;
