@@ -482,9 +482,17 @@ def run_gpu_mosaic(args):
     trace_marks = []
     if os.environ.get("YAM_MOSAIC_TRACE") and rank == 0:
         # diagnostics: phase end times of rank 0 (adds a device sync per phase; not for reported numbers)
+        # YAM_MOSAIC_TRACE=events: CUDA events at the phase ends, no synchronisation (host and device clocks side by side)
+        trace_events = os.environ.get("YAM_MOSAIC_TRACE") == "events"
+
         def _trace(name, strip):
-            torch.cuda.synchronize()
-            trace_marks.append((time.perf_counter(), strip, name))
+            if trace_events:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                trace_marks.append((time.perf_counter(), strip, name, ev))
+            else:
+                torch.cuda.synchronize()
+                trace_marks.append((time.perf_counter(), strip, name, None))
         p.trace = _trace
     r0, r1 = mosaic.input_rows(size, rank, world, p)
     c0, c1 = mosaic.strip_rows(size, p.tile_grid[1], rank, world)
@@ -525,9 +533,16 @@ def run_gpu_mosaic(args):
         times.append(a.elapsed_time(b))
         if p.trace is not None:
             last = t_step
-            for tm, strip, name in sorted(trace_marks):
-                sys.stderr.write(f"[trace] +{1e3 * (tm - last):7.2f} ms strip {strip} {name}\n")
+            prev_ev = a
+            for tm, strip, name, ev in trace_marks:
+                if ev is not None:
+                    sys.stderr.write(f"[trace] host +{1e3 * (tm - last):7.2f} ms | device +{prev_ev.elapsed_time(ev):7.3f} ms  {name}\n")
+                    prev_ev = ev
+                else:
+                    sys.stderr.write(f"[trace] +{1e3 * (tm - last):7.2f} ms strip {strip} {name}\n")
                 last = tm
+            if prev_ev is not a:
+                sys.stderr.write(f"[trace] device tail +{prev_ev.elapsed_time(b):7.3f} ms (after the last mark)\n")
             sys.stderr.write(f"[trace] step total {1e3 * (time.perf_counter() - t_step):.2f} ms\n")
     barrier()
     launches = be.launch_count()

@@ -258,8 +258,10 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
 
     # CLAHE: LUTs of the tile rows this rank owns, gathered from every rank
     luts_local = be.clahe_luts(g[c0 - r0: c1 - r0], p.clip_limit, (tiles_x, tiles_y // world))
+    mark("clahe_luts")
     if comm is not None:  # [world, tile rows per strip, tiles_x, bins] is the global LUT table, already in order
         luts = comm.all_gather(luts_local).reshape(tiles_y, tiles_x, -1)
+        mark("lut_all_gather")
     else:
         luts = luts_local
     c = be.clahe_apply(g[a0 - r0: a1 - r0], luts, (tw, th), y_offset=a0)
@@ -272,6 +274,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     if comm is not None:
         comm.all_reduce(hist, "sum")
     t_dev = be.otsu_from_histogram_device(hist)
+    mark("histogram_all_reduce_scan")
 
     # segmentation on the extended rows, cropped to the core
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
@@ -304,6 +307,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
             be.ccl_emit(b, W, ws_i, rows=(sub_rows - 1, sub_rows), out=pack[i, W:2 * W])
             pack[i, 2 * W:2 * W + 1].copy_(cnt_i)
         packed = comm.all_gather(pack).reshape(-1, stride) if comm is not None else pack
+        mark("boundary_all_gather")
         # The host needs the counts only to size the tables.  They are read back asynchronously and the
         # Otsu mask kernel is enqueued behind the copy, so the GPU has work while the host waits.
         cnt_host = torch.empty((int(packed.shape[0]),), dtype=torch.int32, pin_memory=True)
@@ -319,6 +323,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         # the label image is written once, already in global numbering
         labels = torch.empty((rows_core, W), dtype=torch.int32, device=be.device)
         remaps, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub, k_sub)
+        mark("merge_remap")
         if k_sub == 1:
             remaps = [remaps]
         for i, (b, ws_i, cnt_i) in enumerate(subs):
@@ -328,6 +333,7 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         mark("otsu")
         b, ws_i, total_dev = subs[0]
         labels = be.ccl_emit(b, W, ws_i)
+    mark("emit")
     total = int(total_dev[0].item())   # the only wait for the labelling: everything above is enqueued
     t = int(t_dev[0].item())
     mark("merge")
