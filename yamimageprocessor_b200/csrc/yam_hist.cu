@@ -55,7 +55,7 @@ __device__ __forceinline__ void bump16(uint32_t* __restrict__ sh, CntT* __restri
 }
 
 // Accumulate rows [r0, r1) x cols [c0, c1) of a (possibly reflect-padded) region into `sh`.
-template <typename CntT>
+template <typename CntT, bool NARROW = false>
 __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __restrict__ overflow,
                                              int* __restrict__ spill_flag, const uint16_t* __restrict__ src, int h, int w, int c0, int c1,
                                              int r0, int r1) {
@@ -64,39 +64,69 @@ __device__ __forceinline__ void accumulate16(uint32_t* __restrict__ sh, CntT* __
     const int cw = c1 - c0;
     const int cin = min(c1, w) - c0;               // columns inside the image
     const int nvec = aligned ? (cin > 0 ? cin / 8 : 0) : 0;
-    for (int r = r0 + warp; r < r1; r += nwarps) {
-        const int gy = yam_border(r, h, YAM_BORDER_REFLECT101);
-        const uint16_t* row = src + (int64_t)gy * w;
-        // Eight pixels per call: all eight shared-memory atomics are issued back to back (independent), the
-        // returned words are checked together afterwards (one predicate per call instead of a dependent
-        // atomic -> compare -> branch chain per pixel).  A counter spills when THIS increment took its half
-        // to 0x8000 (bit 15 of the half goes 0 -> 1); between that atomic and the subtraction in the rare
-        // path at most threads x 8 further increments can land, far below the 0x8000 of head room, so a
-        // half never carries into its neighbour.
-        auto consume = [&](const uint4& q) {
-            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
-            uint32_t old[8];
-            uint32_t flips = 0;
+    // Eight pixels per call: all eight shared-memory atomics are issued back to back (independent), the
+    // returned words are checked together afterwards (one predicate per call instead of a dependent
+    // atomic -> compare -> branch chain per pixel).  A counter spills when THIS increment took its half
+    // to 0x8000 (bit 15 of the half goes 0 -> 1); between that atomic and the subtraction in the rare
+    // path at most threads x 8 further increments can land, far below the 0x8000 of head room, so a
+    // half never carries into its neighbour.
+    auto consume = [&](const uint4& q) {
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+        uint32_t old[8];
+        uint32_t flips = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t v = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu);
+            const uint32_t inc = 1u + (v & 1u) * 0xffffu;             // 1 or 0x10000
+            old[i] = atomicAdd(&sh[v >> 1], inc);
+            flips |= ~old[i] & (old[i] + inc) & (inc << 15);
+        }
+        if (flips) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const uint32_t v = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu);
-                const uint32_t inc = 1u + (v & 1u) * 0xffffu;             // 1 or 0x10000
-                old[i] = atomicAdd(&sh[v >> 1], inc);
-                flips |= ~old[i] & (old[i] + inc) & (inc << 15);
-            }
-            if (flips) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint32_t v = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu);
-                    const uint32_t inc = 1u + (v & 1u) * 0xffffu;
-                    if (~old[i] & (old[i] + inc) & (inc << 15)) {
-                        atomicSub(&sh[v >> 1], inc << 15);
-                        atomicAdd(&overflow[v], (CntT)0x8000u);
-                        if (spill_flag) *spill_flag = 1;
-                    }
+                const uint32_t inc = 1u + (v & 1u) * 0xffffu;
+                if (~old[i] & (old[i] + inc) & (inc << 15)) {
+                    atomicSub(&sh[v >> 1], inc << 15);
+                    atomicAdd(&overflow[v], (CntT)0x8000u);
+                    if (spill_flag) *spill_flag = 1;
                 }
             }
-        };
+        }
+    };
+    // Narrow regions (CLAHE tiles of single frames: 256 or 512 px wide = one or two vectors per lane and row):
+    // a warp issues the loads of FOUR vectors (four rows x 1 or two rows x 2) before the first atomic; row by
+    // row the kernel paid one exposed memory round trip per vector (8-32 sequential round trips per warp and tile).
+    if (NARROW && nvec > 0 && nvec <= 64) {
+        const int vpr = nvec <= 32 ? 1 : 2;          // vectors per lane and row
+        const int rows_per = 4 / vpr;                // rows per batch
+        for (int r = r0 + warp; r < r1; r += rows_per * nwarps) {
+            uint4 q[4];
+#pragma unroll
+            for (int s4 = 0; s4 < 4; s4++) {
+                const int rr = r + (s4 / vpr) * nwarps, vi = lane + 32 * (s4 % vpr);
+                if (rr < r1 && vi < nvec)
+                    q[s4] = yam_ld_stream(reinterpret_cast<const uint4*>(src + (int64_t)yam_border(rr, h, YAM_BORDER_REFLECT101) * w + c0) + vi);
+            }
+#pragma unroll
+            for (int s4 = 0; s4 < 4; s4++) {
+                const int rr = r + (s4 / vpr) * nwarps, vi = lane + 32 * (s4 % vpr);
+                if (rr < r1 && vi < nvec) consume(q[s4]);
+            }
+            if (nvec * 8 < cw) {                     // columns past the last whole vector / the image edge
+                for (int j = 0; j < rows_per; j++) {
+                    const int rr = r + j * nwarps;
+                    if (rr >= r1) break;
+                    const uint16_t* row = src + (int64_t)yam_border(rr, h, YAM_BORDER_REFLECT101) * w;
+                    for (int c = nvec * 8 + lane; c < cw; c += 32) bump16(sh, overflow, spill_flag, row[yam_border(c0 + c, w, YAM_BORDER_REFLECT101)], 1u);
+                }
+            }
+        }
+        return;
+    }
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+        const int gy = yam_border(r, h, YAM_BORDER_REFLECT101);
+        const uint16_t* row = src + (int64_t)gy * w;
         const uint4* vrow = reinterpret_cast<const uint4*>(row + c0);
         int v = lane;
         // four 16-byte loads in flight per thread AT ALL TIMES: every consumed vector is replaced by the
@@ -1122,7 +1152,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) clahe_lut16_kernel(const uint
         for (int i = threadIdx.x; i < kWords16; i += kHistThreads) sh[i] = 0;
         if (threadIdx.x == 0) s_spilled = 0;
         __syncthreads();
-        accumulate16<uint32_t>(sh, ovf, &s_spilled, src, g.h, g.w, txi * g.tw, (txi + 1) * g.tw, tyi * g.th,
+        accumulate16<uint32_t, true>(sh, ovf, &s_spilled, src, g.h, g.w, txi * g.tw, (txi + 1) * g.tw, tyi * g.th,
                                (tyi + 1) * g.th);
         __threadfence();
         __syncthreads();
