@@ -153,6 +153,12 @@ int yam_morph_open_close(yam_ctx* ctx, const void* src, void* dst, int64_t n, in
  * yam_bits_unpack = packed bits -> uint8 {0,255}; yam_ccl_label_bits = yam_ccl_label on bits. */
 int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h,
                                 int64_t w, int dtype, int block_size, double C);
+/* The same, and in the same pass over src the GLOBAL threshold mask mask_out = src > thresh_dev[frame] ? maxval : 0
+ * (source dtype; = yam_threshold_frames): a pipeline that needs both the Otsu mask (core/segmentation.py:147) and the
+ * adaptive segmentation (:91-94) of one image reads it once.  thresh_dev: int32[n] on the device. */
+int yam_adaptive_threshold_bits_mask(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h,
+                                     int64_t w, int dtype, int block_size, double C, const int32_t* thresh_dev,
+                                     void* mask_out, double maxval);
 int yam_bits_morph(yam_ctx* ctx, const uint32_t* bits_in, uint32_t* bits_out, int64_t n, int64_t h,
                    int64_t w, int op, int ksize, int iterations);
 int yam_bits_unpack(yam_ctx* ctx, const uint32_t* bits, void* mask_u8, int64_t n, int64_t h, int64_t w);

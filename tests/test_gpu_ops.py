@@ -627,6 +627,37 @@ def test_adaptive_bits_tma_kernel(backend, rng, dt):
                 assert int((raw[..., -1] >> (shape[-1] % 32)).max()) == 0
 
 
+@pytest.mark.parametrize("dt", [U8, U16])
+def test_adaptive_bits_with_global_threshold_mask(backend, rng, dt):
+    """yam_adaptive_threshold_bits_mask: same bits as the plain call, and the global threshold mask
+    (src > t[frame] ? maxval : 0, cv2.threshold THRESH_BINARY) written in the same pass -- TMA kernel shapes
+    (16-bit: fused into the tile loop; borders, ragged widths, stacks, per-frame thresholds incl. t < 0 and
+    t >= max) and shapes / dtypes that fall back to the separate threshold kernel."""
+    import torch
+
+    hi = 255 if dt == U8 else 65535
+    for shape in ((80, 256), (130, 272), (201, 1104), (3, 90, 512), (2, 150, 720), (33, 71), (64, 64)):
+        a = blobs(rng, shape[-2:], dt) if len(shape) == 2 else np.stack([blobs(rng, shape[-2:], dt) for _ in range(shape[0])])
+        n = 1 if a.ndim == 2 else a.shape[0]
+        x = dev(backend, a)
+        for ts, maxval in (([int(hi * 0.3)] * n, 255), ([-1, hi, int(hi * 0.5)][:n] if n > 1 else [0], hi), ([hi - 1] * n, 1)):
+            t_dev = torch.tensor(ts, dtype=torch.int32, device=backend.device)
+            bits, mask = backend.adaptive_threshold_bits(x, 11, 2, mask_thresh=t_dev, maxval=maxval)
+            assert_same(host(backend, bits), host(backend, backend.adaptive_threshold_bits(x, 11, 2)), f"bits with mask {shape}")
+            frames = a if a.ndim == 3 else a[None]
+            want = np.stack([O.threshold_binary(f, t, maxval) for f, t in zip(frames, ts)]).reshape(a.shape)
+            assert_same(host(backend, mask), want, f"fused threshold mask {shape} t={ts} maxval={maxval}")
+    # the fused segmentation entry returns the same labels and the mask
+    a = np.stack([synth.nuclei(512, 512, seed=s) for s in (3, 4)])
+    x = dev(backend, a)
+    t, _ = backend.otsu_threshold(x, want_image=False)
+    labels, counts, mask = backend.segment_fused(x, 11, 2, 5, 1, mask_thresh=t, maxval=255)
+    l2, c2 = backend.segment_fused(x, 11, 2, 5, 1)
+    assert_same(host(backend, labels), host(backend, l2), "segment_fused labels with mask")
+    assert host(backend, counts).tolist() == host(backend, c2).tolist()
+    assert_same(host(backend, mask), np.stack([O.otsu_threshold(f, 255)[1] for f in a]), "segment_fused Otsu mask")
+
+
 @pytest.mark.parametrize("k,it", [(1, 1), (2, 1), (3, 1), (3, 2), (3, 3), (4, 2), (5, 1), (7, 1), (5, 3), (9, 2), (15, 3), (31, 2)])
 def test_bits_morph(backend, rng, k, it):
     for shape in ((64, 64), (33, 71), (130, 257), (70, 1200), (37, 2000)):

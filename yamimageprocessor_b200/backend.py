@@ -657,17 +657,26 @@ class Backend:
         return out
 
     # ------------------------------------------------------------------ fused binary segmentation
-    def adaptive_threshold_bits(self, img, block_size: int = 11, C_: float = 2.0):
-        """Adaptive threshold with a 1-bit-per-pixel result: int32 tensor (..., h, ceil(w/32))."""
+    def adaptive_threshold_bits(self, img, block_size: int = 11, C_: float = 2.0, mask_thresh=None, maxval: float = 255.0):
+        """Adaptive threshold with a 1-bit-per-pixel result: int32 tensor (..., h, ceil(w/32)).
+
+        ``mask_thresh`` (int32[n] on the device, e.g. the Otsu thresholds): also return the global threshold
+        mask ``img > t[frame] ? maxval : 0`` (= ``threshold_frames``), written in the same pass over ``img``;
+        the result is then ``(bits, mask)``."""
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8, torch.uint16))
         n, h, w = self._nhw(img)
         wpr = (w + 31) // 32
         shape = (h, wpr) if img.dim() == 2 else (n, h, wpr)
         bits = torch.empty(shape, dtype=torch.int32, device=self.device)
-        self._call("yam_adaptive_threshold_bits", self._p(img), self._p(bits), n, h, w, _dtype_code(img),
-                   int(block_size), float(C_))
-        return bits
+        if mask_thresh is None:
+            self._call("yam_adaptive_threshold_bits", self._p(img), self._p(bits), n, h, w, _dtype_code(img),
+                       int(block_size), float(C_))
+            return bits
+        mask = torch.empty_like(img)
+        self._call("yam_adaptive_threshold_bits_mask", self._p(img), self._p(bits), n, h, w, _dtype_code(img),
+                   int(block_size), float(C_), self._p(mask_thresh), self._p(mask), float(maxval))
+        return bits, mask
 
     def bits_morph(self, bits, width: int, op: int, kernel_size: int = 3, iterations: int = 1):
         """Rectangular erode / dilate / open / close / open+close (op = MORPH_* or 4) on packed bits."""
@@ -744,13 +753,19 @@ class Backend:
                        self._p(labels))
         return labels
 
-    def segment_fused(self, img, block_size: int = 11, C_: float = 2.0, morph_ksize: int = 5, iterations: int = 1):
+    def segment_fused(self, img, block_size: int = 11, C_: float = 2.0, morph_ksize: int = 5, iterations: int = 1,
+                      mask_thresh=None, maxval: float = 255.0):
         """adaptive threshold -> open -> close (rectangular) -> connected components, the mask never
-        leaving its 1-bit-per-pixel form.  Same labels as the unfused chain."""
+        leaving its 1-bit-per-pixel form.  Same labels as the unfused chain.  ``mask_thresh`` (int32[n] on the
+        device): the first kernel also writes the global threshold mask of ``img`` (see
+        ``adaptive_threshold_bits``); the result is then ``(labels, counts, mask)``."""
         w = int(img.shape[-1])
-        bits = self.adaptive_threshold_bits(img, block_size, C_)
-        bits = self.bits_morph(bits, w, 4, morph_ksize, iterations)
-        return self.ccl_label_bits(bits, w)
+        if mask_thresh is None:
+            bits = self.adaptive_threshold_bits(img, block_size, C_)
+            return self.ccl_label_bits(self.bits_morph(bits, w, 4, morph_ksize, iterations), w)
+        bits, mask = self.adaptive_threshold_bits(img, block_size, C_, mask_thresh=mask_thresh, maxval=maxval)
+        labels, counts = self.ccl_label_bits(self.bits_morph(bits, w, 4, morph_ksize, iterations), w)
+        return labels, counts, mask
 
     # ------------------------------------------------------------------ K10 / K11
     def ccl_label(self, mask):

@@ -147,10 +147,14 @@ __device__ __forceinline__ float2 row_dot2(const float2* x, const Taps16& t) {
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename Tin, int KS>
+// MASK: the kernel also writes the GLOBAL threshold mask of the same pixels (dst = src > t[frame] ? maxval : 0,
+// cv2.threshold(..., THRESH_BINARY) with the Otsu value that is already on the device): the raw tile is in shared
+// memory anyway, so the separate threshold pass (one more read of the image, DRAM-bound) disappears.
+template <typename Tin, int KS, bool MASK>
 __global__ void __launch_bounds__(kThreads, 1)
 adaptive_bits_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint16_t* __restrict__ bits16, int h, int w,
-                         int wpr, Taps16 taps, int ci, int tiles_x, int tiles_y, int total_tiles) {
+                         int wpr, Taps16 taps, int ci, int tiles_x, int tiles_y, int total_tiles,
+                         const int32_t* __restrict__ t_dev, uint16_t* __restrict__ mask_out, uint32_t mv2) {
     typedef TileGeom<KS> G;
     typedef LaneGeom<Tin> L;
     constexpr int R = G::R, TH = G::TH, ROWS = G::ROWS, RP = G::RP, RB = G::RB;
@@ -224,9 +228,29 @@ adaptive_bits_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint16_t* __r
         constexpr int ROUNDS = (RP + kThreads / 32 - 1) / (kThreads / 32);
         // software pipeline: the window (load, convert, halo shuffles) of round it + 1 is prepared
         // before the 88 packed FMAs of round it are issued, so LDS / SHFL latency hides behind them
+        // MASK: the lane has 8 raw pixels of two rows in hand here: the global threshold mask of those 16 pixels
+        // goes out from the H pass (two 16-byte streaming stores per lane and row pair, spread over the FMA-bound
+        // rounds; a separate store loop after the V pass ran at DRAM write speed with nothing to overlap it)
+        const int tv = MASK ? t_dev[frame] : 0;
+        const bool m_all = tv < 0;                                 // src > t holds for every pixel
+        const uint32_t t2 = (uint32_t)min(max(tv, 0), 65535) * 0x10001u;
+        auto mask_row = [&](const uint4& q, int row) {             // row = tile row (0 .. ROWS), this lane's 8 pixels
+            const int gy = y0 - R + row, gx = x0 + 8 * m;
+            if (row < R || row >= R + TH || gy >= h || m < 0 || m >= OUTW / 8 || gx >= w) return;
+            uint4 o;
+            o.x = m_all ? mv2 : (__vcmpgtu2(q.x, t2) & mv2);
+            o.y = m_all ? mv2 : (__vcmpgtu2(q.y, t2) & mv2);
+            o.z = m_all ? mv2 : (__vcmpgtu2(q.z, t2) & mv2);
+            o.w = m_all ? mv2 : (__vcmpgtu2(q.w, t2) & mv2);
+            yam_st_stream(reinterpret_cast<uint4*>(mask_out + ((int64_t)frame * h + gy) * w + gx), o);
+        };
         auto prepare = [&](int it, float2* e) {
             const int rp = min(warp + it * kWarps, RP - 1);
             const Tin* ra = s_raw + (2 * rp) * kBoxW + 8 * lane;
+            if (MASK && sizeof(Tin) == 2 && warp + it * kWarps < RP) {
+                mask_row(*reinterpret_cast<const uint4*>(ra), 2 * rp);
+                mask_row(*reinterpret_cast<const uint4*>(ra + kBoxW), 2 * rp + 1);
+            }
             load_convert8<Tin>(ra, ra + kBoxW, e + R);
 #pragma unroll
             for (int i = 0; i < R; i++) {
@@ -348,7 +372,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 template <typename Tin, int KS>
-int launch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, const Taps16& taps, int idelta) {
+int launch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, const Taps16& taps, int idelta,
+           const int32_t* t_dev, uint16_t* mask_out, uint32_t mv2) {
     typedef TileGeom<KS> G;
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -364,7 +389,8 @@ int launch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h, i
         return YAM_ECUDA;
     }
     constexpr size_t smem = tile_smem<Tin, KS>();
-    YAM_CUDA(cudaFuncSetAttribute(adaptive_bits_tma_kernel<Tin, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YAM_CUDA(cudaFuncSetAttribute(adaptive_bits_tma_kernel<Tin, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YAM_CUDA(cudaFuncSetAttribute(adaptive_bits_tma_kernel<Tin, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int wpr = (int)((w + 31) / 32);
     // 16-bit units past the last tile column (w % 32 != 0 only) are never written by a tile: clear them
     constexpr int kOutW = LaneGeom<Tin>::OUTW;
@@ -377,22 +403,27 @@ int launch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h, i
         return YAM_EINVAL;
     }
     const unsigned grid = (unsigned)(total < ctx->num_sms ? total : ctx->num_sms);   // persistent: one CTA per SM
-    adaptive_bits_tma_kernel<Tin, KS><<<grid, kThreads, smem, ctx->stream>>>(map, reinterpret_cast<uint16_t*>(bits), (int)h, (int)w,
-                                                                             wpr, taps, 0x4B400000 + idelta, tiles_x, tiles_y,
-                                                                             (int)total);
+    if (mask_out)
+        adaptive_bits_tma_kernel<Tin, KS, true><<<grid, kThreads, smem, ctx->stream>>>(
+            map, reinterpret_cast<uint16_t*>(bits), (int)h, (int)w, wpr, taps, 0x4B400000 + idelta, tiles_x, tiles_y, (int)total,
+            t_dev, mask_out, mv2);
+    else
+        adaptive_bits_tma_kernel<Tin, KS, false><<<grid, kThreads, smem, ctx->stream>>>(
+            map, reinterpret_cast<uint16_t*>(bits), (int)h, (int)w, wpr, taps, 0x4B400000 + idelta, tiles_x, tiles_y, (int)total,
+            nullptr, nullptr, 0u);
     YAM_LAUNCHED(ctx);
     return YAM_OK;
 }
 
 template <typename Tin>
 int dispatch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, int ks, const Taps16& taps,
-             int idelta) {
+             int idelta, const int32_t* t_dev, uint16_t* mask_out, uint32_t mv2) {
     switch (ks) {
-        case 3: return launch<Tin, 3>(ctx, src, bits, n, h, w, taps, idelta);
-        case 5: return launch<Tin, 5>(ctx, src, bits, n, h, w, taps, idelta);
-        case 7: return launch<Tin, 7>(ctx, src, bits, n, h, w, taps, idelta);
-        case 11: return launch<Tin, 11>(ctx, src, bits, n, h, w, taps, idelta);
-        case 15: return launch<Tin, 15>(ctx, src, bits, n, h, w, taps, idelta);
+        case 3: return launch<Tin, 3>(ctx, src, bits, n, h, w, taps, idelta, t_dev, mask_out, mv2);
+        case 5: return launch<Tin, 5>(ctx, src, bits, n, h, w, taps, idelta, t_dev, mask_out, mv2);
+        case 7: return launch<Tin, 7>(ctx, src, bits, n, h, w, taps, idelta, t_dev, mask_out, mv2);
+        case 11: return launch<Tin, 11>(ctx, src, bits, n, h, w, taps, idelta, t_dev, mask_out, mv2);
+        case 15: return launch<Tin, 15>(ctx, src, bits, n, h, w, taps, idelta, t_dev, mask_out, mv2);
     }
     return YAM_EINVAL;
 }
@@ -403,9 +434,12 @@ int dispatch(yam_ctx* ctx, const Tin* src, uint32_t* bits, int64_t n, int64_t h,
 // shape does not qualify (the caller then uses sep_f32_tiled): rows must be 16-byte multiples of a
 // 16-byte aligned base (tensor-map rule), the frame at least one box wide and high, block size one
 // of 3, 5, 7, 11, 15, and the integer compare needs |C| < 2^20.
+// t_dev / mask_out (both or neither; 16-bit input only): also write the global threshold mask, see the kernel.
 int yam_adaptive_bits_tma(yam_ctx* ctx, const void* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, int dtype,
-                          int block_size, const float* taps_f, int idelta, int* handled) {
+                          int block_size, const float* taps_f, int idelta, int* handled, const int32_t* t_dev, void* mask_out,
+                          double maxval) {
     *handled = 0;
+    if (mask_out && (dtype != YAM_U16 || !t_dev)) return YAM_OK;
     const int es = dtype == YAM_U8 ? 1 : 2;
     const bool ks_ok = block_size == 3 || block_size == 5 || block_size == 7 || block_size == 11 || block_size == 15;
     if (!ks_ok || (dtype != YAM_U8 && dtype != YAM_U16)) return YAM_OK;
@@ -416,8 +450,11 @@ int yam_adaptive_bits_tma(yam_ctx* ctx, const void* src, uint32_t* bits, int64_t
     if (!encode_tiled()) return YAM_OK;
     Taps16 taps;
     for (int i = 0; i < 16; i++) taps.v[i] = i < block_size ? taps_f[i] : 0.0f;
-    const int rc = dtype == YAM_U8 ? dispatch<uint8_t>(ctx, (const uint8_t*)src, bits, n, h, w, block_size, taps, idelta)
-                                   : dispatch<uint16_t>(ctx, (const uint16_t*)src, bits, n, h, w, block_size, taps, idelta);
+    const double mr = rint(maxval);
+    const uint32_t mv2 = (uint32_t)(mr < 0 ? 0 : mr > 65535 ? 65535 : mr) * 0x10001u;
+    const int rc = dtype == YAM_U8 ? dispatch<uint8_t>(ctx, (const uint8_t*)src, bits, n, h, w, block_size, taps, idelta, nullptr, nullptr, 0u)
+                                   : dispatch<uint16_t>(ctx, (const uint16_t*)src, bits, n, h, w, block_size, taps, idelta, t_dev,
+                                                        (uint16_t*)mask_out, mv2);
     if (rc == YAM_OK) *handled = 1;
     return rc;
 }

@@ -10,6 +10,10 @@
 
 #include "yam_common.cuh"
 #include "yam_host.h"
+
+// yam_pointwise.cu: dst = src > t_dev[frame] ? maxval : 0 per frame
+int yam_threshold_dev(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t frame_px, int dtype,
+                      const int32_t* t_dev, double maxval);
 #include "yam_median_net.h"
 
 namespace {
@@ -884,9 +888,25 @@ int yam_adaptive_threshold(yam_ctx* ctx, const void* src, void* dst, int64_t n, 
                                                         block_size, YAM_BORDER_REPLICATE, 65535, idelta);
 }
 
+static int adaptive_threshold_bits_impl(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h, int64_t w,
+                                        int dtype, int block_size, double C, const int32_t* t_dev, void* mask_out, double maxval);
+
 int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h, int64_t w,
                                 int dtype, int block_size, double C) {
     if (int rc = yam_enter(ctx)) return rc;
+    return adaptive_threshold_bits_impl(ctx, src, bits_out, n, h, w, dtype, block_size, C, nullptr, nullptr, 0.0);
+}
+
+int yam_adaptive_threshold_bits_mask(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h, int64_t w,
+                                     int dtype, int block_size, double C, const int32_t* thresh_dev, void* mask_out,
+                                     double maxval) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(thresh_dev && mask_out && mask_out != src && n <= 65535, "adaptive_threshold_bits_mask: bad arguments");
+    return adaptive_threshold_bits_impl(ctx, src, bits_out, n, h, w, dtype, block_size, C, thresh_dev, mask_out, maxval);
+}
+
+static int adaptive_threshold_bits_impl(yam_ctx* ctx, const void* src, uint32_t* bits_out, int64_t n, int64_t h, int64_t w,
+                                        int dtype, int block_size, double C, const int32_t* t_dev, void* mask_out, double maxval) {
     if (int rc = check_shape(src, bits_out, n, h, w, "adaptive_threshold_bits")) return rc;
     YAM_REQUIRE((block_size & 1) && block_size >= 3 && block_size <= YAM_MAX_TAPS,
                 "adaptive_threshold_bits: block_size must be odd in [3,%d], got %d", YAM_MAX_TAPS, block_size);
@@ -899,9 +919,18 @@ int yam_adaptive_threshold_bits(yam_ctx* ctx, const void* src, uint32_t* bits_ou
     YAM_REQUIRE(dtype == YAM_U8 || dtype == YAM_U16, "adaptive_threshold_bits: unsupported dtype %d", dtype);
     {
         int handled = 0;  // TMA-staged kernel (yam_adaptive.cu) for the shapes a tensor map can describe
-        if (int rc = yam_adaptive_bits_tma(ctx, src, bits_out, n, h, w, dtype, block_size, taps.v, idelta, &handled)) return rc;
+        // the fused mask exists for 16-bit input; 8-bit input (and shapes the TMA kernel does not take) get the
+        // mask from the plain threshold kernel
+        const bool fuse_mask = mask_out && dtype == YAM_U16;
+        if (int rc = yam_adaptive_bits_tma(ctx, src, bits_out, n, h, w, dtype, block_size, taps.v, idelta, &handled,
+                                           fuse_mask ? t_dev : nullptr, fuse_mask ? mask_out : nullptr, maxval))
+            return rc;
+        if (handled && mask_out && !fuse_mask)
+            if (int rc = yam_threshold_dev(ctx, src, mask_out, n, h * w, dtype, t_dev, maxval)) return rc;
         if (handled) return YAM_OK;
     }
+    if (mask_out)
+        if (int rc = yam_threshold_dev(ctx, src, mask_out, n, h * w, dtype, t_dev, maxval)) return rc;
     if (dtype == YAM_U8)
         return launch_f32<uint8_t, uint8_t, FEPI_ADAPTIVE_BITS>(ctx, (const uint8_t*)src, (uint8_t*)nullptr, n, h, w, taps,
                                                                 block_size, YAM_BORDER_REPLICATE, 255, idelta, bits_out, wpr);

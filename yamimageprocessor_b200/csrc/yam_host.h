@@ -19,7 +19,8 @@ void yam_host_otsu_group(const void* hists, size_t stride_bytes, int count, int 
 // does not qualify and the caller must use the generic tiled kernel
 struct yam_ctx;
 int yam_adaptive_bits_tma(yam_ctx* ctx, const void* src, uint32_t* bits, int64_t n, int64_t h, int64_t w, int dtype,
-                          int block_size, const float* taps_f, int idelta, int* handled);
+                          int block_size, const float* taps_f, int idelta, int* handled, const int32_t* t_dev, void* mask_out,
+                          double maxval);
 // TMA fast path of the 16-bit fixed-point Gaussian (yam_gauss_tma.cu); *handled = 0 -> use sep_fixed_tiled
 int yam_gauss16_tma(yam_ctx* ctx, const void* src, void* dst, int64_t n, int64_t h, int64_t w, int ksize,
                     const uint32_t* taps_q, int border, int* handled);

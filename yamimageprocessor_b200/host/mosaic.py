@@ -279,7 +279,11 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     # segmentation on the extended rows, cropped to the core
     # (the binary mask stays 1 bit/pixel from the threshold through open/close into the labelling;
     # cropping whole rows of the packed mask is a view, not a copy)
-    bits = be.bits_morph(be.adaptive_threshold_bits(c, p.block_size, p.C), W, 4, p.morph_ksize, 1)
+    # (the adaptive kernel has every pixel of c staged in shared memory: it writes the Otsu mask of the same rows in
+    # the same pass -- the threshold is on the device by now -- instead of a separate DRAM-bound threshold pass)
+    raw_bits, otsu_ext = be.adaptive_threshold_bits(c, p.block_size, p.C, mask_thresh=t_dev, maxval=255)
+    otsu_mask = otsu_ext[c0 - a0: c1 - a0]
+    bits = be.bits_morph(raw_bits, W, 4, p.morph_ksize, 1)
     bits_core = bits[c0 - a0: c1 - a0]
     # labelling in two steps: resolve now, write the label image once the global numbering is known.
     # The labeller indexes pixels with 32 bits, so a strip of 2^31 pixels or more (65536^2 on one or two
@@ -308,14 +312,11 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
             pack[i, 2 * W:2 * W + 1].copy_(cnt_i)
         packed = comm.all_gather(pack).reshape(-1, stride) if comm is not None else pack
         mark("boundary_all_gather")
-        # The host needs the counts only to size the tables.  They are read back asynchronously and the
-        # Otsu mask kernel is enqueued behind the copy, so the GPU has work while the host waits.
+        # The host needs the counts only to size the tables.
         cnt_host = torch.empty((int(packed.shape[0]),), dtype=torch.int32, pin_memory=True)
         cnt_host.copy_(packed[:, 2 * W], non_blocking=True)
         cnt_ready = torch.cuda.Event()
         cnt_ready.record()
-        otsu_mask = be.threshold_frames(c_core, t_dev, 255)
-        mark("otsu")
         cnt_ready.synchronize()
         offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
         # union of the ids that touch across (sub-)strip boundaries + raster-first renumbering: one
@@ -329,8 +330,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         for i, (b, ws_i, cnt_i) in enumerate(subs):
             be.ccl_emit(b, W, ws_i, remap=remaps[i], out=labels[i * sub_rows:(i + 1) * sub_rows])
     else:
-        otsu_mask = be.threshold_frames(c_core, t_dev, 255)
-        mark("otsu")
         b, ws_i, total_dev = subs[0]
         labels = be.ccl_emit(b, W, ws_i)
     mark("emit")
