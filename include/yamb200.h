@@ -227,6 +227,11 @@ int yam_ccl_resolve_bits(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t 
 int yam_ccl_emit_rows(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w,
                       const void* workspace, const int32_t* remap_dev, int64_t row_begin, int64_t row_end,
                       int32_t* labels);
+/* the same with the table length stated (remap_size > 0): local labels >= remap_size map to 0 instead of
+ * reading past the table (tables sized from bounds, yam_merge_strips_remap_bounded) */
+int yam_ccl_emit_rows_bounded(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w,
+                              const void* workspace, const int32_t* remap_dev, int64_t remap_size,
+                              int64_t row_begin, int64_t row_end, int32_t* labels);
 
 /* labels[i] = remap_dev[labels[i]] for labels in (0, remap_size); used by the cross-strip label merge */
 int yam_relabel(yam_ctx* ctx, int32_t* labels, int64_t count, const int32_t* remap_dev,
@@ -254,6 +259,15 @@ int64_t yam_merge_strips_workspace_bytes(int64_t total);
 int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
                            const int64_t* offsets_host, int rank, int rank_count, void* workspace,
                            int32_t* remap_dev, int32_t* total_dev);
+/* The same without the host ever learning the counts: offsets_bound_host are exclusive prefixes of per-strip UPPER
+ * BOUNDS (e.g. from the previous run over the same source), the real counts stay on the device
+ * (counts_dev[r * counts_stride], r < world).  Ids between a count and its bound take no rank, so remap / total are
+ * the same as with exact offsets; *overflow_dev = 1 when a count exceeds its bound (results are then unusable and the
+ * caller repeats the merge with exact offsets).  Tables hold bound_r + 1 entries per strip. */
+int yam_merge_strips_remap_bounded(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                                   const int64_t* offsets_bound_host, const int32_t* counts_dev, int64_t counts_stride,
+                                   int rank, int rank_count, void* workspace, int32_t* remap_dev, int32_t* total_dev,
+                                   int32_t* overflow_dev);
 
 /* Interleaved (px, channels) <-> planar (channels, px) copies, channels <= 4: cv2's neighbourhood
  * filters (GaussianBlur, medianBlur, blur, erode / dilate, modules/preprocessing.py:140-150) treat the

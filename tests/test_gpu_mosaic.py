@@ -66,6 +66,36 @@ def test_sharded_mosaic_with_labelling_sub_strips(backend, world):
     assert np.array_equal(backend.to_host(res[0].props), want_props)
 
 
+def test_repeated_runs_size_the_merge_from_learnt_bounds(backend):
+    """Second run over a same-shaped source: the merge tables are sized from the previous counts and the real
+    counts stay on the device (yam_merge_strips_remap_bounded, no host wait).  Same labels as the first run and
+    as the dense run, with tight and with very loose bounds; bounds that are too small overflow and the merge
+    falls back to exact sizes."""
+    p = mosaic.MosaicParams(count_bound_slack=(0.0, 1))
+    frame = synth.nuclei(1024, 768, seed=21)
+    frame[:, 300:303] = 60000
+    want = dense(backend, frame, p)
+
+    def check(res, what):
+        assert all(r.n_components == want[4] for r in res), what
+        assert np.array_equal(np.concatenate([backend.to_host(r.labels) for r in res]), want[3]), what
+
+    for world in (4, 1):
+        pp = mosaic.MosaicParams(ccl_max_px=768 * 256, count_bound_slack=(0.0, 1)) if world == 1 else p   # world 1: four sub-strips
+        mosaic._COUNT_BOUNDS.clear()
+        for attempt in range(3):                                   # exact, then bounded with bound = count + 1
+            check(mosaic.run_emulated(backend, frame, world, pp), (world, "attempt", attempt))
+            assert len(mosaic._COUNT_BOUNDS) == 1
+        (key, learnt), = mosaic._COUNT_BOUNDS.items()
+        assert learnt.shape == (4,) and int(learnt.sum()) >= want[4]
+        mosaic._COUNT_BOUNDS[key] = learnt * 10 + 1000            # very loose bounds: large gaps in the id space
+        check(mosaic.run_emulated(backend, frame, world, pp), (world, "loose"))
+        mosaic._COUNT_BOUNDS[key] = np.maximum(learnt // 2, 1)     # too small: overflow -> exact merge
+        check(mosaic.run_emulated(backend, frame, world, pp), (world, "overflow"))
+        assert np.array_equal(mosaic._COUNT_BOUNDS[key], learnt)   # re-learnt from the real counts
+    mosaic._COUNT_BOUNDS.clear()
+
+
 def test_dense_chain_matches_oracle(backend):
     """anchor: the dense chain the sharded path is compared with equals the CPU oracle"""
     p = mosaic.MosaicParams()

@@ -478,12 +478,17 @@ class Backend:
         self._call("yam_merge_strip_labels", self._p(edges), self._p(offsets), world, w, total, self._p(root))
         return root
 
-    def merge_strips_remap(self, packed, width: int, offsets: Sequence[int], rank: int, count: int = 1):
+    def merge_strips_remap(self, packed, width: int, offsets: Sequence[int], rank: int, count: int = 1, counts_dev=None):
         """Cross-strip label merge + raster-first renumbering in one call (yam_merge_strips_remap).
         ``packed`` int32 [world, stride >= 2*width]: first and last label row of every strip;
         ``offsets`` host ints [world + 1].  Returns (remaps, total int32[1]): ``remaps`` is the int32
         table of strip ``rank`` (count_rank + 1 entries) or, for ``count`` > 1, the list of tables of
-        strips rank .. rank + count - 1 (views of one buffer)."""
+        strips rank .. rank + count - 1 (views of one buffer).
+
+        ``counts_dev`` (a strided int32 device view with one real count per strip): ``offsets`` are then prefixes
+        of UPPER BOUNDS and the host never needs the counts (yam_merge_strips_remap_bounded); the result is
+        ``(remaps, total, overflow int32[1])`` -- overflow != 0 means a count exceeded its bound and the merge
+        has to be repeated with exact offsets."""
         torch = _torch()
         packed = self._check(packed, ndim=(2,), dtypes=(torch.int32,), name="packed")
         world, stride = int(packed.shape[0]), int(packed.shape[1])
@@ -497,15 +502,24 @@ class Backend:
         sizes = [int(offs[r + 1] - offs[r]) + 1 for r in range(rank, rank + count)]
         remap = torch.empty((sum(sizes),), dtype=torch.int32, device=self.device)
         total = torch.empty((1,), dtype=torch.int32, device=self.device)
-        self._call("yam_merge_strips_remap", self._p(packed), stride, world, int(width),
-                   offs.ctypes.data_as(C.c_void_p), int(rank), int(count), self._p(ws), self._p(remap), self._p(total))
+        overflow = None
+        if counts_dev is None:
+            self._call("yam_merge_strips_remap", self._p(packed), stride, world, int(width),
+                       offs.ctypes.data_as(C.c_void_p), int(rank), int(count), self._p(ws), self._p(remap), self._p(total))
+        else:
+            if counts_dev.dtype != torch.int32 or counts_dev.dim() != 1 or int(counts_dev.shape[0]) != world:
+                raise TypeError("counts_dev must be an int32 device vector with one entry per strip")
+            overflow = torch.empty((1,), dtype=torch.int32, device=self.device)
+            self._call("yam_merge_strips_remap_bounded", self._p(packed), stride, world, int(width),
+                       offs.ctypes.data_as(C.c_void_p), self._p(counts_dev), int(counts_dev.stride(0)), int(rank), int(count),
+                       self._p(ws), self._p(remap), self._p(total), self._p(overflow))
         if count == 1:
-            return remap, total
+            return (remap, total) if overflow is None else (remap, total, overflow)
         views, at = [], 0
         for n in sizes:
             views.append(remap[at:at + n])
             at += n
-        return views, total
+        return (views, total) if overflow is None else (views, total, overflow)
 
     # ------------------------------------------------------------------ watershed front half
     def threshold_inv(self, img, thresh: float = 0.0, maxval: float = 255.0, t_dev=None):
@@ -749,8 +763,10 @@ class Backend:
             remap = self._check(remap, ndim=(1,), dtypes=(torch.int32,), name="remap")
             rptr = self._p(remap)
         if r1 > r0:
-            self._call("yam_ccl_emit_rows", self._p(bits), n, h, int(width), self._p(workspace), rptr, r0, r1,
-                       self._p(labels))
+            # the table length travels with the table: a local label beyond it maps to 0 instead of reading past
+            # the allocation (tables sized from bounds whose overflow is only detected afterwards)
+            self._call("yam_ccl_emit_rows_bounded", self._p(bits), n, h, int(width), self._p(workspace), rptr,
+                       int(remap.numel()) if remap is not None else 0, r0, r1, self._p(labels))
         return labels
 
     def segment_fused(self, img, block_size: int = 11, C_: float = 2.0, morph_ksize: int = 5, iterations: int = 1,

@@ -694,9 +694,10 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
                                                                   const uint32_t* __restrict__ frame_off, CclGeom g,
                                                                   const int* __restrict__ P,
                                                                   int32_t* __restrict__ labels,
-                                                                  const int32_t* __restrict__ remap,
+                                                                  const int32_t* __restrict__ remap, int remap_size,
                                                                   int64_t word_begin, int64_t word_end) {
     // words [word_begin, word_end) are written; labels points at the pixel of word_begin
+    // (remap_size > 0: labels beyond the table map to 0 instead of reading past it -- bounded merge tables)
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = word_begin + ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
     if (warp_base >= word_end) return;
@@ -723,8 +724,8 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
         l0 = -v0 - off;
         l1 = -v1 - off;
         if (remap) {  // strip-local label -> global label (cross-strip merge)
-            l0 = __ldg(remap + l0);
-            if (nseg > 1) l1 = __ldg(remap + l1);
+            l0 = (remap_size <= 0 || l0 < remap_size) ? __ldg(remap + l0) : 0;
+            if (nseg > 1) l1 = (remap_size <= 0 || l1 < remap_size) ? __ldg(remap + l1) : 0;
         }
     }
     // bits that belong to the second (or a later) segment
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(kThreads) ccl_final_warp_kernel(const uint32_t
                 int v = __ldg(P + base + k);
                 if (v >= 0) v = __ldg(P + v);
                 cur = -v - off;
-                if (remap) cur = __ldg(remap + cur);
+                if (remap) cur = (remap_size <= 0 || cur < remap_size) ? __ldg(remap + cur) : 0;
                 k++;
             }
             d[i] = ((b >> i) & 1u) ? cur : 0;
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
                                                              const uint32_t* __restrict__ nbase,
                                                              const uint32_t* __restrict__ frame_off, CclGeom g,
                                                              const int* __restrict__ P, int32_t* __restrict__ labels,
-                                                             bool vec_ok, const int32_t* __restrict__ remap,
+                                                             bool vec_ok, const int32_t* __restrict__ remap, int remap_size,
                                                              int64_t word_begin, int64_t word_end) {
     // words [word_begin, word_end) (whole rows) are written; labels points at the first pixel of that range
     const int64_t t_base = word_begin * 8 + (int64_t)blockIdx.x * (kThreads * kFinalIter) + threadIdx.x;
@@ -804,8 +805,8 @@ __global__ void __launch_bounds__(kThreads) ccl_final_kernel(const uint32_t* __r
             if (v1 >= 0) v1 = __ldg(P + v1);
             int l0 = -v0 - off, l1 = -v1 - off;
             if (remap) {
-                l0 = __ldg(remap + l0);
-                if (second) l1 = __ldg(remap + l1);
+                l0 = (remap_size <= 0 || l0 < remap_size) ? __ldg(remap + l0) : 0;
+                if (second) l1 = (remap_size <= 0 || l1 < remap_size) ? __ldg(remap + l1) : 0;
             }
             out.x = (nib & 1u) ? ((second & 1u) ? l1 : l0) : 0;
             out.y = (nib & 2u) ? ((second & 2u) ? l1 : l0) : 0;
@@ -1053,6 +1054,38 @@ __global__ void __launch_bounds__(kThreads) merge_init_kernel(int32_t* __restric
     if (i < nwords) nonroot[i] = 0u;
 }
 
+// The same when the offsets are UPPER BOUNDS (offs.v[r + 1] - offs.v[r] >= the strip's real count, which only
+// the device knows: counts[r * counts_stride]): ids between a strip's count and its bound do not exist and are
+// marked non-root, so they take no rank.  *overflow = 1 if a count exceeds its bound (the caller then redoes
+// the merge with exact offsets).
+__global__ void __launch_bounds__(kThreads) merge_init_bounded_kernel(int32_t* __restrict__ P, int64_t count,
+                                                                      uint32_t* __restrict__ nonroot, int64_t nwords,
+                                                                      StripOffsets offs, int world,
+                                                                      const int32_t* __restrict__ counts, int64_t counts_stride,
+                                                                      int32_t* __restrict__ overflow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) P[i] = (int32_t)i;
+    if (i < nwords) {
+        uint32_t m = 0;
+        const int64_t id0 = i * 32;
+        int r = 0;
+        while (r < world && offs.v[r + 1] < id0) r++;          // strip r holds ids (offs[r], offs[r + 1]]
+        for (int b = 0; b < 32; b++) {
+            const int64_t id = id0 + b;
+            if (id == 0 || id >= count) continue;
+            while (r < world && offs.v[r + 1] < id) r++;
+            if (r < world && id - offs.v[r] > (int64_t)counts[(int64_t)r * counts_stride]) m |= 1u << b;
+        }
+        nonroot[i] = m;
+    }
+    if (i == 0) {
+        int bad = 0;
+        for (int r = 0; r < world; r++)
+            if ((int64_t)counts[(int64_t)r * counts_stride] > offs.v[r + 1] - offs.v[r]) bad = 1;
+        *overflow = bad;
+    }
+}
+
 // thread = (boundary r | r+1, column x) over the packed rows [world][stride]: row 0 = first label row,
 // row 1 = last label row of a strip
 __global__ void __launch_bounds__(kThreads) merge_union_kernel(const int32_t* __restrict__ packed, int64_t stride,
@@ -1063,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads) merge_union_kernel(const int32_t* __
     const int r = (int)(t / w);
     const int64_t x = t - (int64_t)r * w;
     const int32_t a = packed[(int64_t)r * stride + w + x];
-    if (a <= 0) return;
+    if (a <= 0 || a > offs.v[r + 1] - offs.v[r]) return;      // (beyond the strip's range: only with overflowed bounds)
     const int ga = (int)(offs.v[r] + a);
     const int32_t* top = packed + (int64_t)(r + 1) * stride;
     const long long ob = offs.v[r + 1];
@@ -1073,7 +1106,7 @@ __global__ void __launch_bounds__(kThreads) merge_union_kernel(const int32_t* __
         const int64_t xx = x + dx;
         if (xx < 0 || xx >= w) continue;
         const int32_t b = top[xx];
-        if (b > 0 && b != last) {
+        if (b > 0 && b != last && b <= offs.v[r + 2] - ob) {
             unite(P, ga, (int)(ob + b));
             last = b;
         }
@@ -1090,7 +1123,7 @@ __global__ void __launch_bounds__(kThreads) merge_flatten_kernel(const int32_t* 
     const int r = (int)(t / (2 * w));
     const int64_t x = t - (int64_t)r * 2 * w;
     const int32_t a = packed[(int64_t)r * stride + x];
-    if (a <= 0) return;
+    if (a <= 0 || a > offs.v[r + 1] - offs.v[r]) return;
     if (x > 0 && x != w && packed[(int64_t)r * stride + x - 1] == a) return;  // one thread per run of a label
     const int g = (int)(offs.v[r] + a);
     int cur = g, p = __ldcg(P + cur);
@@ -1168,10 +1201,30 @@ int64_t yam_merge_strips_workspace_bytes(int64_t total) {
     return (int64_t)yam_align_up((size_t)(total + 1) * 4, 256) + 2 * (int64_t)yam_align_up((size_t)nwords * 4, 256);
 }
 
+static int merge_strips_remap_impl(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                                   const int64_t* offsets_host, int rank, int rank_count, void* workspace, int32_t* remap_dev,
+                                   int32_t* total_dev, const int32_t* counts_dev, int64_t counts_stride, int32_t* overflow_dev);
+
 int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
                            const int64_t* offsets_host, int rank, int rank_count, void* workspace, int32_t* remap_dev,
                            int32_t* total_dev) {
     if (int rc = yam_enter(ctx)) return rc;
+    return merge_strips_remap_impl(ctx, packed_dev, stride, world, w, offsets_host, rank, rank_count, workspace, remap_dev, total_dev,
+                                   nullptr, 0, nullptr);
+}
+
+int yam_merge_strips_remap_bounded(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                                   const int64_t* offsets_bound_host, const int32_t* counts_dev, int64_t counts_stride, int rank,
+                                   int rank_count, void* workspace, int32_t* remap_dev, int32_t* total_dev, int32_t* overflow_dev) {
+    if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(counts_dev && counts_stride >= 1 && overflow_dev, "merge_strips_remap_bounded: NULL argument");
+    return merge_strips_remap_impl(ctx, packed_dev, stride, world, w, offsets_bound_host, rank, rank_count, workspace, remap_dev,
+                                   total_dev, counts_dev, counts_stride, overflow_dev);
+}
+
+static int merge_strips_remap_impl(yam_ctx* ctx, const int32_t* packed_dev, int64_t stride, int world, int64_t w,
+                                   const int64_t* offsets_host, int rank, int rank_count, void* workspace, int32_t* remap_dev,
+                                   int32_t* total_dev, const int32_t* counts_dev, int64_t counts_stride, int32_t* overflow_dev) {
     YAM_REQUIRE(packed_dev && offsets_host && workspace && remap_dev && total_dev, "merge_strips_remap: NULL argument");
     YAM_REQUIRE(world >= 1 && world <= 64 && w > 0 && stride >= 2 * w && rank >= 0 && rank_count >= 1 && rank + rank_count <= world,
                 "merge_strips_remap: bad geometry (world %d, w %lld, stride %lld, strips %d..+%d)", world, (long long)w,
@@ -1189,7 +1242,11 @@ int yam_merge_strips_remap(yam_ctx* ctx, const int32_t* packed_dev, int64_t stri
     uint32_t* nonroot = (uint32_t*)((char*)workspace + yam_align_up((size_t)count * 4, 256));
     uint32_t* prefix = (uint32_t*)((char*)nonroot + yam_align_up((size_t)nwords * 4, 256));
     const auto blocks = [](int64_t items) { return (unsigned)((items + kThreads - 1) / kThreads); };
-    merge_init_kernel<<<blocks(count), kThreads, 0, ctx->stream>>>(P, count, nonroot, nwords);
+    if (counts_dev)
+        merge_init_bounded_kernel<<<blocks(count), kThreads, 0, ctx->stream>>>(P, count, nonroot, nwords, offs, world, counts_dev,
+                                                                               counts_stride, overflow_dev);
+    else
+        merge_init_kernel<<<blocks(count), kThreads, 0, ctx->stream>>>(P, count, nonroot, nwords);
     YAM_LAUNCHED(ctx);
     if (world > 1) {
         merge_union_kernel<<<blocks((int64_t)(world - 1) * w), kThreads, 0, ctx->stream>>>(packed_dev, stride, offs,
@@ -1346,18 +1403,18 @@ static int ccl_resolve(yam_ctx* ctx, const void* mask, const uint32_t* bits_in, 
 
 // labels of the words [word_begin, word_end) (whole rows), optionally mapped through remap
 static int ccl_emit(yam_ctx* ctx, const uint32_t* bits, const CclGeom& g, const CclWorkspace& ws, int32_t* labels,
-                    const int32_t* remap, int64_t word_begin, int64_t word_end) {
+                    const int32_t* remap, int64_t word_begin, int64_t word_end, int remap_size = 0) {
     const int64_t words = word_end - word_begin;
     if (words <= 0) return YAM_OK;
     const bool lab_aligned = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
     if ((g.w & 31) == 0 && lab_aligned) {
         const unsigned wblocks32 = (unsigned)((words + kThreads - 1) / kThreads);  // 8 warps x 32 words
         ccl_final_warp_kernel<<<wblocks32, kThreads, 0, ctx->stream>>>(bits, ws.nbase, ws.frame_off, g, ws.P, labels, remap,
-                                                                      word_begin, word_end);
+                                                                      remap_size, word_begin, word_end);
     } else {
         const unsigned fblocks = (unsigned)((words * 8 + kThreads * kFinalIter - 1) / (kThreads * kFinalIter));
         ccl_final_kernel<<<fblocks, kThreads, 0, ctx->stream>>>(bits, ws.nbase, ws.frame_off, g, ws.P, labels,
-                                                                lab_aligned && (g.w & 3) == 0, remap, word_begin, word_end);
+                                                                lab_aligned && (g.w & 3) == 0, remap, remap_size, word_begin, word_end);
     }
     YAM_LAUNCHED(ctx);
     return YAM_OK;
@@ -1445,9 +1502,18 @@ int yam_ccl_resolve_bits(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t 
     return ccl_resolve(ctx, nullptr, bits, g, ws, counts_dev);
 }
 
+int yam_ccl_emit_rows_bounded(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, const void* workspace,
+                              const int32_t* remap_dev, int64_t remap_size, int64_t row_begin, int64_t row_end, int32_t* labels);
+
 int yam_ccl_emit_rows(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, const void* workspace,
                       const int32_t* remap_dev, int64_t row_begin, int64_t row_end, int32_t* labels) {
+    return yam_ccl_emit_rows_bounded(ctx, bits, n, h, w, workspace, remap_dev, 0, row_begin, row_end, labels);
+}
+
+int yam_ccl_emit_rows_bounded(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, int64_t w, const void* workspace,
+                              const int32_t* remap_dev, int64_t remap_size, int64_t row_begin, int64_t row_end, int32_t* labels) {
     if (int rc = yam_enter(ctx)) return rc;
+    YAM_REQUIRE(remap_size >= 0 && remap_size < (1ll << 31), "ccl_emit_rows: bad remap_size");
     YAM_REQUIRE(bits && workspace && labels, "ccl_emit_rows: NULL argument");
     CclGeom g;
     if (int rc = ccl_geometry(n, h, w, &g)) return rc;
@@ -1457,7 +1523,7 @@ int yam_ccl_emit_rows(yam_ctx* ctx, const uint32_t* bits, int64_t n, int64_t h, 
     YAM_REQUIRE(!remap_dev || n == 1, "ccl_emit_rows: a remap table applies to a single frame");
     CclWorkspace ws;
     ccl_layout(g, ctx->num_sms, (char*)const_cast<void*>(workspace), &ws);
-    return ccl_emit(ctx, bits, g, ws, labels, remap_dev, row_begin * g.wpr, row_end * g.wpr);
+    return ccl_emit(ctx, bits, g, ws, labels, remap_dev, row_begin * g.wpr, row_end * g.wpr, (int)remap_size);
 }
 
 int yam_region_props(yam_ctx* ctx, const int32_t* labels, const void* intensity, int intensity_dtype, int64_t h,

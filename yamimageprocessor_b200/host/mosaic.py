@@ -44,6 +44,8 @@ class MosaicParams:
     morph_ksize: int = 5
     ccl_max_px: int = _CCL_MAX_PX  # pixels per labelling call; larger strips are labelled as merged sub-strips
     trace: Any = None              # optional callable(phase_name, rank): profiling hook, called at phase ends
+    reuse_count_bounds: bool = True  # size the merge tables from the previous run over a same-shaped source (no host wait)
+    count_bound_slack: Tuple[float, int] = (0.25, 1024)   # bound = count * (1 + slack[0]) + slack[1] per (sub-)strip
 
 
 @dataclass
@@ -87,6 +89,11 @@ class TorchComm:
     def once(self, fn):
         """Host work whose inputs are identical on every strip of this process: run it once."""
         return fn()
+
+
+# per (source shape, sharding, segmentation parameters): upper bounds of the component counts of every (sub-)strip,
+# learnt from the previous run over such a source (MosaicParams.reuse_count_bounds)
+_COUNT_BOUNDS: dict = {}
 
 
 class LocalComm:
@@ -312,23 +319,43 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
             pack[i, 2 * W:2 * W + 1].copy_(cnt_i)
         packed = comm.all_gather(pack).reshape(-1, stride) if comm is not None else pack
         mark("boundary_all_gather")
-        # The host needs the counts only to size the tables.
+        labels = torch.empty((rows_core, W), dtype=torch.int32, device=be.device)
+        counts_view = packed[:, 2 * W]                      # one real count per (sub-)strip, on the device
         cnt_host = torch.empty((int(packed.shape[0]),), dtype=torch.int32, pin_memory=True)
-        cnt_host.copy_(packed[:, 2 * W], non_blocking=True)
+        cnt_host.copy_(counts_view, non_blocking=True)
         cnt_ready = torch.cuda.Event()
         cnt_ready.record()
-        cnt_ready.synchronize()
-        offs = np.concatenate([[0], np.cumsum(cnt_host.numpy().astype(np.int64))])
-        # union of the ids that touch across (sub-)strip boundaries + raster-first renumbering: one
-        # library call, small kernels, all on the device (yam_merge_strips_remap);
-        # the label image is written once, already in global numbering
-        labels = torch.empty((rows_core, W), dtype=torch.int32, device=be.device)
-        remaps, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub, k_sub)
-        mark("merge_remap")
-        if k_sub == 1:
-            remaps = [remaps]
-        for i, (b, ws_i, cnt_i) in enumerate(subs):
-            be.ccl_emit(b, W, ws_i, remap=remaps[i], out=labels[i * sub_rows:(i + 1) * sub_rows])
+        # The host needs the counts only to SIZE the merge tables.  A repeated run over a source of the same
+        # shape (time series of mosaics, the bench's steps) sizes them from the previous run's counts plus
+        # head room and leaves the real counts on the device (yam_merge_strips_remap_bounded): no host wait in
+        # the middle of the pipeline.  Every rank derives the same bounds from the same all-gathered counts.
+        hint_key = (H, W, world, k_sub, p.block_size, p.morph_ksize)
+        bounds = _COUNT_BOUNDS.get(hint_key) if p.reuse_count_bounds else None
+        overflow_dev = None
+
+        def emit_all(remaps):
+            for i, (b, ws_i, cnt_i) in enumerate(subs):
+                be.ccl_emit(b, W, ws_i, remap=remaps[i], out=labels[i * sub_rows:(i + 1) * sub_rows])
+
+        if bounds is not None:
+            offs = np.concatenate([[0], np.cumsum(bounds)])
+            remaps, total_dev, overflow_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub, k_sub, counts_dev=counts_view)
+            mark("merge_remap")
+            emit_all([remaps] if k_sub == 1 else remaps)
+        cnt_ready.synchronize()        # (with bounds: everything is enqueued by now, this wait costs nothing extra)
+        counts = cnt_host.numpy().astype(np.int64)
+        if bounds is None or int(overflow_dev[0].item()) != 0:
+            # first run over this shape, or a count outgrew its bound: exact offsets.
+            # union of the ids that touch across (sub-)strip boundaries + raster-first renumbering: one
+            # library call, small kernels, all on the device (yam_merge_strips_remap);
+            # the label image is written once, already in global numbering
+            offs = np.concatenate([[0], np.cumsum(counts)])
+            remaps, total_dev = be.merge_strips_remap(packed, W, offs, rank * k_sub, k_sub)
+            mark("merge_remap")
+            emit_all([remaps] if k_sub == 1 else remaps)
+        if p.reuse_count_bounds:
+            _COUNT_BOUNDS[hint_key] = (counts + np.ceil(counts * float(p.count_bound_slack[0])).astype(np.int64)
+                                       + int(p.count_bound_slack[1])).astype(np.int64)
     else:
         b, ws_i, total_dev = subs[0]
         labels = be.ccl_emit(b, W, ws_i)
