@@ -627,6 +627,20 @@ def test_adaptive_bits_tma_kernel(backend, rng, dt):
                 assert int((raw[..., -1] >> (shape[-1] % 32)).max()) == 0
 
 
+def test_morph_zero_iterations_copies_like_cv2(backend, rng):
+    import cv2
+
+    a = blobs(rng, (64, 80), U8)
+    k = cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3))
+    assert np.array_equal(cv2.erode(a, k, iterations=0), a) and np.array_equal(cv2.morphologyEx(a, cv2.MORPH_OPEN, k, iterations=0), a)
+    x = dev(backend, a)
+    for fn in (backend.erode, backend.dilate, backend.morph_open, backend.morph_close):
+        got = fn(x, "Rectangular", 3, 0)
+        assert got.data_ptr() != x.data_ptr()
+        assert_same(host(backend, got), a, "iterations = 0")
+    assert_same(host(backend, backend.morph_open_close(x, 5, 0)), a, "open+close, iterations = 0")
+
+
 @pytest.mark.parametrize("dt", [U8, U16])
 def test_adaptive_bits_with_global_threshold_mask(backend, rng, dt):
     """yam_adaptive_threshold_bits_mask: same bits as the plain call, and the global threshold mask

@@ -322,6 +322,8 @@ class Backend:
     def morph(self, img, op: int, kernel_shape: str = "Rectangular", kernel_size: int = 3, iterations: int = 1):
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        if int(iterations) == 0:      # cv2.erode / dilate / morphologyEx with iterations = 0 copy the input
+            return img.clone()
         n, h, w = self._nhw(img)
         out = torch.empty_like(img)
         self._call("yam_morph", self._p(img), self._p(out), n, h, w, _dtype_code(img), int(op),
@@ -343,6 +345,8 @@ class Backend:
     def morph_open_close(self, img, kernel_size: int = 5, iterations: int = 1):
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8, torch.uint16))
+        if int(iterations) == 0:
+            return img.clone()
         n, h, w = self._nhw(img)
         out = torch.empty_like(img)
         self._call("yam_morph_open_close", self._p(img), self._p(out), n, h, w, _dtype_code(img),
@@ -699,6 +703,8 @@ class Backend:
         n, h, wpr = self._nhw(bits)
         if wpr != (int(width) + 31) // 32:
             raise ValueError("bits tensor does not match the image width")
+        if int(iterations) == 0:
+            return bits.clone()
         out = torch.empty_like(bits)
         self._call("yam_bits_morph", self._p(bits), self._p(out), n, h, int(width), int(op), int(kernel_size),
                    int(iterations))
