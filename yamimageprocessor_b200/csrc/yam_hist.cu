@@ -1661,7 +1661,12 @@ int clahe_luts16(yam_ctx* ctx, const uint16_t* s_ptr, const ClaheGeom& g, int64_
         YAM_CUDA(cudaFuncSetAttribute(clahe_hist16_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem16));
         if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
     }
-    if (total_tiles * 2 <= slots && area >= (4ll << 20)) {
+    // (YAM_CLAHE_PARTS_MIN_AREA: experiment knob, pixels per tile from which tiles are split over several CTAs)
+    static const long long parts_min_area = [] {
+        const char* e = getenv("YAM_CLAHE_PARTS_MIN_AREA");
+        return e ? atoll(e) : (4ll << 20);
+    }();
+    if (total_tiles * 2 <= slots && area >= parts_min_area) {
         // few huge tiles: split every tile over several CTAs
         int64_t parts = (2 * (int64_t)slots + total_tiles - 1) / total_tiles;
         if (parts > g.th) parts = g.th;
