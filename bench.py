@@ -291,7 +291,7 @@ def build_gpu_workload(workload: str, cfg, be, frames_np):
             bits = be.adaptive_threshold_bits(inp, 11, 2)
             bits2 = be.bits_morph(bits, wd, 4, 5, 1)
             return [
-                ("adaptive_threshold_bits_u16_b11 (sep_f32_tiled -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(inp, 11, 2)),
+                ("adaptive_threshold_bits_u16_b11 (adaptive_bits_tma_kernel -> packed bits)", 2.125, lambda: be.adaptive_threshold_bits(inp, 11, 2)),
                 ("bits_morph open+close 5x5 (bit_morph_reg_kernel)", 0.25, lambda: be.bits_morph(bits, wd, 4, 5, 1)),
                 ("ccl_label_bits (scan, tile, border, rank, final_warp)", 4.125, lambda: be.ccl_label_bits(bits2, wd)),
             ]
@@ -611,7 +611,7 @@ def run_gpu_mosaic(args):
         return lab
 
     op_rows = [
-        ("gaussian_fixed_u16_k11 (sep_fixed_tiled)", 4.0, measure(lambda: be.gaussian(g_core, p.gauss_ksize, 0.0))),
+        ("gaussian_fixed_u16_k11 (gauss16_tma_kernel)", 4.0, measure(lambda: be.gaussian(g_core, p.gauss_ksize, 0.0))),
         ("clahe_u16 (tile LUTs + apply)", 6.0, measure(lambda: be.clahe_apply(
             g_core, be.clahe_luts(g_core, p.clip_limit, (p.tile_grid[0], p.tile_grid[1] // world)), (tw, th), 0))),
         ("otsu_u16 (histogram + certified scan)", 2.0, measure(otsu_op)),
