@@ -14,8 +14,12 @@ g = be.gaussian(x, 11, 0.0)
 luts = be.clahe_luts(g, 2.0, (8, 1))
 c = be.clahe_apply(g, luts, (W // 8, rows), 0)
 hist = be.histogram(c)
-m = be.threshold(c, 30000.0, 255)
-bits = be.adaptive_threshold_bits(c, 11, 2)
+t_dev = be.otsu_from_histogram_device(hist)                       # certified scan (+ early-exit chain / sigma kernels)
+if os.environ.get("FUSED_MASK", "1") == "1":
+    bits, m = be.adaptive_threshold_bits(c, 11, 2, mask_thresh=t_dev, maxval=255)   # final schedule: the Otsu mask rides along
+else:
+    m = be.threshold_frames(c, t_dev, 255)
+    bits = be.adaptive_threshold_bits(c, 11, 2)
 bits2 = be.bits_morph(bits, W, 4, 5, 1)
 # the labeller indexes pixels with 32 bits: strips of 2^31 px or more go through in sub-strips (as host/mosaic.py does)
 sub = rows
