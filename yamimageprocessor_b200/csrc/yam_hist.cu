@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
     const int span = m.last + 1 - m.first;
     const int tiles = (span + kOtsuTile - 1) / kOtsuTile;
     double q1 = 0.0, mu1 = 0.0, qprev = 0.0;
+    bool plateau = false;
     // prologue: q1 chain over tile 0
     {
         const int cnt = min(kOtsuTile, span);
@@ -359,13 +360,22 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
         if (lane == 0) {
             // blocks of 4 bins with the operands preloaded: shared-memory latency stays off the chains
             auto mu_step = [&](int k, double q, double r, double ip) {
+                // Runs of EMPTY bins (sparse histograms: 12-bit data, small frames): q1 does not move and mu1
+                // goes through x -> fl(fl(x q1) / q1); once an empty bin leaves mu1 unchanged, so does every
+                // following empty bin: copy instead of five dependent fp64 operations per bin.
+                if (plateau && ip == 0.0 && q == qprev) {
+                    s_m[k] = mu1;
+                    return;
+                }
                 // mu1 = (mu1 * q1_prev + i p_i) / q1_i with the corrected quotient
                 const double t = __dmul_rn(mu1, qprev);
                 const double nsum = __dadd_rn(t, ip);
                 const double qq = __dmul_rn(nsum, r);
                 const double e = __fma_rn(-qq, q, nsum);
                 const double quo = __fma_rn(e, r, qq);
-                mu1 = r == 0.0 ? t : quo;  // skipped bin: the reference multiplied by q1 before `continue`
+                const double nm = r == 0.0 ? t : quo;  // skipped bin: the reference multiplied by q1 before `continue`
+                plateau = r != 0.0 && ip == 0.0 && q == qprev && nm == mu1;
+                mu1 = nm;
                 s_m[k] = mu1;
                 qprev = q;
             };
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    q1 = __dadd_rn(q1, pn[j]);   // q1 chain, one tile ahead
+                    if (pn[j] != 0.0) q1 = __dadd_rn(q1, pn[j]);   // q1 chain, one tile ahead (x + 0 = x: no dependent add)
                     s_qn[k + j] = q1;
                     mu_step(k + j, q[j], r[j], ip[j]);
                 }
