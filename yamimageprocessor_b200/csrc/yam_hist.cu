@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
                 // Runs of EMPTY bins (sparse histograms: 12-bit data, small frames): q1 does not move and mu1
                 // goes through x -> fl(fl(x q1) / q1); once an empty bin leaves mu1 unchanged, so does every
                 // following empty bin: copy instead of five dependent fp64 operations per bin.
-                if (plateau && ip == 0.0 && q == qprev) {
+                // (bit-pattern compares: integer ALU latency instead of the fp64 pipe's; all values are >= +0)
+                const bool empty_bin = __double_as_longlong(ip) == 0ll && __double_as_longlong(q) == __double_as_longlong(qprev);
+                if (plateau && empty_bin) {
                     s_m[k] = mu1;
                     return;
                 }
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
                 const double e = __fma_rn(-qq, q, nsum);
                 const double quo = __fma_rn(e, r, qq);
                 const double nm = r == 0.0 ? t : quo;  // skipped bin: the reference multiplied by q1 before `continue`
-                plateau = r != 0.0 && ip == 0.0 && q == qprev && nm == mu1;
+                plateau = empty_bin && __double_as_longlong(r) != 0ll && __double_as_longlong(nm) == __double_as_longlong(mu1);
                 mu1 = nm;
                 s_m[k] = mu1;
                 qprev = q;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(32) otsu_chain_kernel(const unsigned long long
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (pn[j] != 0.0) q1 = __dadd_rn(q1, pn[j]);   // q1 chain, one tile ahead (x + 0 = x: no dependent add)
+                    if (__double_as_longlong(pn[j]) != 0ll) q1 = __dadd_rn(q1, pn[j]);   // q1 chain, one tile ahead (x + 0 = x: no dependent add)
                     s_qn[k + j] = q1;
                     mu_step(k + j, q[j], r[j], ip[j]);
                 }
