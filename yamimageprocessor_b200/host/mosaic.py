@@ -248,6 +248,19 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     halo_seg = p.block_size // 2 + 4 * (p.morph_ksize // 2)   # adaptive + erode,dilate,dilate,erode
     a0, a1 = max(0, c0 - halo_seg), min(H, c1 + halo_seg)      # rows of CLAHE output needed
     r0, r1 = max(0, a0 - hg), min(H, a1 + hg)                  # rows of input needed
+    # The labeller indexes pixels with 32 bits, so a strip of 2^31 pixels or more (65536^2 on one or two
+    # GPUs) is resolved as `k_sub` equal sub-strips that the cross-strip merge below stitches exactly like
+    # strips of different ranks.
+    rows_core = c1 - c0
+    k_sub = max(1, -(-(rows_core * W) // int(p.ccl_max_px)))
+    while rows_core % k_sub:
+        k_sub += 1
+    sub_rows = rows_core // k_sub
+    # Learnt bounds of the component counts (see the merge below) are read HERE, before any collective: every
+    # strip of this step -- other processes, or the lock-step threads of an emulated run, which share the table --
+    # then sizes its tables from the same previous step, whichever strip finishes first and updates the table.
+    hint_key = (H, W, world, k_sub, p.block_size, p.morph_ksize)
+    bounds = _COUNT_BOUNDS.get(hint_key) if p.reuse_count_bounds else None
 
     # rows are streamed from the (memmap) source through a pinned ring, gather overlapping the DMA
     import os
@@ -293,14 +306,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
     bits = be.bits_morph(raw_bits, W, 4, p.morph_ksize, 1)
     bits_core = bits[c0 - a0: c1 - a0]
     # labelling in two steps: resolve now, write the label image once the global numbering is known.
-    # The labeller indexes pixels with 32 bits, so a strip of 2^31 pixels or more (65536^2 on one or two
-    # GPUs) is resolved as `k_sub` equal sub-strips that the cross-strip merge below stitches exactly like
-    # strips of different ranks.
-    rows_core = c1 - c0
-    k_sub = max(1, -(-(rows_core * W) // int(p.ccl_max_px)))
-    while rows_core % k_sub:
-        k_sub += 1
-    sub_rows = rows_core // k_sub
     subs = []
     for i in range(k_sub):
         b = bits_core[i * sub_rows:(i + 1) * sub_rows]
@@ -329,8 +334,6 @@ def run_strip(be: Backend, source, rank: int = 0, world: int = 1, params: Option
         # shape (time series of mosaics, the bench's steps) sizes them from the previous run's counts plus
         # head room and leaves the real counts on the device (yam_merge_strips_remap_bounded): no host wait in
         # the middle of the pipeline.  Every rank derives the same bounds from the same all-gathered counts.
-        hint_key = (H, W, world, k_sub, p.block_size, p.morph_ksize)
-        bounds = _COUNT_BOUNDS.get(hint_key) if p.reuse_count_bounds else None
         overflow_dev = None
 
         def emit_all(remaps):
