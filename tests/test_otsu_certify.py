@@ -96,3 +96,22 @@ def test_certificate_edge_cases(chain_t):
     eps_front = z.copy(); eps_front[10] = 2; eps_front[20000] = (1 << 24) - 4; eps_front[40000] = 2
     ok, t, _, kmax = certify(eps_front)                                      # q1 == FLT_EPSILON exactly at bin 10
     assert (ok and t == chain_t(eps_front)) or chain_t(eps_front) <= kmax
+
+
+def test_equalised_images_have_comb_histograms_and_fall_back(chain_t):
+    """A pure LUT-transformed image (equalizeHist, single-tile CLAHE) has a comb histogram: empty bins tie exactly,
+    so the certificate must refuse -- and the bin where it lets the exact chain stop must still cover the answer."""
+    rng = np.random.default_rng(3)
+    v = np.clip(rng.normal(9000, 1200, 1 << 20), 0, 65535).astype(np.int64)
+    v[: 1 << 17] = np.clip(rng.normal(30000, 2500, 1 << 17), 0, 65535).astype(np.int64)
+    h = np.bincount(v, minlength=65536)
+    lut = np.round(np.cumsum(h) * (65535.0 / h.sum())).astype(np.int64)          # equalisation LUT: steep where counts are dense
+    comb = np.bincount(lut[v], minlength=65536)
+    assert (comb == 0).sum() > 50000                                             # mostly empty bins
+    ok, t, _, kmax = certify(comb)
+    want = chain_t(comb)
+    assert want == O.otsu_from_hist(comb)
+    assert (ok and t == want) or (not ok and want <= kmax < 65535)
+    twelve = np.bincount((v >> 4) << 4, minlength=65536)                         # 12-bit data in a 16-bit container
+    ok, t, _, kmax = certify(twelve)
+    assert not ok and chain_t(twelve) <= kmax
