@@ -1,0 +1,43 @@
+"""bench.py contract on a box without a GPU: the reference arm prints one JSON line with the agreed keys (it times
+the reference's CPU path -- the unmodified reference when /root/reference is importable, else the restated call
+sites), and the GPU arm refuses to run instead of falling back to the CPU."""
+from __future__ import annotations
+
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _run(*args, timeout=600):
+    return subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_reference_arm_line():
+    r = _run("--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "megapixels/s per pipeline" and d["unit"] == "megapixels/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "u16" and d["data"] == "synthetic"
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == pytest.approx(d["value"]) and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] == pytest.approx(d["value"]) and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_gpu_arm_has_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the GPU arm runs")
+    r = _run("--workload", "c1", "--steps", "1", "--warmup", "1", timeout=300)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout) or "BackendUnavailable" in (r.stderr + r.stdout)
