@@ -294,6 +294,23 @@ int yam_watershed_combine(yam_ctx* ctx, const int32_t* labels, const uint8_t* su
                           int32_t* markers, int64_t count);
 int yam_region_moments(yam_ctx* ctx, const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, int64_t* moments_dev);
 
+/* ---- perimeter and solidity of labelled regions (core/extraction.py:80,83: prop.perimeter, prop.solidity;
+ * skimage.measure.regionprops) ----------------------------------------------------------------------------
+ * yam_region_perimeter: skimage.measure.perimeter(region image, neighborhood=4) decomposed into exact
+ *   integer counts: counts_dev[n_labels][3] (int64) = border pixels of label i+1 whose class
+ *   v = 1 + 2 * (border 4-neighbours of the same label) + 10 * (border diagonal neighbours) weighs
+ *   1 ({5,7,15,17,25,27}), sqrt 2 ({21,33}) and (1 + sqrt 2) / 2 ({13,23}); a border pixel has a
+ *   4-neighbour outside its region (the image edge counts as outside).  perimeter = the weighted sum.
+ * yam_region_convex_area: RegionProperties.area_convex = pixels whose centre lies in the closed convex
+ *   hull of the edge midpoints of the region's pixels (skimage.morphology.convex_hull_image with
+ *   offset_coordinates=True, include_borders=True), exact integer arithmetic; convex_area_dev[n_labels]
+ *   (int64), 0 for labels without pixels.  props_dev = the table yam_region_props wrote for the SAME
+ *   label image (area and bounding rows are read from it).  solidity = area / area_convex.
+ *   Synchronises the stream once (the per-region row tables are sized on the device). */
+int yam_region_perimeter(yam_ctx* ctx, const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, int64_t* counts_dev);
+int yam_region_convex_area(yam_ctx* ctx, const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, const int64_t* props_dev,
+                           int64_t* convex_area_dev);
+
 /* Order-independent 64-bit content checksum: ADDS to *sum_dev (device, caller zeroes it) the sum over
  * i < count of mix64((index_base + i) * 0x9E3779B97F4A7C15 + value_i) mod 2^64 (mix64 = splitmix64's
  * finalizer; values zero-extended from U8 | U16 | I32 bit patterns).  A row strip passes the linear

@@ -580,6 +580,32 @@ class Backend:
             self._call("yam_region_moments", self._p(labels), int(labels.shape[0]), int(labels.shape[1]), int(n_labels), self._p(out))
         return out
 
+    def region_perimeter_counts(self, labels, n_labels: int):
+        """int64 [n_labels, 3] on device: border pixels per label in the three weight classes of
+        skimage.measure.perimeter(neighborhood=4) (1, sqrt 2, (1 + sqrt 2) / 2); see ``contour_columns``."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(2,), dtypes=(torch.int32,), name="labels")
+        out = torch.zeros((int(n_labels), 3), dtype=torch.int64, device=self.device)
+        if n_labels > 0:
+            self._call("yam_region_perimeter", self._p(labels), int(labels.shape[0]), int(labels.shape[1]), int(n_labels), self._p(out))
+        return out
+
+    def region_convex_area(self, labels, n_labels: int, props=None):
+        """int64 [n_labels] on device: skimage's ``area_convex`` per label (pixels of the convex hull image).
+        ``props`` = the ``region_props`` table of the same label image (computed here when omitted)."""
+        torch = _torch()
+        labels = self._check(labels, ndim=(2,), dtypes=(torch.int32,), name="labels")
+        if props is None:
+            props = self.region_props(labels, None, int(n_labels))
+        if not isinstance(props, torch.Tensor) or props.device != self.device or props.dtype != torch.int64 \
+                or tuple(props.shape) != (int(n_labels), PROPS_STRIDE) or not props.is_contiguous():
+            raise TypeError("region_convex_area: props must be the contiguous int64 [n_labels, 8] table of region_props on this device")
+        out = torch.zeros((int(n_labels),), dtype=torch.int64, device=self.device)
+        if n_labels > 0:
+            self._call("yam_region_convex_area", self._p(labels), int(labels.shape[0]), int(labels.shape[1]), int(n_labels),
+                       self._p(props), self._p(out))
+        return out
+
     def checksum64(self, t, index_base: int = 0, accumulate=None):
         """Order-independent content checksum (yam_checksum64) of a uint8 / uint16 / int32 CUDA tensor;
         returns an int64 tensor [1] (bit pattern of the uint64 sum), adding into ``accumulate`` if given."""
@@ -885,8 +911,8 @@ def shape_columns(props: np.ndarray, moments: np.ndarray) -> Dict[str, np.ndarra
     mu[p,q] = sum (r - rbar)^p (c - cbar)^q (skimage: [[mu02, -mu11], [-mu11, mu20]] / mu00), its
     eigenvalues l1 >= l2, ``eccentricity`` = sqrt(1 - l2 / l1) and ``orientation`` =
     0.5 * atan2(-2 b, c - a) with (a, b, b, c) the tensor (pi/4 conventions when a == c).  float64 on
-    the host from exact integer sums.  (``perimeter`` and ``solidity`` need contour / hull geometry
-    and are not derived here.)"""
+    the host from exact integer sums.  (``perimeter`` and ``solidity`` need contour / hull geometry:
+    ``contour_columns``.)"""
     area = props[:, 0].astype(np.float64)
     safe = np.maximum(area, 1.0)
     sr, sc = props[:, 1].astype(np.float64), props[:, 2].astype(np.float64)
@@ -905,4 +931,15 @@ def shape_columns(props: np.ndarray, moments: np.ndarray) -> Dict[str, np.ndarra
             "inertia_tensor_eigvals": np.stack([l1, l2], axis=1)}
 
 
-__all__ = ["Backend", "get_backend", "props_table", "shape_columns", "shape_code", "BackendUnavailable", "YamError"]
+def contour_columns(props: np.ndarray, perimeter_counts: np.ndarray, convex_area: np.ndarray) -> Dict[str, np.ndarray]:
+    """``perimeter`` and ``solidity`` (core/extraction.py:80,83) from the exact integer tables of
+    ``yam_region_perimeter`` / ``yam_region_convex_area``: perimeter = n1 + n2 * sqrt 2 + n3 * (1 + sqrt 2) / 2
+    (skimage.measure.perimeter's class weights), solidity = area / area_convex; float64 on the host."""
+    c = perimeter_counts.astype(np.float64)
+    perimeter = c[:, 0] + c[:, 1] * np.sqrt(2.0) + c[:, 2] * ((1.0 + np.sqrt(2.0)) / 2.0)
+    area = props[:, 0].astype(np.float64)
+    cva = convex_area.astype(np.int64)
+    return {"perimeter": perimeter, "area_convex": cva.copy(), "solidity": area / np.maximum(cva, 1).astype(np.float64)}
+
+
+__all__ = ["Backend", "get_backend", "props_table", "shape_columns", "contour_columns", "shape_code", "BackendUnavailable", "YamError"]

@@ -221,14 +221,18 @@ DEVICE_STEPS: Dict[str, Callable] = {
 def region_table(be: Backend, labels, intensity=None, n_labels=None) -> Dict[str, np.ndarray]:
     """Per-region table for a single labelled frame, columns in skimage semantics
     (core/extraction.py:70-87: region_index = label, centroid = (row, col)); bbox is half-open."""
-    from ..backend import props_table, shape_columns
+    from ..backend import contour_columns, props_table, shape_columns
 
     if n_labels is None:
         n_labels = int(labels.max().item()) if labels.numel() else 0
-    props = be.to_host(be.region_props(labels, intensity, n_labels))
+    props_dev = be.region_props(labels, intensity, n_labels)
+    props = be.to_host(props_dev)
     table = props_table(props)
     # extent / eccentricity / orientation (core/extraction.py:81-85) from exact second-order sums
     table.update(shape_columns(props, be.to_host(be.region_moments(labels, n_labels))))
+    # perimeter / solidity (core/extraction.py:80,83) from exact border-class counts and hull pixel counts
+    table.update(contour_columns(props, be.to_host(be.region_perimeter_counts(labels, n_labels)),
+                                 be.to_host(be.region_convex_area(labels, n_labels, props_dev))))
     table["region_index"] = np.arange(1, n_labels + 1, dtype=np.int64)
     table["centroid"] = np.stack([table["centroid_row"], table["centroid_col"]], axis=1) if n_labels else np.zeros((0, 2))
     if intensity is None:

@@ -230,8 +230,10 @@ def register_module(app_core) -> None:
 
 
 def region_properties_data(image: np.ndarray) -> Dict[str, np.ndarray]:
-    """GPU counterpart of core/extraction.py:70-87 for the columns on the hot path:
-    region_index, area, centroid (row, col), bbox (half-open) and mean_intensity (extension)."""
+    """GPU counterpart of core/extraction.py:70-87: every column of the reference's table -- region_index,
+    area, perimeter, centroid (row, col), eccentricity, solidity, extent, orientation -- plus bbox
+    (half-open), area_convex and mean_intensity (extensions).  All sums, border-class counts and hull
+    pixel counts are exact integers from the device; the float64 columns are formed from them on the host."""
     from ..host.steps import region_table
 
     ex = _executor()
