@@ -294,6 +294,15 @@ int yam_watershed_combine(yam_ctx* ctx, const int32_t* labels, const uint8_t* su
                           int32_t* markers, int64_t count);
 int yam_region_moments(yam_ctx* ctx, const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, int64_t* moments_dev);
 
+/* ---- histogram equalisation of colour images (Preprocessor.histogram_equalization, core/preprocessing.py:74-79:
+ * cvtColor(BGR2YCrCb) -> equalizeHist(Y) -> cvtColor(YCrCb2BGR), uint8) -------------------------------------
+ * yam_bgr_luma_ycrcb: y[i] = the Y channel cv2.cvtColor(COLOR_BGR2YCrCb) gives pixel i of an interleaved
+ *   BGR uint8 image (px pixels, any number of frames back to back); feed it to yam_equalize_hist.
+ * yam_bgr_replace_luma_ycrcb: dst = cvtColor(YCrCb2BGR) of (y_new, Cr, Cb) with Cr / Cb of the source pixel
+ *   as BGR2YCrCb stores them (saturated uint8); dst may alias bgr.  cv2's 14-bit fixed point, bit-exact. */
+int yam_bgr_luma_ycrcb(yam_ctx* ctx, const uint8_t* bgr, uint8_t* y, int64_t px);
+int yam_bgr_replace_luma_ycrcb(yam_ctx* ctx, const uint8_t* bgr, const uint8_t* y_new, uint8_t* dst, int64_t px);
+
 /* ---- perimeter and solidity of labelled regions (core/extraction.py:80,83: prop.perimeter, prop.solidity;
  * skimage.measure.regionprops) ----------------------------------------------------------------------------
  * yam_region_perimeter: skimage.measure.perimeter(region image, neighborhood=4) decomposed into exact

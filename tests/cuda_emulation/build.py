@@ -1,0 +1,31 @@
+"""Compile the anonymous namespace of a .cu file (its kernels and device helpers) for the HOST, on top of
+emu_prelude.h, together with a driver that launches them: logic checks of CUDA source without a GPU.
+Test infrastructure only."""
+from __future__ import annotations
+
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+EMU = Path(__file__).resolve().parent
+
+
+def kernel_namespace(cu: Path) -> str:
+    text = cu.read_text()
+    start = text.index("namespace {") + len("namespace {")
+    end = text.index("}  // namespace")
+    return text[start:end]
+
+
+def build_emulator(cu: Path, driver: str, workdir: Path, name: str) -> Path:
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    src = workdir / f"{name}.cc"
+    src.write_text('#include "emu_prelude.h"\n' + kernel_namespace(cu) + "\n" + (EMU / driver).read_text())
+    exe = workdir / name
+    proc = subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-Wno-unknown-pragmas", f"-I{EMU}", str(src), "-o", str(exe)],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    return exe

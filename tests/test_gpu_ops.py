@@ -383,6 +383,25 @@ def test_equalize_hist(backend, rng):
         assert_same(got, O.equalize_hist(img), "equalizeHist")
 
 
+def test_equalize_hist_colour(backend, rng):
+    """core/preprocessing.py:77-79 (Y of YCrCb): against the oracle, the reference's own outputs, BGRA input"""
+    from pathlib import Path
+
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "reference_outputs_color.npz")
+    for name in (k[3:] for k in gold.files if k.startswith("in_")):
+        got = host(backend, backend.equalize_hist_bgr(dev(backend, gold[f"in_{name}"])))
+        assert_same(got, gold[f"equalized_{name}"], f"colour equalizeHist {name}")
+    for shape in ((64, 80, 3), (129, 257, 3), (5, 7, 3), (1, 1, 3)):
+        img = rnd(rng, shape, U8)
+        assert_same(host(backend, backend.equalize_hist_bgr(dev(backend, img))), O.equalize_hist_bgr(img), f"colour equalizeHist {shape}")
+    from yamimageprocessor_b200.host.steps import DEVICE_STEPS
+
+    img = gold["in_smooth"]
+    assert_same(host(backend, DEVICE_STEPS["HistogramEqualization"](backend, dev(backend, img), {})), gold["equalized_smooth"], "step, colour")
+    bgra = rnd(rng, (33, 47, 4), U8)
+    assert_same(host(backend, backend.equalize_hist_bgr(dev(backend, bgra))), O.equalize_hist_bgr(bgra[..., :3]), "BGRA")
+
+
 @pytest.mark.parametrize("dt", [U8, U16])
 @pytest.mark.parametrize("clip,grid", [(2.0, (8, 8)), (4.0, (4, 6)), (0.5, (8, 8)), (40.0, (3, 5)), (0.0, (8, 8))])
 def test_clahe(backend, rng, dt, clip, grid):

@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import math
 import re
-import shutil
 import subprocess
 from pathlib import Path
 
@@ -89,20 +88,10 @@ def test_kernel_class_table_matches_model():
 
 @pytest.fixture(scope="module")
 def emulator(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    text = CU.read_text()
-    start = text.index("namespace {")
-    end = text.index("}  // namespace")
-    body = text[start:end + len("}  // namespace")].replace("namespace {", "", 1).rsplit("}  // namespace", 1)[0]
+    from cuda_emulation.build import build_emulator
+
     work = tmp_path_factory.mktemp("regiongeom_emu")
-    src = work / "emu.cc"
-    src.write_text('#include "emu_prelude.h"\n' + body + "\n" + (EMU / "regiongeom_driver.cc").read_text())
-    exe = work / "regiongeom_emu"
-    proc = subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-Wno-unknown-pragmas", f"-I{EMU}", str(src), "-o", str(exe)],
-                          capture_output=True, text=True)
-    assert proc.returncode == 0, proc.stderr[-3000:]
-    return exe, work
+    return build_emulator(CU, "regiongeom_driver.cc", work, "regiongeom_emu"), work
 
 
 def run_emulator(emulator, lab, n, props):

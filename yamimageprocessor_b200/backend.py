@@ -421,6 +421,24 @@ class Backend:
         self._call("yam_equalize_hist", self._p(img), self._p(out), n, h, w)
         return out
 
+    def equalize_hist_bgr(self, img):
+        """Preprocessor.histogram_equalization on a colour image (core/preprocessing.py:77-79): equalise the Y
+        plane of cv2's YCrCb, convert back.  (h, w, 3|4) uint8 BGR[A] -> (h, w, 3) uint8 (cv2's
+        BGR2YCrCb ignores alpha and the reference converts back to three channels)."""
+        torch = _torch()
+        img = self._check(img, ndim=(3,), dtypes=(torch.uint8,))
+        if img.shape[-1] not in (3, 4):
+            raise ValueError(f"equalize_hist_bgr expects (h, w, 3|4), got {tuple(img.shape)}")
+        if img.shape[-1] == 4:
+            img = img[..., :3].contiguous()
+        h, w = int(img.shape[0]), int(img.shape[1])
+        y = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+        self._call("yam_bgr_luma_ycrcb", self._p(img), self._p(y), h * w)
+        y_eq = self.equalize_hist(y)
+        out = torch.empty_like(img)
+        self._call("yam_bgr_replace_luma_ycrcb", self._p(img), self._p(y_eq), self._p(out), h * w)
+        return out
+
     def clahe(self, img, clip_limit: float = 2.0, tile_grid: Tuple[int, int] = (8, 8)):
         torch = _torch()
         img = self._check(img, dtypes=(torch.uint8, torch.uint16))

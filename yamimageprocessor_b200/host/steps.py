@@ -103,7 +103,9 @@ def box_filter(be: Backend, t, p):
 
 
 def histogram_equalization(be: Backend, t, p):
-    return be.equalize_hist(_plane_only(t, "HistogramEqualization"))
+    if _is_colour(t):   # core/preprocessing.py:77-79: equalise Y of YCrCb, convert back
+        return be.equalize_hist_bgr(t)
+    return be.equalize_hist(t)
 
 
 def global_threshold(be: Backend, t, p):
