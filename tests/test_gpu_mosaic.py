@@ -108,6 +108,54 @@ def test_dense_chain_matches_oracle(backend):
     assert n == olab[0] and np.array_equal(lab, olab[1])
 
 
+M64 = (1 << 64) - 1
+
+
+def _u64(t):
+    return int(t.item()) & M64
+
+
+def test_checksum64_matches_oracle(backend, rng):
+    """yam_checksum64 (bench.py's `check` block) against its NumPy statement: every dtype, an index base, and
+    per-strip sums that add up to the checksum of the whole array."""
+    for dt, hi in ((np.uint8, 1 << 8), (np.uint16, 1 << 16), (np.int32, 1 << 31)):
+        a = rng.integers(0, hi, (37, 53)).astype(dt)
+        if dt == np.int32:
+            a[3, 5:9] = -1                      # bit patterns are zero-extended, not sign-extended
+        t = backend.to_device(a)
+        assert _u64(backend.checksum64(t)) == O.checksum64(a)
+        assert _u64(backend.checksum64(t, index_base=123456789012)) == O.checksum64(a, 123456789012)
+    a = rng.integers(0, 1 << 16, (64, 48)).astype(np.uint16)
+    acc = backend.checksum64(backend.to_device(a[:20]))
+    backend.checksum64(backend.to_device(a[20:]), index_base=20 * 48, accumulate=acc)
+    assert _u64(acc) == O.checksum64(a)
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_check_block_of_sharded_run_equals_dense_and_oracle(backend, world):
+    """bench.py's parity evidence at reduced size: the per-strip checksums of the label image and of the Otsu
+    mask (index base = first row x width) add up to the checksum of the dense single-strip run, which equals the
+    oracle's checksum of the oracle's own labels.  (tools/check_bench_check_block.py does the same for whole bench
+    lines against live cv2 on the CPU: profiles/r02_check_c4_*_vs_cv2.json.)"""
+    p = mosaic.MosaicParams()
+    frame = synth.nuclei(1024, 768, seed=17)
+    frame[:, 500:503] = 60000
+    W = frame.shape[1]
+    _, want_t, want_om, want_lab, want_n, _ = dense(backend, frame, p)
+    res = mosaic.run_emulated(backend, frame, world, p)
+    sums = [0, 0]
+    for r in res:
+        base = r.rows[0] * W
+        sums[0] = (sums[0] + _u64(backend.checksum64(r.labels, index_base=base))) & M64
+        sums[1] = (sums[1] + _u64(backend.checksum64(r.otsu_mask, index_base=base))) & M64
+    assert all(r.otsu_threshold == want_t and r.n_components == want_n for r in res)
+    assert sums[0] == O.checksum64(want_lab) == _u64(backend.checksum64(backend.to_device(want_lab)))
+    assert sums[1] == O.checksum64(want_om) == _u64(backend.checksum64(backend.to_device(want_om)))
+    oc = O.clahe(O.gaussian_fixed(frame, 11, 0.0), 2.0, (8, 8))
+    olab = O.ccl_label(O.morph_close(O.morph_open(O.adaptive_threshold(oc, 11, 2), "Rectangular", 5, 1), "Rectangular", 5, 1))[1]
+    assert sums[0] == O.checksum64(olab) and sums[1] == O.checksum64(O.otsu_threshold(oc, 255)[1])
+
+
 def test_strip_geometry_errors():
     with pytest.raises(ValueError):
         mosaic.strip_rows(1000, 8, 0, 3)
