@@ -41,3 +41,22 @@ def test_gpu_arm_has_no_cpu_fallback():
     r = _run("--workload", "c1", "--steps", "1", "--warmup", "1", timeout=300)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) or "BackendUnavailable" in (r.stderr + r.stdout)
+
+
+def test_committed_c4_lines_share_the_cv2_verified_check_block():
+    """The committed 65536^2 lines (1, 2, 4, 8 GPUs) carry one and the same `check` block, and it is the one the
+    reference's cv2 call sites produce over the same mosaic on the CPU (tools/check_bench_check_block.py)."""
+    import json
+    from pathlib import Path
+
+    prof = Path(__file__).resolve().parents[1] / "profiles"
+    cpu = json.loads((prof / "r02_check_c4_65536_vs_cv2.json").read_text())
+    assert cpu["equal"] is True and cpu["mosaic"] == [65536, 65536]
+    want = cpu["gpu bench line"]
+    cpu_side = next(v for k, v in cpu.items() if k.startswith("cpu (cv2"))
+    assert cpu_side == want
+    for n in (1, 2, 4, 8):
+        text = (prof / f"r02_bench_c4_n{n}.json").read_text()      # torchrun output: an NCCL banner may precede the line
+        line = json.loads(next(ln for ln in text.splitlines() if ln.startswith("{")))
+        assert line["n_gpus"] == n and line["config"]["mosaic"] == [65536, 65536]
+        assert {k: line["check"][k] for k in want} == want, f"N = {n}"
