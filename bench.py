@@ -450,6 +450,21 @@ class RowWindowRecord:
         pass
 
 
+def cv2_reference_check(size: int, check: dict):
+    """The `check` values the reference's cv2 call sites give for the same synthetic mosaic, computed on the CPU by
+    tools/check_bench_check_block.py and committed under profiles/ (65536^2 and 16384^2), next to a verdict on this
+    run's values.  None when no committed result covers `size`; never raises (evidence only, not on the timed path)."""
+    try:
+        path = ROOT / "profiles" / f"r02_check_c4_{int(size)}_vs_cv2.json"
+        ref = json.loads(path.read_text())
+        cpu = next(v for k, v in ref.items() if k.startswith("cpu (cv2"))
+        lib = next(k for k in ref if k.startswith("cpu (cv2"))
+        return {"source": f"profiles/{path.name}: {lib} over the same mosaic (tools/check_bench_check_block.py)",
+                "values": cpu, "equal": all(check.get(k) == v for k, v in cpu.items())}
+    except Exception:  # noqa: BLE001 - a missing / unreadable file only drops the extra key
+        return None
+
+
 def _u64hex(v: int) -> str:
     return f"{int(v) & 0xFFFFFFFFFFFFFFFF:016x}"
 
@@ -564,6 +579,9 @@ def run_gpu_mosaic(args):
              "labels_checksum64": _u64hex(sums_host[0]), "otsu_mask_checksum64": _u64hex(sums_host[1]),
              "definition": "yam_checksum64 (include/yamb200.h): sum of mix64(linear index * golden + value) mod 2^64, "
                            "per-strip sums all-reduced; must be identical for N = 1, 2, 4, 8"}
+    reference_check = cv2_reference_check(size, check)
+    if reference_check is not None:
+        check["cv2_cpu_chain"] = reference_check
     n_components = int(res.n_components)
     del res
 

@@ -60,3 +60,21 @@ def test_committed_c4_lines_share_the_cv2_verified_check_block():
         line = json.loads(next(ln for ln in text.splitlines() if ln.startswith("{")))
         assert line["n_gpus"] == n and line["config"]["mosaic"] == [65536, 65536]
         assert {k: line["check"][k] for k in want} == want, f"N = {n}"
+
+
+def test_bench_check_block_cites_the_cv2_cpu_chain():
+    """bench.cv2_reference_check: the committed CPU / cv2 values are attached to a c4 line's `check` block with a
+    verdict; sizes without a committed result (or unreadable files) only drop the key."""
+    import json
+    from pathlib import Path
+
+    import bench
+
+    prof = Path(__file__).resolve().parents[1] / "profiles"
+    line = json.loads((prof / "r02_bench_c4_n1.json").read_text())
+    good = bench.cv2_reference_check(65536, line["check"])
+    assert good["equal"] is True and good["values"]["components"] == 6673681 and "r02_check_c4_65536_vs_cv2.json" in good["source"]
+    bad = dict(line["check"], components=1)
+    assert bench.cv2_reference_check(65536, bad)["equal"] is False
+    assert bench.cv2_reference_check(16384, json.loads((prof / "r02_bench_c4_16k_n1.json").read_text())["check"])["equal"] is True
+    assert bench.cv2_reference_check(4096, line["check"]) is None
