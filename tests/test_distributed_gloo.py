@@ -99,6 +99,14 @@ def _worker(rank: int, world: int, port: int, tmpdir: str):
         assert np.array_equal(comm.all_gather(pack).numpy(), np.stack([np.arange(9) * (r + 1) for r in range(world)]))
         h2 = torch.full((5,), rank + 1, dtype=torch.int64)
         assert comm.all_reduce(h2, "sum").tolist() == [sum(range(1, world + 1))] * 5
+        # --- bench.py's `check` block: per-strip content checksums (index base = first row x width) are added by
+        # an int64 all-reduce that wraps mod 2^64, and equal the checksum of the dense array
+        strip_sum = O.checksum64(mosaic[c0:c1], index_base=c0 * mosaic.shape[1])
+        as_i64 = strip_sum - (1 << 64) if strip_sum >= (1 << 63) else strip_sum
+        sums = torch.tensor([as_i64, (1 << 63) - 1 - rank], dtype=torch.int64)      # second entry: forces the wrap
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        assert int(sums[0].item()) & ((1 << 64) - 1) == O.checksum64(mosaic)
+        assert int(sums[1].item()) & ((1 << 64) - 1) == sum((1 << 63) - 1 - r for r in range(world)) & ((1 << 64) - 1)
         np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([t]))
     finally:
         dist.destroy_process_group()
