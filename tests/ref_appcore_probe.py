@@ -56,6 +56,31 @@ def main() -> None:
         chain[0].enabled, chain[1].enabled, chain[2].enabled = True, True, False
         final, records = cache.predict(sid, chain)
         out["cache"] = {"source_id": sid, "final": final, "signatures": [r.signature for r in records]}
+    # The GpuExecutor protocol through the reference's OWN manager (processing/pipeline_manager.py:448-454): every
+    # enabled requires_gpu step must reach execute(step, ndarray) under a name DEVICE_STEPS knows, in order, and the
+    # returned array must become the pipeline image.  No GPU in this container: the dispatch is recorded, the
+    # kernels themselves are covered by the -m gpu suite.
+    from yamimageprocessor_b200.host.executor import B200Executor
+
+    class RecordingExecutor(B200Executor):
+        def execute(self, step, image):
+            assert isinstance(image, np.ndarray) and self.supports(step.name)
+            self.calls.append(step.name)
+            return np.ascontiguousarray(image) + 1
+
+    chain_names = ["Grayscale", "NoiseReduction", "Otsu", "Opening", "ConnectedComponents"]
+    if all(n in steps for n in chain_names) and all(steps[n].execution.requires_gpu for n in chain_names):
+        pm2 = core.get_pipeline_manager()
+        for s in pm2.steps:
+            s.enabled = s.name in chain_names
+        ex = RecordingExecutor()
+        pm2.set_gpu_executor(ex)
+        src = np.zeros((6, 7), np.uint8)
+        res = pm2.apply(src)
+        clone_ex = pm2.clone()._gpu_executor if hasattr(pm2.clone(), "_gpu_executor") else None
+        out["executor"] = {"calls": ex.calls, "enabled_in_order": [s.name for s in pm2.steps if s.enabled],
+                           "result_sum": int(np.asarray(res).sum()), "input_untouched": bool((src == 0).all()),
+                           "clone_keeps_executor": clone_ex is ex}
     print("PROBE " + json.dumps(out))
 
 

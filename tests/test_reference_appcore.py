@@ -53,6 +53,17 @@ def test_real_appcore_resolves_every_hot_path_identifier_to_the_gpu_module():
     assert got["cache"]["signatures"] == meta["cache"]["signatures"] and got["cache"]["final"] == meta["cache"]["final"]
 
 
+def test_real_pipeline_manager_routes_gpu_steps_to_the_executor():
+    """The reference's own PipelineManager (built by its AppCore from this package's modules) hands every enabled
+    GPU-marked step to B200Executor.execute(step, ndarray), in order, and takes the returned array as the
+    pipeline image (processing/pipeline_manager.py:448-454); set_gpu_executor / clone keep the executor."""
+    got = _probe("b200_first")["executor"]
+    assert got["calls"] == got["enabled_in_order"]        # the manager's own step order
+    assert sorted(got["calls"]) == sorted(["Grayscale", "NoiseReduction", "Otsu", "Opening", "ConnectedComponents"])
+    assert got["result_sum"] == 5 * 6 * 7        # five steps, each +1 on a 6 x 7 zero image
+    assert got["input_untouched"] and got["clone_keeps_executor"]
+
+
 def test_real_appcore_duplicate_rule_is_why_the_order_matters():
     """core/app_core.py:762-771: the FIRST registration of an identifier wins, later ones are dropped
     with a warning.  With the reference package listed first its seven CPU modules shadow ours."""
